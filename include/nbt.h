@@ -1,0 +1,166 @@
+/*
+ * nbt.h — C ABI of the B200-native batched N-body TTV engine.
+ *
+ * This is the drop-in boundary for the reference's generate()/integrate()/analyze()
+ * path.  The reference (pearsonkyle/Nbody-AI) has no FFI of its own: its boundary is the
+ * Python function surface of nbody/simulation.py, below which it calls REBOUND through
+ * ctypes.  Each entry point below names the reference interface it replaces.
+ *
+ *   nbt_run            <- nbody/simulation.py:27-52   generate()   (setup, Jacobi add, move_to_com)
+ *                         nbody/simulation.py:131-160 integrate()  (sampling on linspace grid)
+ *                         nbody/simulation.py:163-177 transit_times() + TTV()
+ *                         nbody/simulation.py:179-231 analyze()    (means, O-C, maxavg, RV, periodograms)
+ *                         nbody/nested.py:44-47       get_ttv()    (ttvfast forward model)
+ *   nbt_lomb_scargle   <- nbody/tools.py:97-104       lomb_scargle() -> astropy autopower
+ *   nbt_chi2           <- nbody/nested.py:85-95       myloglike()  (chi^2 of the forward model)
+ *   nbt_plan_*         <- no reference analogue (the reference grows Python lists); they size
+ *                         the caller-owned CSR buffers the kernels write into.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  Every buffer is caller-owned.
+ *   - units day / AU / Msun, G = NBT_G (nbody/tools.py:18).
+ *   - all functions return 0 on success, <0 for an invalid argument, >0 for a CUDA error
+ *     (the cudaError_t value); nbt_last_error() gives the thread-local message.
+ *   - pointers in nbt_inputs / nbt_outputs are HOST pointers unless cfg.flags has
+ *     NBT_F_DEVICE_PTRS, in which case all of them are device pointers on cfg.device
+ *     and the call only enqueues work on `stream` (no copies, no synchronisation).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef NBT_H
+#define NBT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBT_ABI_VERSION 1
+#define NBT_G 0.00029591220828559104 /* day, AU, Msun — nbody/tools.py:18 */
+#define NBT_MAX_BODIES 9             /* star + 8 planets (solarsystem_nbody.py) */
+
+/* columns of the per-body parameter row (what the reference passes to rebound.add(**obj)) */
+enum { NBT_P_M = 0, NBT_P_P = 1, NBT_P_E = 2, NBT_P_INC = 3, NBT_P_OMEGA_NODE = 4,
+       NBT_P_OMEGA_PERI = 5, NBT_P_F = 6, NBT_NPAR = 7 };
+
+/* integrator scheme: symmetric compositions of the Wisdom-Holman (Jacobi) map */
+enum { NBT_SCHEME_WH2 = 0,   /* kick-drift-kick leapfrog */
+       NBT_SCHEME_Y4 = 1,    /* Yoshida 4th-order triple jump */
+       NBT_SCHEME_SABA4 = 2, /* Laskar-Robutel SBAB/SABA-class, 4 stages */
+       NBT_SCHEME_M64 = 3,   /* order (6,4) 4-stage composition */
+       NBT_SCHEME_COUNT = 4 };
+
+/* transit-time mode */
+enum { NBT_TT_GRID_LINEAR = 0, /* reference semantics: sign test + linear interpolation on the
+                                  output grid, nbody/simulation.py:163-170, tools.py:61-65 */
+       NBT_TT_REFINED = 1 };   /* Newton-refined root of x_p - x_s on the integrator's own step */
+
+/* cfg.flags */
+enum { NBT_F_MEANS = 1 << 0,       /* time means of Jacobi a, e, inc (analyze :216-217) */
+       NBT_F_MEAN_OMEGA = 1 << 1,  /* also the mean of omega */
+       NBT_F_RV = 1 << 2,          /* store RV signal [n_outputs-1][B] + rv_max */
+       NBT_F_ORBIT = 1 << 3,       /* store x[::4], z[::4] per planet */
+       NBT_F_SERIES = 1 << 4,      /* store the full sim_data series (generate() compatibility) */
+       NBT_F_LS_OC = 1 << 5,       /* O-C periodogram per planet */
+       NBT_F_LS_RV = 1 << 6,       /* RV periodogram per system (needs NBT_F_RV) */
+       NBT_F_PLANET1_ONLY = 1 << 7,/* ttvfast: transit products for planet 1 only (analyze :181-184) */
+       NBT_F_DEVICE_PTRS = 1 << 8  /* all buffers are device pointers; async on `stream` */
+};
+
+/* per-system status bits (the reference signals these only indirectly) */
+enum { NBT_S_NONFINITE = 1 << 0, NBT_S_UNBOUND = 1 << 1, NBT_S_KEPLER = 1 << 2,
+       NBT_S_TT_OVERFLOW = 1 << 3, NBT_S_FEW_TRANSITS = 1 << 4 };
+
+typedef struct nbt_config {
+    int32_t struct_size; /* = sizeof(nbt_config), ABI guard */
+    int32_t n_systems;   /* B */
+    int32_t n_bodies;    /* star + planets, 2..NBT_MAX_BODIES */
+    int32_t n_outputs;   /* Noutputs of np.linspace(0, Ndays, Noutputs) */
+    double n_days;       /* Ndays */
+    int32_t substeps;    /* composition steps per output interval; <=0: use inputs.substeps[] */
+    int32_t scheme;      /* NBT_SCHEME_* */
+    int32_t tt_mode;     /* NBT_TT_* */
+    int32_t flags;       /* NBT_F_* */
+    int32_t device;      /* CUDA device ordinal */
+    int32_t orbit_stride;/* 4 in the reference (analyze :227-228) */
+    double ls_oc_minfreq, ls_oc_maxfreq; /* 1/180, 1/2 (analyze :213) */
+    double ls_rv_minfreq, ls_rv_maxfreq; /* 1/365, 1/2 (tools.py:97) */
+    int32_t ls_samples_per_peak;         /* 10 (tools.py:104) */
+    int32_t reserved;
+} nbt_config;
+
+typedef struct nbt_inputs {
+    const double* params;      /* [B][n_bodies][NBT_NPAR] */
+    const int32_t* substeps;   /* [B] or NULL (then cfg.substeps applies to all) */
+    const int64_t* tt_offsets; /* [B*Np + 1] CSR capacity offsets into tt/ttv (nbt_plan_tt) */
+    const int64_t* ls_offsets; /* [B*Np + 1] CSR capacity offsets into ls_oc_power, or NULL */
+} nbt_inputs;
+
+typedef struct nbt_outputs {
+    /* transit products, CSR over (system, planet) */
+    double* tt;        /* mid-transit times [day] */
+    double* ttv;       /* O-C [day] */
+    int32_t* n_tt;     /* [B*Np] transits found (may exceed capacity -> NBT_S_TT_OVERFLOW) */
+    double* period;    /* [B*Np] OLS slope, or objects P when n_tt < 3 */
+    double* t0;        /* [B*Np] OLS intercept, or 0 */
+    double* ttv_max;   /* [B*Np] maxavg(ttv) [day] (tools.py:22) */
+    /* orbit means over all outputs (NBT_F_MEANS) */
+    double* mean_a;    /* [B*Np] */
+    double* mean_e;
+    double* mean_inc;
+    double* mean_omega;/* NBT_F_MEAN_OMEGA */
+    int32_t* status;   /* [B] NBT_S_* */
+    /* optional series, all time-major so that a warp's stores coalesce */
+    double* rv;        /* [n_outputs-1][B]   NBT_F_RV */
+    double* rv_max;    /* [B]                NBT_F_RV */
+    double* orbit_xz;  /* [ceil(n_outputs/stride)][B][Np][2]  NBT_F_ORBIT */
+    double* series;    /* [n_outputs][B][3 + 10*Np]  NBT_F_SERIES: star x,y,z then per planet
+                          x,y,z,P,a,e,inc,Omega,omega,M (simulation.py:13-25) */
+    /* periodograms */
+    double* ls_oc_power; /* CSR by ls_offsets     NBT_F_LS_OC */
+    int32_t* ls_oc_nfreq;/* [B*Np] */
+    double* ls_rv_power; /* [B][nbt_ls_nfreq(n_outputs-1 samples)]  NBT_F_LS_RV */
+} nbt_outputs;
+
+int nbt_abi_version(void);
+int nbt_device_count(void);
+const char* nbt_last_error(void);
+
+/* Number of frequencies of astropy's autofrequency grid for a series of n samples spanning
+ * `baseline` (= t.max - t.min): 1 + round((fmax - fmin) * spp * baseline).  tools.py:104. */
+int64_t nbt_ls_nfreq(double baseline, double minfreq, double maxfreq, int samples_per_peak);
+
+/* Fill tt_offsets[B*Np+1] with CSR capacities ceil(1.05*Ndays/P)+3 per planet (host helper). */
+int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets);
+/* Fill ls_offsets[B*Np+1] from tt_offsets (capacity of the O-C periodogram). */
+int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets);
+
+/* Recommended composition steps per output interval for each system (host helper). */
+int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* substeps);
+
+/* Number of system-steps (kick+drift stages) nbt_run will execute for this plan. */
+int64_t nbt_count_steps(const nbt_config* cfg, const int32_t* substeps);
+
+/* The hot path: set up, integrate, detect transits, fit ephemerides, reduce. */
+int nbt_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, void* cuda_stream);
+
+/* Generalised (floating-mean) Lomb-Scargle of `n_series` independent series.
+ * t, y: [n_series][n] (t == NULL -> t = 0..n-1), power: [n_series][n_freq],
+ * freq_k = f0 + k*df.  device_ptrs != 0: pointers are device memory. */
+int nbt_lomb_scargle(const double* t, const double* y, int64_t n_series, int64_t n,
+                     double f0, double df, int64_t n_freq, double* power,
+                     int device, int device_ptrs, void* cuda_stream);
+
+/* chi^2 of nested.py:85-95 for B forward models against one data vector:
+ * loglike[b] = -0.5 * sum_i ((y_i - (c1[b]*x_i + c0[b]) - ttv[b][x_i]) / yerr_i)^2,
+ * with the reference's penalty branch when epoch x_i is missing. */
+int nbt_chi2(const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt, int32_t n_systems,
+             int32_t n_planets, const double* c0, const double* c1, const double* x, const double* y,
+             const double* yerr, int32_t n_data, double* loglike, int device, int device_ptrs,
+             void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBT_H */

@@ -1,0 +1,716 @@
+/*
+ * nbt_oracle.c — CPU ORACLE.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C restatement of the reference's generate()/integrate()/analyze() path
+ * (pearsonkyle/Nbody-AI).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product (nbody_ai_b200 + libnbt.so) never
+ * does and has no CPU fallback.
+ *
+ * PARITY PINNING.  The arithmetic of the reference path lives in third-party packages that
+ * are neither vendored nor pinned nor installable here: `rebound` (nbody/simulation.py:8,
+ * a 3.2x release is implied by sim.ri_tes at :35-38) and `astropy` LombScargle
+ * (nbody/tools.py:4).  The reference ships no executable test.  This oracle is therefore
+ * pinned (tests/test_oracle.py) against
+ *   G1  the numeric table + periodogram peaks of figures/report_simulation.png (2-3 digits),
+ *   G2  the 30 transit times of sim_data.txt (noise-limited, sigma 0.5 min),
+ *   an independent scipy DOP853 (rtol 1e-13) integration of the same initial conditions,
+ *   scipy.signal.lombscargle(floating_mean=True, normalize=True) for the periodogram.
+ * In the strict sense (no runnable reference, no bit-level vectors) parity is UNPINNED beyond
+ * those artefacts; DESIGN.md says the same.
+ *
+ * What is restated, in reference order:
+ *   nbody/simulation.py:27-52    generate(): units day/AU/Msun, rebound.add(**obj) per body
+ *                                (Jacobi primaries, a from P), move_to_com()
+ *   nbody/simulation.py:131-160  integrate(): default REBOUND integrator (IAS15, adaptive
+ *                                Gauss-Radau 15, Rein & Spiegel 2015) landing on
+ *                                np.linspace(0, Ndays, Noutputs); star x,y,z; planet x,y,z and
+ *                                Jacobi osculating P,a,e,inc,Omega,omega,M
+ *   nbody/simulation.py:163-170  transit_times();  nbody/tools.py:61-65 find_zero()
+ *   nbody/simulation.py:172-177  TTV() (2-parameter least squares)
+ *   nbody/simulation.py:179-231  analyze()
+ *   nbody/tools.py:22            maxavg();  nbody/tools.py:97-104 lomb_scargle()
+ *   nbody/nested.py:85-95        myloglike()
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include <unistd.h>
+
+#include "../include/nbt.h"
+
+#define MAXN NBT_MAX_BODIES
+#define PI 3.14159265358979323846264338327950288
+
+/* ------------------------------------------------------------------------------------------ */
+/* rebound.Simulation.add(m=, P=, e=, inc=, Omega=, omega=, f=) + move_to_com()                 */
+/* nbody/simulation.py:44-47.  [3P] REBOUND adds a body given by orbital elements relative to  */
+/* the centre of mass of the bodies already present (Jacobi), with mu = G (M_interior + m).    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int n;
+    double m[MAXN];
+    double x[3 * MAXN], v[3 * MAXN];
+} sys_t;
+
+static void elements_to_state(double mu, double a, double e, double inc, double Om, double om,
+                              double f, double* r3, double* v3) {
+    /* Murray & Dermott rotation of the orbital-plane vector */
+    double cf = cos(f), sf = sin(f);
+    double r = a * (1.0 - e * e) / (1.0 + e * cf);
+    double v0 = sqrt(mu / (a * (1.0 - e * e)));
+    double cO = cos(Om), sO = sin(Om), co = cos(om), so = sin(om), ci = cos(inc), si = sin(inc);
+    /* cos(om+f), sin(om+f) kept as products so rounding follows the element definition */
+    double cwf = co * cf - so * sf, swf = so * cf + co * sf;
+    r3[0] = r * (cO * cwf - sO * swf * ci);
+    r3[1] = r * (sO * cwf + cO * swf * ci);
+    r3[2] = r * (swf * si);
+    /* velocity: v0 * [ -(sin(om+f) + e sin om) , (cos(om+f) + e cos om) ] rotated */
+    double vp = -(swf + e * so), vq = (cwf + e * co);
+    v3[0] = v0 * (cO * vp - sO * vq * ci);
+    v3[1] = v0 * (sO * vp + cO * vq * ci);
+    v3[2] = v0 * (vq * si);
+}
+
+static void build_system(const double* params, int n, sys_t* s) {
+    s->n = n;
+    double M = 0, cx[3] = {0, 0, 0}, cv[3] = {0, 0, 0}; /* running COM of bodies present */
+    for (int i = 0; i < n; i++) {
+        const double* p = params + (size_t)i * NBT_NPAR;
+        double m = p[NBT_P_M];
+        s->m[i] = m;
+        if (i == 0) { /* {'m': M}: at the origin, at rest */
+            for (int k = 0; k < 3; k++) s->x[k] = s->v[k] = 0.0;
+        } else {
+            double mu = NBT_G * (M + m);
+            double P = p[NBT_P_P];
+            double a = cbrt(P * P * mu / (4.0 * PI * PI));
+            double r3[3], v3[3];
+            elements_to_state(mu, a, p[NBT_P_E], p[NBT_P_INC], p[NBT_P_OMEGA_NODE],
+                              p[NBT_P_OMEGA_PERI], p[NBT_P_F], r3, v3);
+            for (int k = 0; k < 3; k++) {
+                s->x[3 * i + k] = cx[k] + r3[k];
+                s->v[3 * i + k] = cv[k] + v3[k];
+            }
+        }
+        for (int k = 0; k < 3; k++) {
+            cx[k] = (cx[k] * M + s->x[3 * i + k] * m) / (M + m);
+            cv[k] = (cv[k] * M + s->v[3 * i + k] * m) / (M + m);
+        }
+        M += m;
+    }
+    /* move_to_com() */
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            s->x[3 * i + k] -= cx[k];
+            s->v[3 * i + k] -= cv[k];
+        }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Direct-summation Newtonian accelerations (REBOUND gravity "basic", no softening)            */
+/* ------------------------------------------------------------------------------------------ */
+static void accel(const sys_t* s, const double* x, double* a) {
+    int n = s->n;
+    for (int i = 0; i < 3 * n; i++) a[i] = 0.0;
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) {
+            double dx = x[3 * j] - x[3 * i], dy = x[3 * j + 1] - x[3 * i + 1],
+                   dz = x[3 * j + 2] - x[3 * i + 2];
+            double r2 = dx * dx + dy * dy + dz * dz;
+            double pre = NBT_G / (r2 * sqrt(r2));
+            double pi_ = pre * s->m[j], pj = pre * s->m[i];
+            a[3 * i] += pi_ * dx; a[3 * i + 1] += pi_ * dy; a[3 * i + 2] += pi_ * dz;
+            a[3 * j] -= pj * dx;  a[3 * j + 1] -= pj * dy;  a[3 * j + 2] -= pj * dz;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* IAS15: 15th-order Gauss-Radau predictor-corrector with adaptive step (Rein & Spiegel 2015,  */
+/* MNRAS 446, 1424 — the published algorithm behind rebound's default integrator; restated     */
+/* from the paper, not from REBOUND's source, which is not available here).                    */
+/*   a(s) = a0 + b0 s + b1 s^2 + ... + b6 s^7,  s in [0,1], sampled at the Radau nodes H[1..7] */
+/* ------------------------------------------------------------------------------------------ */
+static const double H[8] = {0.0,
+                            0.0562625605369221464656521910318,
+                            0.180240691736892364987579942780,
+                            0.352624717113169637373907769648,
+                            0.547153626330555383001448554766,
+                            0.734210177215410531523210605558,
+                            0.885320946839095768090359771030,
+                            0.977520613561287501891174488626};
+static double RR[8][8]; /* 1/(H[j]-H[k]) */
+static double CC[7][7]; /* Newton basis -> monomial: b_k = sum_{j>=k} CC[j][k] g_j */
+static double DD[7][7]; /* monomial -> Newton: g_k = sum_{j>=k} DD[j][k] b_j */
+static int tables_ready = 0;
+
+static void init_tables(void) {
+    if (tables_ready) return;
+    for (int j = 1; j < 8; j++)
+        for (int k = 0; k < j; k++) RR[j][k] = 1.0 / (H[j] - H[k]);
+    /* s (s-h1) ... (s-h_j) = sum_k CC[j][k] s^{k+1}  (long double to keep the tables exact) */
+    long double c[7][7];
+    memset(c, 0, sizeof c);
+    c[0][0] = 1.0L;
+    for (int j = 1; j < 7; j++) {
+        for (int k = 0; k <= j; k++) {
+            long double up = (k > 0) ? c[j - 1][k - 1] : 0.0L;
+            long double same = (k < j) ? c[j - 1][k] : 0.0L;
+            c[j][k] = up - (long double)H[j] * same;
+        }
+    }
+    /* inverse of the (unit upper-triangular in (j>=k)) map: solve sum_{j>=k} c[j][k] g_j = b_k */
+    long double d[7][7];
+    memset(d, 0, sizeof d);
+    for (int col = 0; col < 7; col++) { /* g as a function of unit b_col */
+        long double g[7];
+        for (int k = 6; k >= 0; k--) {
+            long double rhs = (k == col) ? 1.0L : 0.0L;
+            for (int j = k + 1; j < 7; j++) rhs -= c[j][k] * g[j];
+            g[k] = rhs; /* c[k][k] == 1 */
+        }
+        for (int k = 0; k < 7; k++) d[col][k] = g[k];
+    }
+    for (int j = 0; j < 7; j++)
+        for (int k = 0; k < 7; k++) {
+            CC[j][k] = (double)c[j][k];
+            DD[j][k] = (double)d[j][k];
+        }
+    tables_ready = 1;
+}
+
+typedef struct {
+    sys_t s;
+    double t, dt, dt_last;
+    double a0[3 * MAXN];
+    double b[7][3 * MAXN], e[7][3 * MAXN], g[7][3 * MAXN];
+    double csx[3 * MAXN], csv[3 * MAXN]; /* compensated-summation carries */
+    int have_b;
+    long n_steps, n_force;
+} ias15_t;
+
+static void ias15_init(ias15_t* I, const sys_t* s) {
+    init_tables();
+    memset(I, 0, sizeof *I);
+    I->s = *s;
+    I->dt = 1e-3; /* REBOUND's default initial dt */
+}
+
+static inline void add_cs(double* sum, double* carry, double inc) {
+    double y = inc - *carry;
+    double t = *sum + y;
+    *carry = (t - *sum) - y;
+    *sum = t;
+}
+
+/* try one step of size dt; returns 1 if accepted (state advanced), 0 if rejected (I->dt shrunk) */
+static int ias15_step(ias15_t* I, double dt) {
+    const int n3 = 3 * I->s.n;
+    double* x0 = I->s.x; double* v0 = I->s.v; double* a0 = I->a0;
+    double xs[3 * MAXN], as[3 * MAXN];
+    const double eps_b = 1e-9, safety = 0.25;
+
+    accel(&I->s, x0, a0); I->n_force++;
+
+    /* predict b for this step from the previous step's b (ratio q), plus the last correction */
+    if (I->have_b) {
+        double q = dt / I->dt_last, q2 = q * q, q3 = q2 * q, q4 = q2 * q2, q5 = q4 * q, q6 = q3 * q3,
+               q7 = q6 * q;
+        for (int i = 0; i < n3; i++) {
+            double b0 = I->b[0][i], b1 = I->b[1][i], b2 = I->b[2][i], b3 = I->b[3][i],
+                   b4 = I->b[4][i], b5 = I->b[5][i], b6 = I->b[6][i];
+            double be[7];
+            for (int k = 0; k < 7; k++) be[k] = I->b[k][i] - I->e[k][i];
+            I->e[0][i] = q * (b6 * 7.0 + b5 * 6.0 + b4 * 5.0 + b3 * 4.0 + b2 * 3.0 + b1 * 2.0 + b0);
+            I->e[1][i] = q2 * (b6 * 21.0 + b5 * 15.0 + b4 * 10.0 + b3 * 6.0 + b2 * 3.0 + b1);
+            I->e[2][i] = q3 * (b6 * 35.0 + b5 * 20.0 + b4 * 10.0 + b3 * 4.0 + b2);
+            I->e[3][i] = q4 * (b6 * 35.0 + b5 * 15.0 + b4 * 5.0 + b3);
+            I->e[4][i] = q5 * (b6 * 21.0 + b5 * 6.0 + b4);
+            I->e[5][i] = q6 * (b6 * 7.0 + b5);
+            I->e[6][i] = q7 * b6;
+            for (int k = 0; k < 7; k++) I->b[k][i] = I->e[k][i] + be[k];
+        }
+    }
+    for (int i = 0; i < n3; i++)
+        for (int k = 0; k < 7; k++) {
+            double gk = 0.0;
+            for (int j = k; j < 7; j++) gk += DD[j][k] * I->b[j][i];
+            I->g[k][i] = gk;
+        }
+
+    double pc_err = 1e300, pc_err_last = 2.0;
+    int iter = 0;
+    while (1) {
+        if (pc_err < 1e-16) break;
+        if (iter > 2 && pc_err_last <= pc_err) break; /* stopped converging (round-off floor) */
+        if (iter >= 12) break;
+        pc_err_last = pc_err;
+        iter++;
+        double max_a = 0.0, max_db6 = 0.0;
+        for (int n = 1; n < 8; n++) {
+            double s = H[n];
+            for (int i = 0; i < n3; i++) {
+                double p = I->b[6][i] * (1.0 / 72.0);
+                p = p * s + I->b[5][i] * (1.0 / 56.0);
+                p = p * s + I->b[4][i] * (1.0 / 42.0);
+                p = p * s + I->b[3][i] * (1.0 / 30.0);
+                p = p * s + I->b[2][i] * (1.0 / 20.0);
+                p = p * s + I->b[1][i] * (1.0 / 12.0);
+                p = p * s + I->b[0][i] * (1.0 / 6.0);
+                p = p * s + a0[i] * 0.5;
+                xs[i] = x0[i] - I->csx[i] + s * dt * (v0[i] + s * dt * p);
+            }
+            accel(&I->s, xs, as); I->n_force++;
+            for (int i = 0; i < n3; i++) {
+                double gk = (as[i] - a0[i]) * RR[n][0];
+                for (int k = 1; k < n; k++) gk = (gk - I->g[k - 1][i]) * RR[n][k];
+                double dg = gk - I->g[n - 1][i];
+                I->g[n - 1][i] = gk;
+                for (int k = 0; k < n; k++) I->b[k][i] += CC[n - 1][k] * dg;
+                if (n == 7) {
+                    double aa = fabs(as[i]), d6 = fabs(dg);
+                    if (aa > max_a) max_a = aa;
+                    if (d6 > max_db6) max_db6 = d6;
+                }
+            }
+        }
+        pc_err = max_db6 / max_a;
+    }
+
+    /* step-size control on the magnitude of the last series term */
+    double max_a = 0.0, max_b6 = 0.0;
+    for (int i = 0; i < n3; i++) {
+        double aa = fabs(a0[i]), bb = fabs(I->b[6][i]);
+        if (aa > max_a) max_a = aa;
+        if (bb > max_b6) max_b6 = bb;
+    }
+    double err = max_b6 / max_a;
+    double dt_new = (err > 0 && isfinite(err)) ? dt * pow(eps_b / err, 1.0 / 7.0) : dt / safety;
+    if (fabs(dt_new / dt) < safety) { /* reject and retry with the smaller step */
+        I->dt = dt_new;
+        if (I->have_b) { /* undo prediction: restore b as of the end of the last step */
+            for (int i = 0; i < n3; i++)
+                for (int k = 0; k < 7; k++) I->b[k][i] = I->e[k][i] = 0.0;
+            I->have_b = 0;
+        }
+        return 0;
+    }
+    if (dt_new / dt > 1.0 / safety) dt_new = dt / safety;
+
+    /* advance with compensated summation */
+    for (int i = 0; i < n3; i++) {
+        double b0 = I->b[0][i], b1 = I->b[1][i], b2 = I->b[2][i], b3 = I->b[3][i], b4 = I->b[4][i],
+               b5 = I->b[5][i], b6 = I->b[6][i];
+        double dx2 = (b6 / 72.0 + b5 / 56.0 + b4 / 42.0 + b3 / 30.0 + b2 / 20.0 + b1 / 12.0 + b0 / 6.0 +
+                      a0[i] / 2.0) * dt * dt;
+        add_cs(&x0[i], &I->csx[i], dx2);
+        add_cs(&x0[i], &I->csx[i], v0[i] * dt);
+        double dv = (b6 / 8.0 + b5 / 7.0 + b4 / 6.0 + b3 / 5.0 + b2 / 4.0 + b1 / 3.0 + b0 / 2.0 + a0[i]) * dt;
+        add_cs(&v0[i], &I->csv[i], dv);
+    }
+    /* e currently holds the prediction made for this step; keep (b - e) semantics for the next */
+    I->t += dt;
+    I->dt_last = dt;
+    I->dt = dt_new;
+    I->have_b = 1;
+    I->n_steps++;
+    return 1;
+}
+
+/* sim.integrate(t_end) with exact_finish_time=1: the last step is shortened to land on t_end */
+static void ias15_integrate_to(ias15_t* I, double t_end) {
+    while (I->t < t_end) {
+        double remaining = t_end - I->t;
+        if (remaining <= 1e-14 * fabs(t_end)) { I->t = t_end; break; }
+        double dt = I->dt, keep = I->dt;
+        int shortened = 0;
+        if (dt >= remaining) { dt = remaining; shortened = 1; }
+        if (ias15_step(I, dt)) {
+            if (shortened) { /* landed on the output; restore the un-shortened step suggestion */
+                I->t = t_end;
+                I->dt = keep;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Jacobi osculating elements as rebound's particle.P/a/e/inc/Omega/omega/M return them [3P]:  */
+/* primary = centre of mass of all lower-index bodies, mu = G (M_interior + m).                */
+/* nbody/simulation.py:148-150.                                                                */
+/* ------------------------------------------------------------------------------------------ */
+static double acos2(double num, double den, double disamb) {
+    double val, c = num / den;
+    if (c > -1.0 && c < 1.0) val = acos(c);
+    else val = (c <= -1.0) ? PI : 0.0;
+    return (disamb < 0.0) ? -val : val;
+}
+
+typedef struct { double P, a, e, inc, Omega, omega, M; } orbit_t;
+
+static orbit_t state_to_orbit(double mu, const double* d, const double* w) {
+    const double MIN_INC = 1e-8, MIN_ECC = 1e-8;
+    orbit_t o;
+    double hx = d[1] * w[2] - d[2] * w[1], hy = d[2] * w[0] - d[0] * w[2], hz = d[0] * w[1] - d[1] * w[0];
+    double h = sqrt(hx * hx + hy * hy + hz * hz);
+    double v2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    double r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    double vc2 = mu / r;
+    o.a = -mu / (v2 - 2.0 * vc2);
+    double vr = (d[0] * w[0] + d[1] * w[1] + d[2] * w[2]) / r;
+    double rvr = r * vr, vd2 = v2 - vc2;
+    double ex = (vd2 * d[0] - rvr * w[0]) / mu, ey = (vd2 * d[1] - rvr * w[1]) / mu,
+           ez = (vd2 * d[2] - rvr * w[2]) / mu;
+    o.e = sqrt(ex * ex + ey * ey + ez * ez);
+    double nmm = o.a / fabs(o.a) * sqrt(fabs(mu / (o.a * o.a * o.a)));
+    o.P = 2.0 * PI / nmm;
+    o.inc = acos2(hz, h, 1.0);
+    double nx = -hy, ny = hx, nn = sqrt(nx * nx + ny * ny);
+    o.Omega = acos2(nx, nn, ny);
+    double ea = 0.0, f;
+    if (o.e < 1.0) {
+        ea = acos2(1.0 - r / o.a, o.e, vr);
+        o.M = ea - o.e * sin(ea);
+    } else {
+        ea = acosh((1.0 - r / o.a) / o.e);
+        if (vr < 0.0) ea = -ea;
+        o.M = o.e * sinh(ea) - ea;
+    }
+    if (o.inc < MIN_INC || o.inc > PI - MIN_INC) { /* planar: longitudes measured from x */
+        double theta = acos2(d[0], r, d[1]);
+        double pomega = acos2(ex, o.e, ey);
+        if (o.inc < PI / 2.0) { o.omega = pomega - o.Omega; f = theta - pomega; }
+        else { o.omega = o.Omega - pomega; f = pomega - theta; }
+        if (o.e <= MIN_ECC) { o.omega = 0.0; }
+    } else {
+        double wpf = acos2(nx * d[0] + ny * d[1], nn * r, d[2]);
+        o.omega = acos2(nx * ex + ny * ey, nn * o.e, ez);
+        f = wpf - o.omega;
+        if (o.e <= MIN_ECC) { o.omega = 0.0; }
+    }
+    (void)f;
+    return o;
+}
+
+/* series row layout (NBT_F_SERIES): star x,y,z, then per planet x,y,z,P,a,e,inc,Omega,omega,M */
+static void sample_row(const sys_t* s, double* row) {
+    int n = s->n;
+    row[0] = s->x[0]; row[1] = s->x[1]; row[2] = s->x[2];
+    double M = s->m[0], cx[3], cv[3];
+    for (int k = 0; k < 3; k++) { cx[k] = s->x[k]; cv[k] = s->v[k]; }
+    for (int i = 1; i < n; i++) {
+        double d[3], w[3];
+        for (int k = 0; k < 3; k++) { d[k] = s->x[3 * i + k] - cx[k]; w[k] = s->v[3 * i + k] - cv[k]; }
+        orbit_t o = state_to_orbit(NBT_G * (M + s->m[i]), d, w);
+        double* p = row + 3 + 10 * (i - 1);
+        p[0] = s->x[3 * i]; p[1] = s->x[3 * i + 1]; p[2] = s->x[3 * i + 2];
+        p[3] = o.P; p[4] = o.a; p[5] = o.e; p[6] = o.inc; p[7] = o.Omega; p[8] = o.omega; p[9] = o.M;
+        for (int k = 0; k < 3; k++) {
+            cx[k] = (cx[k] * M + s->x[3 * i + k] * s->m[i]) / (M + s->m[i]);
+            cv[k] = (cv[k] * M + s->v[3 * i + k] * s->m[i]) / (M + s->m[i]);
+        }
+        M += s->m[i];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* exported fine-grained pieces (used by tests to pin each stage separately)                   */
+/* ------------------------------------------------------------------------------------------ */
+
+/* state[n][7] = m, x, y, z, vx, vy, vz after add()+move_to_com() */
+void nbo_initial_state(const double* params, int n_bodies, double* state) {
+    sys_t s;
+    build_system(params, n_bodies, &s);
+    for (int i = 0; i < n_bodies; i++) {
+        state[7 * i] = s.m[i];
+        for (int k = 0; k < 3; k++) { state[7 * i + 1 + k] = s.x[3 * i + k]; state[7 * i + 4 + k] = s.v[3 * i + k]; }
+    }
+}
+
+/* integrate(): series[n_outputs][3 + 10*Np]; returns number of IAS15 steps taken */
+long nbo_integrate_series(const double* params, int n_bodies, double n_days, int n_outputs,
+                          double* series, double* final_state) {
+    sys_t s;
+    build_system(params, n_bodies, &s);
+    ias15_t* I = (ias15_t*)malloc(sizeof(ias15_t));
+    ias15_init(I, &s);
+    int W = 3 + 10 * (n_bodies - 1);
+    double step = n_days / (double)(n_outputs - 1); /* np.linspace(0, Ndays, Noutputs) */
+    for (int o = 0; o < n_outputs; o++) {
+        double t = (o == n_outputs - 1) ? n_days : o * step;
+        ias15_integrate_to(I, t);
+        sample_row(&I->s, series + (size_t)o * W);
+    }
+    if (final_state)
+        for (int i = 0; i < n_bodies; i++)
+            for (int k = 0; k < 3; k++) {
+                final_state[6 * i + k] = I->s.x[3 * i + k];
+                final_state[6 * i + 3 + k] = I->s.v[3 * i + k];
+            }
+    long ns = I->n_steps;
+    free(I);
+    return ns;
+}
+
+/* transit_times(xp, xs, times): simulation.py:163-170 with find_zero of tools.py:61-65 */
+int nbo_transit_times(const double* xp, const double* xs, const double* times, int n, double* tt, int cap) {
+    int c = 0;
+    double prev = xp[0] - xs[0];
+    for (int i = 1; i < n; i++) {
+        double cur = xp[i] - xs[i];
+        if (prev >= 0.0 && cur <= 0.0) {
+            double m = (cur - prev) / (times[i] - times[i - 1]);
+            double t0 = -prev / m + times[i - 1];
+            if (c < cap) tt[c] = t0;
+            c++;
+        }
+        prev = cur;
+    }
+    return c;
+}
+
+/* TTV(epochs = arange(n), tt): simulation.py:172-177.  out: ttv[n]; returns slope m, intercept b */
+void nbo_ttv_fit(const double* tt, int n, double* ttv, double* m_out, double* b_out) {
+    /* least squares of tt on k = 0..n-1 (what np.linalg.lstsq solves), centred for stability */
+    double kbar = 0.5 * (n - 1), tbar = 0;
+    for (int k = 0; k < n; k++) tbar += tt[k];
+    tbar /= n;
+    double skk = 0, skt = 0;
+    for (int k = 0; k < n; k++) { double dk = k - kbar; skk += dk * dk; skt += dk * (tt[k] - tbar); }
+    double m = (n > 1) ? skt / skk : 0.0;
+    double b = tbar - m * kbar;
+    for (int k = 0; k < n; k++) ttv[k] = tt[k] - m * k - b;
+    *m_out = m; *b_out = b;
+}
+
+static int cmp_double(const void* a, const void* b) {
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+
+/* maxavg(x) = (percentile(|x|, 75) + max|x|) / 2, numpy 'linear' percentile.  tools.py:22 */
+double nbo_maxavg(const double* x, int n) {
+    if (n <= 0) return NAN;
+    double* s = (double*)malloc(sizeof(double) * n);
+    for (int i = 0; i < n; i++) s[i] = fabs(x[i]);
+    qsort(s, n, sizeof(double), cmp_double);
+    double pos = 0.75 * (n - 1);
+    int lo = (int)floor(pos);
+    double frac = pos - lo;
+    double p75 = (lo + 1 < n) ? s[lo] + (s[lo + 1] - s[lo]) * frac : s[lo];
+    double r = 0.5 * (p75 + s[n - 1]);
+    free(s);
+    return r;
+}
+
+/* astropy autofrequency grid size (tools.py:104): Nf = 1 + round((fmax - fmin) * spp * T) */
+int64_t nbo_ls_nfreq(double baseline, double minfreq, double maxfreq, int spp) {
+    double df = 1.0 / (spp * baseline);
+    return 1 + (int64_t)llround((maxfreq - minfreq) / df);
+}
+
+/* Generalised (floating-mean) Lomb-Scargle, standard normalisation, unit weights:
+ * what LombScargle(t, y).power(f, method='cython'|'slow') evaluates [3P]. */
+void nbo_lomb_scargle(const double* t, const double* y, int n, double f0, double df, int64_t nf,
+                      double* power) {
+    double w = 1.0 / n, ybar = 0;
+    for (int i = 0; i < n; i++) ybar += w * y[i];
+    double YY = 0;
+    for (int i = 0; i < n; i++) YY += w * (y[i] - ybar) * (y[i] - ybar);
+    for (int64_t k = 0; k < nf; k++) {
+        double om = 2.0 * PI * (f0 + k * df);
+        double S = 0, C = 0, S2 = 0, C2 = 0;
+        for (int i = 0; i < n; i++) {
+            double sn = sin(om * t[i]), cs = cos(om * t[i]);
+            S += w * sn; C += w * cs;
+            S2 += 2.0 * w * sn * cs; C2 += w * (cs * cs - sn * sn);
+        }
+        S2 -= 2.0 * S * C;
+        C2 -= (C * C - S * S);
+        double omtau = 0.5 * atan2(S2, C2);
+        double ct = cos(omtau), st = sin(omtau);
+        double YC = 0, YS = 0, Cc = 0, Ss = 0, Ct = 0, St = 0;
+        for (int i = 0; i < n; i++) {
+            double sn = sin(om * t[i]), cs = cos(om * t[i]);
+            double cst = cs * ct + sn * st, snt = sn * ct - cs * st; /* cos, sin of om(t - tau) */
+            double yc = y[i] - ybar;
+            YC += w * yc * cst; YS += w * yc * snt;
+            Cc += w * cst * cst; Ss += w * snt * snt;
+            Ct += w * cst; St += w * snt;
+        }
+        Cc -= Ct * Ct; Ss -= St * St;
+        power[k] = (YC * YC / Cc + YS * YS / Ss) / YY;
+    }
+}
+
+/* nested.py:85-95 myloglike for one forward model */
+double nbo_loglike(const double* ttv, int n_ttv, double c0, double c1, const double* x,
+                   const double* y, const double* yerr, int n_data) {
+    int ok = 1;
+    for (int i = 0; i < n_data; i++) if ((int)x[i] >= n_ttv || (int)x[i] < -n_ttv) ok = 0;
+    if (ok) {
+        double s = 0;
+        for (int i = 0; i < n_data; i++) {
+            int k = (int)x[i]; if (k < 0) k += n_ttv;
+            double r = (y[i] - (c1 * x[i] + c0) - ttv[k]) / yerr[i];
+            s += r * r;
+        }
+        return -0.5 * s;
+    }
+    /* except-branch: -10 * sum over the ttv that exist, paired index-for-index with the data */
+    double s = 0;
+    for (int i = 0; i < n_ttv && i < n_data; i++) {
+        double r = (y[i] - (c1 * x[i] + c0) - ttv[i]) / yerr[i];
+        s += r * r;
+    }
+    /* (the reference raises IndexError inside the loop too if n_ttv > n_data; it never is) */
+    return -10.0 * s;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Batched driver with the product's output layout (include/nbt.h), for parity tests and as   */
+/* the timed CPU baseline.  Pointers are host memory.  Returns 0.                             */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const nbt_config* cfg; const nbt_inputs* in; nbt_outputs* out;
+    atomic_int next; atomic_llong steps;
+} run_ctx;
+
+static void run_one(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, int b, int64_t* steps) {
+    const int B = cfg->n_systems, N = cfg->n_bodies, Np = N - 1, NO = cfg->n_outputs;
+    const int W = 3 + 10 * Np;
+    const int stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
+    int64_t total_steps = 0;
+    {
+        const double* par = in->params + (size_t)b * N * NBT_NPAR;
+        double* series = (double*)malloc(sizeof(double) * (size_t)NO * W);
+        double* times = (double*)malloc(sizeof(double) * NO);
+        double* col_p = (double*)malloc(sizeof(double) * NO);
+        double* col_s = (double*)malloc(sizeof(double) * NO);
+        total_steps += nbo_integrate_series(par, N, cfg->n_days, NO, series, NULL);
+        double step = cfg->n_days / (double)(NO - 1);
+        for (int o = 0; o < NO; o++) times[o] = (o == NO - 1) ? cfg->n_days : o * step;
+        int status = 0;
+        for (int o = 0; o < NO; o++) {
+            col_s[o] = series[(size_t)o * W];
+            for (int k = 0; k < W; k++) if (!isfinite(series[(size_t)o * W + k])) status |= NBT_S_NONFINITE;
+        }
+        /* RV = np.diff(star x) * 1.496e11 * dt, dt = Noutputs/(Ndays*86400)  (simulation.py:157,186) */
+        if ((cfg->flags & NBT_F_RV) && out->rv) {
+            double dtc = (double)NO / (cfg->n_days * 24.0 * 60.0 * 60.0);
+            double* rvs = (double*)malloc(sizeof(double) * (NO - 1));
+            for (int o = 0; o + 1 < NO; o++) {
+                rvs[o] = (col_s[o + 1] - col_s[o]) * 1.496e11 * dtc;
+                out->rv[(size_t)o * B + b] = rvs[o];
+            }
+            if (out->rv_max) out->rv_max[b] = nbo_maxavg(rvs, NO - 1);
+            if ((cfg->flags & NBT_F_LS_RV) && out->ls_rv_power) {
+                double T = times[NO - 1] - times[1];
+                int64_t nf = nbo_ls_nfreq(T, cfg->ls_rv_minfreq, cfg->ls_rv_maxfreq, cfg->ls_samples_per_peak);
+                nbo_lomb_scargle(times + 1, rvs, NO - 1, cfg->ls_rv_minfreq,
+                                 1.0 / (cfg->ls_samples_per_peak * T), nf, out->ls_rv_power + (size_t)b * nf);
+            }
+            free(rvs);
+        }
+        for (int j = 0; j < Np; j++) {
+            size_t sp = (size_t)b * Np + j;
+            double* row0 = series + 3 + 10 * j;
+            if (cfg->flags & NBT_F_MEANS) {
+                double sa = 0, se = 0, si = 0, so = 0;
+                for (int o = 0; o < NO; o++) {
+                    const double* p = row0 + (size_t)o * W;
+                    sa += p[4]; se += p[5]; si += p[6]; so += p[8];
+                    if (p[4] < 0) status |= NBT_S_UNBOUND;
+                }
+                out->mean_a[sp] = sa / NO; out->mean_e[sp] = se / NO; out->mean_inc[sp] = si / NO;
+                if ((cfg->flags & NBT_F_MEAN_OMEGA) && out->mean_omega) out->mean_omega[sp] = so / NO;
+            }
+            if ((cfg->flags & NBT_F_ORBIT) && out->orbit_xz)
+                for (int o = 0, q = 0; o < NO; o += stride, q++) {
+                    const double* p = row0 + (size_t)o * W;
+                    double* dst = out->orbit_xz + (((size_t)q * B + b) * Np + j) * 2;
+                    dst[0] = p[0]; dst[1] = p[2];
+                }
+            if ((cfg->flags & NBT_F_PLANET1_ONLY) && j > 0) {
+                out->n_tt[sp] = 0; out->period[sp] = par[(j + 1) * NBT_NPAR + NBT_P_P]; out->t0[sp] = 0;
+                out->ttv_max[sp] = 0;
+                continue;
+            }
+            for (int o = 0; o < NO; o++) col_p[o] = row0[(size_t)o * W];
+            int64_t off = in->tt_offsets[sp], cap = in->tt_offsets[sp + 1] - off;
+            int n = nbo_transit_times(col_p, col_s, times, NO, out->tt + off, (int)cap);
+            out->n_tt[sp] = n;
+            if (n > cap) { status |= NBT_S_TT_OVERFLOW; n = (int)cap; }
+            if (n >= 3) {
+                double m, c;
+                nbo_ttv_fit(out->tt + off, n, out->ttv + off, &m, &c);
+                out->period[sp] = m; out->t0[sp] = c;
+                out->ttv_max[sp] = nbo_maxavg(out->ttv + off, n);
+            } else { /* simulation.py:207-210 fallback: per = objects P, t0 = 0, ttv = [0] */
+                status |= NBT_S_FEW_TRANSITS;
+                out->period[sp] = par[(j + 1) * NBT_NPAR + NBT_P_P]; out->t0[sp] = 0.0;
+                if (cap > 0) out->ttv[off] = 0.0;
+                out->ttv_max[sp] = 0.0;
+            }
+            if ((cfg->flags & NBT_F_LS_OC) && out->ls_oc_power && in->ls_offsets) {
+                int64_t loff = in->ls_offsets[sp], lcap = in->ls_offsets[sp + 1] - loff;
+                int64_t nf = 0;
+                if (n >= 3) {
+                    double T = (double)(n - 1);
+                    nf = nbo_ls_nfreq(T, cfg->ls_oc_minfreq, cfg->ls_oc_maxfreq, cfg->ls_samples_per_peak);
+                    if (nf > lcap) nf = lcap;
+                    double* ep = (double*)malloc(sizeof(double) * n);
+                    for (int k = 0; k < n; k++) ep[k] = k;
+                    nbo_lomb_scargle(ep, out->ttv + off, n, cfg->ls_oc_minfreq,
+                                     1.0 / (cfg->ls_samples_per_peak * T), nf, out->ls_oc_power + loff);
+                    free(ep);
+                }
+                out->ls_oc_nfreq[sp] = (int32_t)nf;
+            }
+        }
+        if ((cfg->flags & NBT_F_SERIES) && out->series)
+            for (int o = 0; o < NO; o++)
+                memcpy(out->series + ((size_t)o * B + b) * W, series + (size_t)o * W, sizeof(double) * W);
+        out->status[b] = status;
+        free(series); free(times); free(col_p); free(col_s);
+    }
+    *steps = total_steps;
+}
+
+static void* run_worker(void* arg) {
+    run_ctx* c = (run_ctx*)arg;
+    for (;;) {
+        int b = atomic_fetch_add(&c->next, 1);
+        if (b >= c->cfg->n_systems) break;
+        int64_t st = 0;
+        run_one(c->cfg, c->in, c->out, b, &st);
+        atomic_fetch_add(&c->steps, (long long)st);
+    }
+    return NULL;
+}
+
+int nbo_max_threads(void) {
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+int nbo_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, int n_threads,
+            int64_t* ias15_steps_out) {
+    init_tables();
+    run_ctx c;
+    c.cfg = cfg; c.in = in; c.out = out;
+    atomic_init(&c.next, 0); atomic_init(&c.steps, 0);
+    if (n_threads <= 0) n_threads = nbo_max_threads();
+    if (n_threads > cfg->n_systems) n_threads = cfg->n_systems > 0 ? cfg->n_systems : 1;
+    if (n_threads <= 1) run_worker(&c);
+    else {
+        pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * n_threads);
+        for (int i = 0; i < n_threads; i++) pthread_create(&th[i], NULL, run_worker, &c);
+        for (int i = 0; i < n_threads; i++) pthread_join(th[i], NULL);
+        free(th);
+    }
+    if (ias15_steps_out) *ias15_steps_out = (int64_t)atomic_load(&c.steps);
+    return 0;
+}
