@@ -65,7 +65,8 @@ enum { NBT_F_MEANS = 1 << 0,       /* time means of Jacobi a, e, inc (analyze :2
        NBT_F_LS_OC = 1 << 5,       /* O-C periodogram per planet */
        NBT_F_LS_RV = 1 << 6,       /* RV periodogram per system (needs NBT_F_RV) */
        NBT_F_PLANET1_ONLY = 1 << 7,/* ttvfast: transit products for planet 1 only (analyze :181-184) */
-       NBT_F_DEVICE_PTRS = 1 << 8  /* all buffers are device pointers; async on `stream` */
+       NBT_F_DEVICE_PTRS = 1 << 8, /* all buffers are device pointers; async on `stream` */
+       NBT_F_TIMING = 1 << 9       /* record CUDA events around each stage (read with nbt_timing) */
 };
 
 /* per-system status bits (the reference signals these only indirectly) */
@@ -87,12 +88,15 @@ typedef struct nbt_config {
     double ls_oc_minfreq, ls_oc_maxfreq; /* 1/180, 1/2 (analyze :213) */
     double ls_rv_minfreq, ls_rv_maxfreq; /* 1/365, 1/2 (tools.py:97) */
     int32_t ls_samples_per_peak;         /* 10 (tools.py:104) */
-    int32_t reserved;
+    int32_t tt_cap_max;  /* largest per-planet CSR capacity (nbt_plan_tt returns it); 0 = derive
+                            from host tt_offsets (required > 0 with NBT_F_DEVICE_PTRS) */
 } nbt_config;
 
 typedef struct nbt_inputs {
     const double* params;      /* [B][n_bodies][NBT_NPAR] */
     const int32_t* substeps;   /* [B] or NULL (then cfg.substeps applies to all) */
+    const int32_t* order;      /* [B] launch order (nbt_plan_order: systems sorted by substeps so
+                                  that a warp's lanes run equal trip counts) or NULL */
     const int64_t* tt_offsets; /* [B*Np + 1] CSR capacity offsets into tt/ttv (nbt_plan_tt) */
     const int64_t* ls_offsets; /* [B*Np + 1] CSR capacity offsets into ls_oc_power, or NULL */
 } nbt_inputs;
@@ -128,11 +132,15 @@ int nbt_device_count(void);
 const char* nbt_last_error(void);
 
 /* Number of frequencies of astropy's autofrequency grid for a series of n samples spanning
- * `baseline` (= t.max - t.min): 1 + round((fmax - fmin) * spp * baseline).  tools.py:104. */
+ * `baseline` (= t.max - t.min): df = 1/baseline/spp, Nf = 1 + rint((fmax - fmin)/df)
+ * (np.round is round-half-even), freq_k = fmin + k*df.  tools.py:104. */
 int64_t nbt_ls_nfreq(double baseline, double minfreq, double maxfreq, int samples_per_peak);
 
-/* Fill tt_offsets[B*Np+1] with CSR capacities ceil(1.05*Ndays/P)+3 per planet (host helper). */
+/* Fill tt_offsets[B*Np+1] with CSR capacities ceil(1.05*Ndays/P)+3 per planet (host helper).
+ * Returns the largest single capacity (>0), or <0 on error. */
 int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets);
+/* Fill order[B]: permutation of 0..B-1 sorted by decreasing substeps (host helper). */
+int nbt_plan_order(const nbt_config* cfg, const int32_t* substeps, int32_t* order);
 /* Fill ls_offsets[B*Np+1] from tt_offsets (capacity of the O-C periodogram). */
 int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets);
 
@@ -144,6 +152,30 @@ int64_t nbt_count_steps(const nbt_config* cfg, const int32_t* substeps);
 
 /* The hot path: set up, integrate, detect transits, fit ephemerides, reduce. */
 int nbt_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, void* cuda_stream);
+
+/* analyze() on a recorded sim_data series (nbody/simulation.py:179-231): same outputs as
+ * nbt_run, but the front end scans `series` ([n_outputs][B][3+10*Np], the NBT_F_SERIES layout)
+ * sampled at `times` [n_outputs] instead of integrating; `dt` is sim_data['dt'] (:157).
+ * in->params supplies the objects' P (the `< 3 transits` fallback, :207-210). */
+int nbt_analyze(const nbt_config* cfg, const double* series, const double* times, double dt,
+                const nbt_inputs* in, nbt_outputs* out, void* cuda_stream);
+
+/* Stand-alone batched forms of the reference's array functions (device_ptrs as below).
+ * transit_times(xp, xs, times): nbody/simulation.py:163-170. xp, xs: [n_series][n]; times: [n] if
+ * times_shared else [n_series][n]; tt: [n_series][cap]; n_tt: [n_series] (may exceed cap). */
+int nbt_transit_times(const double* xp, const double* xs, const double* times, int64_t n_series, int64_t n,
+                      double* tt, int32_t* n_tt, int64_t cap, int times_shared, int device, int device_ptrs,
+                      void* cuda_stream);
+/* find_zero(t1, dx1, t2, dx2), elementwise over n: nbody/tools.py:61-65. */
+int nbt_find_zero(const double* t1, const double* dx1, const double* t2, const double* dx2, int64_t n,
+                  double* t0, int device, int device_ptrs, void* cuda_stream);
+/* TTV(epochs, tt): nbody/simulation.py:172-177. epochs (NULL -> 0..n-1), tt, ttv: [n_series][n];
+ * slope (= period m), intercept (= t0 b): [n_series]. */
+int nbt_ttv_fit(const double* epochs, const double* tt, int64_t n_series, int64_t n, double* ttv,
+                double* slope, double* intercept, int device, int device_ptrs, void* cuda_stream);
+/* maxavg(x) = (percentile(|x|,75) + max|x|)/2: nbody/tools.py:22. x: [n_series][n]; out: [n_series]. */
+int nbt_maxavg(const double* x, int64_t n_series, int64_t n, double* out, int device, int device_ptrs,
+               void* cuda_stream);
 
 /* Generalised (floating-mean) Lomb-Scargle of `n_series` independent series.
  * t, y: [n_series][n] (t == NULL -> t = 0..n-1), power: [n_series][n_freq],
@@ -159,6 +191,16 @@ int nbt_chi2(const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt, 
              int32_t n_planets, const double* c0, const double* c1, const double* x, const double* y,
              const double* yerr, int32_t n_data, double* loglike, int device, int device_ptrs,
              void* cuda_stream);
+
+/* Device time [ms] of the stages of this thread's last nbt_run / nbt_analyze issued with
+ * NBT_F_TIMING, from CUDA events on the launch stream: ms4 = {front end (k_integrate or
+ * k_scan_series), k_fit, k_ls_oc, RV stages}.  Synchronises on the last event. */
+int nbt_timing(double* ms4);
+
+/* Diagnostic: measured FP64 DFMA throughput of `device` (8 independent chains per thread,
+ * 8 CTAs of 256 threads per SM) — the roofline denominator bench.py reports against, since
+ * MEASURED_PEAKS.json carries no FP64 figure. */
+int nbt_fp64_peak(int device, int iters, double* tflops_out, double* ms_out);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,7 @@ F_LS_OC = 1 << 5
 F_LS_RV = 1 << 6
 F_PLANET1_ONLY = 1 << 7
 F_DEVICE_PTRS = 1 << 8
+F_TIMING = 1 << 9
 
 S_NONFINITE = 1 << 0
 S_UNBOUND = 1 << 1
@@ -58,12 +59,12 @@ class nbt_config(C.Structure):
         ("ls_rv_minfreq", C.c_double),
         ("ls_rv_maxfreq", C.c_double),
         ("ls_samples_per_peak", C.c_int32),
-        ("reserved", C.c_int32),
+        ("tt_cap_max", C.c_int32),
     ]
 
 
 class nbt_inputs(C.Structure):
-    _fields_ = [("params", _dp), ("substeps", _ip), ("tt_offsets", _lp), ("ls_offsets", _lp)]
+    _fields_ = [("params", _dp), ("substeps", _ip), ("order", _ip), ("tt_offsets", _lp), ("ls_offsets", _lp)]
 
 
 class nbt_outputs(C.Structure):
@@ -122,6 +123,7 @@ def load():
     lib.nbt_ls_nfreq.restype = C.c_int64
     lib.nbt_ls_nfreq.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
     lib.nbt_plan_tt.argtypes = [C.POINTER(nbt_config), _dp, _lp]
+    lib.nbt_plan_order.argtypes = [C.POINTER(nbt_config), _ip, _ip]
     lib.nbt_plan_ls.argtypes = [C.POINTER(nbt_config), _lp, _lp]
     lib.nbt_plan_substeps.argtypes = [C.POINTER(nbt_config), _dp, _ip]
     lib.nbt_count_steps.restype = C.c_int64
@@ -131,6 +133,15 @@ def load():
                                      _dp, C.c_int, C.c_int, C.c_void_p]
     lib.nbt_chi2.argtypes = [_dp, _lp, _ip, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.c_int32, _dp,
                              C.c_int, C.c_int, C.c_void_p]
+    lib.nbt_analyze.argtypes = [C.POINTER(nbt_config), _dp, _dp, C.c_double, C.POINTER(nbt_inputs),
+                                C.POINTER(nbt_outputs), C.c_void_p]
+    lib.nbt_transit_times.argtypes = [_dp, _dp, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_int64, C.c_int, C.c_int,
+                                      C.c_int, C.c_void_p]
+    lib.nbt_find_zero.argtypes = [_dp, _dp, _dp, _dp, C.c_int64, _dp, C.c_int, C.c_int, C.c_void_p]
+    lib.nbt_ttv_fit.argtypes = [_dp, _dp, C.c_int64, C.c_int64, _dp, _dp, _dp, C.c_int, C.c_int, C.c_void_p]
+    lib.nbt_maxavg.argtypes = [_dp, C.c_int64, C.c_int64, _dp, C.c_int, C.c_int, C.c_void_p]
+    lib.nbt_fp64_peak.argtypes = [C.c_int, C.c_int, _dp, _dp]
+    lib.nbt_timing.argtypes = [_dp]
     if lib.nbt_abi_version() != NBT_ABI_VERSION:
         raise RuntimeError("libnbt.so ABI version mismatch")
     _LIB = lib

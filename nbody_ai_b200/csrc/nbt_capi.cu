@@ -1,0 +1,1175 @@
+// nbt_capi.cu — CUDA kernels (sm_100a) + the C ABI of include/nbt.h.
+//
+// Kernels (all FP64, no tensor cores: nothing on the path is a dense contraction)
+//   k_integrate<NP>   one system per thread, state in registers; integrate + sample on the
+//                     linspace grid + transit detection + Jacobi-element sums, fused
+//                     (nbody/simulation.py:27-52, 131-170, 216-217)                FP64-pipe bound
+//   k_fit             one warp per (system, planet): linear ephemeris, O-C, maxavg
+//                     (nbody/simulation.py:172-177, 205-210; nbody/tools.py:22)    tiny, HBM/latency
+//   k_ls_oc           one warp per (system, planet): floating-mean Lomb-Scargle of the O-C
+//                     (nbody/simulation.py:213 -> nbody/tools.py:97-104)           FP64-pipe bound
+//   k_transpose / k_rv_max / k_ls_series   RV products (nbody/simulation.py:186-188)
+//   k_chi2            nested-sampling log-likelihood (nbody/nested.py:85-95)
+//   k_dfma_peak       DFMA-chain microbenchmark: the measured FP64 roofline denominator
+//
+// There is no CPU path in this library: without a CUDA device every compute entry fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "nbt_core.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int nbt_fail(int rc, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return rc;
+}
+
+#define NBT_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            rc = nbt_fail((int)e__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),    \
+                          __FILE__, __LINE__);                                                  \
+            goto done;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// k-th smallest (0-based) of |x[0..n)| by bisection on the IEEE bit pattern (monotone for
+// non-negative doubles): 63 warp-wide counting passes, no scratch memory, no sort.
+__device__ double warp_kth_abs(const double* x, int n, int k, int lane) {
+    unsigned long long ans = 0ull;
+    for (int bit = 62; bit >= 0; bit--) {
+        const unsigned long long cand = ans | (1ull << bit);
+        int c = 0;
+        for (int i = lane; i < n; i += 32)
+            c += ((unsigned long long)__double_as_longlong(fabs(x[i])) < cand) ? 1 : 0;
+        c = warp_sum_i(c);
+        if (c <= k) ans = cand;
+    }
+    return __longlong_as_double((long long)ans);
+}
+
+// maxavg(x) = (percentile(|x|, 75, 'linear') + max|x|) / 2   — nbody/tools.py:22
+__device__ double warp_maxavg(const double* x, int n, int lane) {
+    double mx = 0.0;
+    for (int i = lane; i < n; i += 32) mx = fmax(mx, fabs(x[i]));
+    mx = warp_max(mx);
+    const double pos = 0.75 * (double)(n - 1);
+    const int lo = (int)floor(pos);
+    const double frac = pos - (double)lo;
+    const double vlo = warp_kth_abs(x, n, lo, lane);
+    double p75 = vlo;
+    if (lo + 1 < n) {
+        const double vhi = warp_kth_abs(x, n, lo + 1, lane);
+        p75 = vlo + (vhi - vlo) * frac;
+    }
+    return 0.5 * (p75 + mx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_integrate: the hot kernel
+// ---------------------------------------------------------------------------------------------
+#define NBT_BLOCK 64
+
+template <int NP>
+__global__ void __launch_bounds__(NBT_BLOCK) k_integrate(const nbt_run_args A) {
+    const int g = blockIdx.x * NBT_BLOCK + threadIdx.x;
+    if (g >= A.B) return;
+    const int sys = (A.order != nullptr) ? A.order[g] : g;
+    nbt_simulate_system<NP>(A, sys);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fit: linear ephemeris + O-C + maxavg, one warp per (system, planet)
+// ---------------------------------------------------------------------------------------------
+struct nbt_fit_args {
+    const double* params;
+    const int64_t* tt_offsets;
+    const double* tt;
+    const int32_t* n_tt;
+    double* ttv; double* period; double* t0; double* ttv_max;
+    int32_t* status;
+    int32_t B, Np, flags;
+};
+
+__global__ void __launch_bounds__(128) k_fit(const nbt_fit_args F) {
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= F.B * F.Np) return;
+    const int sys = w / F.Np, j = w % F.Np;
+    const double Pj = F.params[((size_t)sys * (F.Np + 1) + j + 1) * NBT_NPAR + NBT_P_P];
+    if ((F.flags & NBT_F_PLANET1_ONLY) && j > 0) {
+        if (lane == 0) { F.period[w] = Pj; F.t0[w] = 0.0; F.ttv_max[w] = 0.0; }
+        return;
+    }
+    const int64_t off = F.tt_offsets[w];
+    const int cap = (int)(F.tt_offsets[w + 1] - off);
+    const int n = min(F.n_tt[w], cap);
+    const double* tt = F.tt + off;
+    double* ttv = F.ttv + off;
+    if (n >= 3) {
+        // least squares of tt on k = 0..n-1, centred (what np.linalg.lstsq solves, simulation.py:172-177)
+        double st = 0.0;
+        for (int k = lane; k < n; k += 32) st += tt[k];
+        const double tbar = warp_sum(st) / (double)n;
+        const double kbar = 0.5 * (double)(n - 1);
+        double skk = 0.0, skt = 0.0;
+        for (int k = lane; k < n; k += 32) {
+            const double dk = (double)k - kbar;
+            skk = fma(dk, dk, skk);
+            skt = fma(dk, tt[k] - tbar, skt);
+        }
+        skk = warp_sum(skk); skt = warp_sum(skt);
+        const double m = skt / skk;
+        const double b = tbar - m * kbar;
+        for (int k = lane; k < n; k += 32) ttv[k] = tt[k] - m * (double)k - b;
+        __syncwarp();
+        const double mx = warp_maxavg(ttv, n, lane);
+        if (lane == 0) { F.period[w] = m; F.t0[w] = b; F.ttv_max[w] = mx; }
+    } else if (lane == 0) { // simulation.py:207-210: per = objects[j]['P'], t0 = 0, ttv = [0]
+        atomicOr(&F.status[sys], NBT_S_FEW_TRANSITS);
+        F.period[w] = Pj; F.t0[w] = 0.0; F.ttv_max[w] = 0.0;
+        for (int k = 0; k < max(n, 1) && k < cap; k++) ttv[k] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Floating-mean (generalised) Lomb-Scargle, standard normalisation, unit weights
+// (astropy LombScargle(t, y).power(f) exact methods [3P]; nbody/tools.py:97-104).
+// One pass, six sums; for uniformly sampled series the phasors advance by a complex rotation
+// (2 DMUL + 2 DFMA) and are re-seeded exactly every NBT_LS_RESYNC samples.
+// ---------------------------------------------------------------------------------------------
+#define NBT_LS_RESYNC 64
+
+__device__ __forceinline__ double ls_finish(double C, double S, double C2, double S2, double YC, double YS,
+                                            double invn, double YY) {
+    C *= invn; S *= invn; C2 *= invn; S2 *= 2.0 * invn; YC *= invn; YS *= invn;
+    const double S2p = S2 - 2.0 * S * C;
+    const double C2p = C2 - (C * C - S * S);
+    const double omtau = 0.5 * atan2(S2p, C2p);
+    double st, ct;
+    sincos(omtau, &st, &ct);
+    const double c2t = ct * ct - st * st, s2t = 2.0 * st * ct;
+    const double YCt = YC * ct + YS * st, YSt = YS * ct - YC * st;
+    const double Ct = C * ct + S * st, St = S * ct - C * st;
+    const double rot = C2 * c2t + S2 * s2t;
+    const double CC = 0.5 * (1.0 + rot) - Ct * Ct;
+    const double SS = 0.5 * (1.0 - rot) - St * St;
+    return (YCt * YCt / CC + YSt * YSt / SS) / YY;
+}
+
+// y: n samples at t_i = i (arbitrary origin/scale folded into nu = cycles per sample)
+__device__ double ls_power_uniform(const double* __restrict__ y, int n, double ybar, double YY, double nu) {
+    double sd, cd;
+    sincospi(2.0 * nu, &sd, &cd);
+    double C = 0, S = 0, C2 = 0, S2 = 0, YC = 0, YS = 0;
+    for (int i0 = 0; i0 < n; i0 += NBT_LS_RESYNC) {
+        double s, c;
+        sincospi(2.0 * nu * (double)i0, &s, &c);
+        const int i1 = min(n, i0 + NBT_LS_RESYNC);
+        for (int i = i0; i < i1; i++) {
+            const double yi = y[i] - ybar;
+            C += c; S += s;
+            C2 = fma(c, c, fma(-s, s, C2));
+            S2 = fma(s, c, S2);
+            YC = fma(yi, c, YC); YS = fma(yi, s, YS);
+            const double cn = fma(c, cd, -s * sd);
+            s = fma(s, cd, c * sd);
+            c = cn;
+        }
+    }
+    return ls_finish(C, S, C2, S2, YC, YS, 1.0 / (double)n, YY);
+}
+
+__device__ double ls_power_times(const double* __restrict__ t, const double* __restrict__ y, int n, double ybar,
+                                 double YY, double f) {
+    double C = 0, S = 0, C2 = 0, S2 = 0, YC = 0, YS = 0;
+    for (int i = 0; i < n; i++) {
+        double s, c;
+        sincospi(2.0 * (f * t[i]), &s, &c);
+        const double yi = y[i] - ybar;
+        C += c; S += s;
+        C2 = fma(c, c, fma(-s, s, C2));
+        S2 = fma(s, c, S2);
+        YC = fma(yi, c, YC); YS = fma(yi, s, YS);
+    }
+    return ls_finish(C, S, C2, S2, YC, YS, 1.0 / (double)n, YY);
+}
+
+__device__ __forceinline__ void warp_mean_var(const double* __restrict__ y, int n, int lane, double& ybar, double& YY) {
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += y[i];
+    ybar = warp_sum(s) / (double)n;
+    double q = 0.0;
+    for (int i = lane; i < n; i += 32) { const double d = y[i] - ybar; q = fma(d, d, q); }
+    YY = warp_sum(q) / (double)n;
+}
+
+__device__ __forceinline__ double ls_df(double baseline, int spp) { return 1.0 / baseline / (double)spp; }
+__device__ __forceinline__ long long ls_nfreq(double baseline, double fmin, double fmax, int spp) {
+    return 1 + (long long)rint((fmax - fmin) / ls_df(baseline, spp));
+}
+
+struct nbt_lsoc_args {
+    const int64_t* tt_offsets; const int64_t* ls_offsets;
+    const double* ttv; const int32_t* n_tt;
+    double* power; int32_t* nfreq;
+    int32_t B, Np, flags, spp;
+    double fmin, fmax;
+};
+
+__global__ void __launch_bounds__(128) k_ls_oc(const nbt_lsoc_args L) {
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= L.B * L.Np) return;
+    const int j = w % L.Np;
+    const int64_t off = L.tt_offsets[w];
+    const int cap = (int)(L.tt_offsets[w + 1] - off);
+    const int n = min(L.n_tt[w], cap);
+    if (n < 3 || ((L.flags & NBT_F_PLANET1_ONLY) && j > 0)) {
+        if (lane == 0) L.nfreq[w] = 0;
+        return;
+    }
+    const int64_t loff = L.ls_offsets[w];
+    const long long lcap = L.ls_offsets[w + 1] - loff;
+    const double T = (double)(n - 1); // epochs = arange(n)
+    long long nf = ls_nfreq(T, L.fmin, L.fmax, L.spp);
+    if (nf > lcap) nf = lcap;
+    const double df = ls_df(T, L.spp);
+    const double* y = L.ttv + off;
+    double ybar, YY;
+    warp_mean_var(y, n, lane, ybar, YY);
+    for (long long k = lane; k < nf; k += 32)
+        L.power[loff + k] = ls_power_uniform(y, n, ybar, YY, L.fmin + (double)k * df);
+    if (lane == 0) L.nfreq[w] = (int32_t)nf;
+}
+
+// generic batched periodogram: one warp per (series, chunk of 32 frequencies)
+__global__ void __launch_bounds__(128) k_ls_series(const double* __restrict__ t, const double* __restrict__ y,
+                                                   long long n_series, int n, double f0, double df,
+                                                   long long n_freq, double tscale, double* __restrict__ power) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long chunks = (n_freq + 31) / 32;
+    if (w >= n_series * chunks) return;
+    const long long s = w / chunks, ch = w % chunks;
+    const double* ys = y + s * (long long)n;
+    double ybar, YY;
+    warp_mean_var(ys, n, lane, ybar, YY);
+    const long long k = ch * 32 + lane;
+    if (k >= n_freq) return;
+    const double f = f0 + (double)k * df;
+    power[s * n_freq + k] = (t != nullptr) ? ls_power_times(t + s * (long long)n, ys, n, ybar, YY, f)
+                                           : ls_power_uniform(ys, n, ybar, YY, f * tscale);
+}
+
+// [rows][cols] -> [cols][rows] through a padded shared tile (coalesced both ways)
+__global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, int rows, int cols) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int rr = r0 + r, cc = c0 + threadIdx.x;
+        if (rr < rows && cc < cols) tile[r][threadIdx.x] = in[(size_t)rr * cols + cc];
+    }
+    __syncthreads();
+    for (int c = threadIdx.y; c < 32; c += blockDim.y) {
+        const int cc = c0 + c, rr = r0 + threadIdx.x;
+        if (rr < rows && cc < cols) out[(size_t)cc * rows + rr] = tile[threadIdx.x][c];
+    }
+}
+
+__global__ void __launch_bounds__(128) k_rv_max(const double* __restrict__ rv_sm, int B, int n, double* __restrict__ rv_max) {
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= B) return;
+    const double mx = warp_maxavg(rv_sm + (size_t)w * n, n, lane);
+    if (lane == 0) rv_max[w] = mx;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone forms of the reference's array functions (same arithmetic as the fused path)
+// ---------------------------------------------------------------------------------------------
+// transit_times(xp, xs, times): nbody/simulation.py:163-170 + tools.py:61-65, one thread per series
+__global__ void k_transit_times(const double* __restrict__ xp, const double* __restrict__ xs,
+                                const double* __restrict__ times, long long n_series, long long n,
+                                double* __restrict__ tt, int32_t* __restrict__ n_tt, long long cap, int times_shared) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_series) return;
+    const double* a = xp + s * n; const double* b = xs + s * n;
+    const double* t = times_shared ? times : times + s * n;
+    double prev = a[0] - b[0];
+    int c = 0;
+    for (long long i = 1; i < n; i++) {
+        const double cur = a[i] - b[i];
+        if (prev >= 0.0 && cur <= 0.0) {
+            const double m = (cur - prev) / (t[i] - t[i - 1]);
+            const double t0 = -prev / m + t[i - 1];
+            if (c < cap) tt[s * cap + c] = t0;
+            c++;
+        }
+        prev = cur;
+    }
+    n_tt[s] = c;
+}
+
+// find_zero(t1, dx1, t2, dx2), elementwise: nbody/tools.py:61-65
+__global__ void k_find_zero(const double* __restrict__ t1, const double* __restrict__ dx1,
+                            const double* __restrict__ t2, const double* __restrict__ dx2, long long n,
+                            double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = (dx2[i] - dx1[i]) / (t2[i] - t1[i]);
+    out[i] = -dx1[i] / m + t1[i];
+}
+
+// TTV(epochs, tt): least squares tt ~ b + m*epoch, one warp per series (nbody/simulation.py:172-177)
+__global__ void __launch_bounds__(128) k_ttv_fit(const double* __restrict__ epochs, const double* __restrict__ tt,
+                                                 long long n_series, int n, double* __restrict__ ttv,
+                                                 double* __restrict__ slope, double* __restrict__ icpt) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_series) return;
+    const double* t = tt + w * n;
+    const double* ep = epochs ? epochs + w * n : nullptr;
+    double st = 0.0, sk = 0.0;
+    for (int k = lane; k < n; k += 32) { st += t[k]; sk += ep ? ep[k] : (double)k; }
+    const double tbar = warp_sum(st) / (double)n, kbar = warp_sum(sk) / (double)n;
+    double skk = 0.0, skt = 0.0;
+    for (int k = lane; k < n; k += 32) {
+        const double dk = (ep ? ep[k] : (double)k) - kbar;
+        skk = fma(dk, dk, skk);
+        skt = fma(dk, t[k] - tbar, skt);
+    }
+    skk = warp_sum(skk); skt = warp_sum(skt);
+    const double m = (skk > 0.0) ? skt / skk : 0.0; // rank-deficient (n == 1): minimum-norm solution of lstsq
+    const double b = tbar - m * kbar;
+    for (int k = lane; k < n; k += 32) ttv[w * n + k] = t[k] - m * (ep ? ep[k] : (double)k) - b;
+    if (lane == 0) { slope[w] = m; icpt[w] = b; }
+}
+
+__global__ void __launch_bounds__(128) k_maxavg(const double* __restrict__ x, long long n_series, int n,
+                                                double* __restrict__ out) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_series) return;
+    const double v = warp_maxavg(x + w * n, n, lane);
+    if (lane == 0) out[w] = v;
+}
+
+// analyze() front end on a recorded sim_data series (nbody/simulation.py:179-231): one thread per
+// (system, planet) scans the time-major series [n_outputs][B][3+10*Np] and produces what
+// k_integrate produces in-flight: transit times, element means, RV, orbit samples.
+struct nbt_scan_args {
+    const double* series; const double* times; const int64_t* tt_offsets;
+    double* tt; int32_t* n_tt; double* mean_a; double* mean_e; double* mean_inc; double* mean_omega;
+    int32_t* status; double* rv; double* orbit_xz;
+    int32_t B, Np, n_outputs, flags, orbit_stride;
+    double rv_scale;
+};
+
+__global__ void __launch_bounds__(128) k_scan_series(const nbt_scan_args A) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)A.B * A.Np) return;
+    const int sys = (int)(g / A.Np), j = (int)(g % A.Np);
+    const int W = 3 + 10 * A.Np, NO = A.n_outputs;
+    const size_t rowstride = (size_t)A.B * W;
+    const double* base = A.series + (size_t)sys * W;
+    const double* pj = base + 3 + 10 * j;
+    const bool tt_on = !((A.flags & NBT_F_PLANET1_ONLY) && j > 0);
+    const bool want_means = (A.flags & NBT_F_MEANS) != 0;
+    const bool want_rv = (A.flags & NBT_F_RV) != 0 && A.rv != nullptr && j == 0;
+    const bool want_orbit = (A.flags & NBT_F_ORBIT) != 0 && A.orbit_xz != nullptr;
+    const int64_t off = A.tt_offsets[g];
+    const int cap = (int)(A.tt_offsets[g + 1] - off);
+    double sa = 0, se = 0, si = 0, so = 0;
+    double prev = 0, xs_prev = 0, t_prev = 0;
+    int cnt = 0, status = 0;
+    for (int o = 0; o < NO; o++) {
+        const double* star = base + (size_t)o * rowstride;
+        const double* p = pj + (size_t)o * rowstride;
+        const double xs = star[0], t = A.times[o];
+        const double cur = p[0] - xs;
+        if (o > 0) {
+            if (tt_on && prev >= 0.0 && cur <= 0.0) {
+                const double m = (cur - prev) / (t - t_prev);
+                const double t0 = -prev / m + t_prev;
+                if (cnt < cap) A.tt[off + cnt] = t0; else status |= NBT_S_TT_OVERFLOW;
+                cnt++;
+            }
+            if (want_rv) A.rv[(size_t)(o - 1) * A.B + sys] = (xs - xs_prev) * A.rv_scale;
+        }
+        prev = cur; xs_prev = xs; t_prev = t;
+        if (want_means) {
+            sa += p[4]; se += p[5]; si += p[6]; so += p[8];
+            if (!(p[4] > 0.0)) status |= NBT_S_UNBOUND;
+            if (!isfinite(p[0] + p[1] + p[2] + p[4] + p[5])) status |= NBT_S_NONFINITE;
+        }
+        if (want_orbit && (o % A.orbit_stride) == 0) {
+            double* dst = A.orbit_xz + (((size_t)(o / A.orbit_stride) * A.B + sys) * A.Np + j) * 2;
+            dst[0] = p[0]; dst[1] = p[2];
+        }
+    }
+    A.n_tt[g] = cnt;
+    if (want_means) {
+        const double inv = 1.0 / (double)NO;
+        A.mean_a[g] = sa * inv; A.mean_e[g] = se * inv; A.mean_inc[g] = si * inv;
+        if (A.mean_omega) A.mean_omega[g] = so * inv;
+    }
+    if (status) atomicOr(&A.status[sys], status);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_chi2: nbody/nested.py:85-95, one thread per forward model
+// ---------------------------------------------------------------------------------------------
+__global__ void k_chi2(const double* __restrict__ ttv, const int64_t* __restrict__ tt_offsets,
+                       const int32_t* __restrict__ n_tt, int B, int Np, const double* __restrict__ c0,
+                       const double* __restrict__ c1, const double* __restrict__ x,
+                       const double* __restrict__ y, const double* __restrict__ yerr, int n_data,
+                       double* __restrict__ loglike) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int64_t off = tt_offsets[(size_t)b * Np];
+    const int cap = (int)(tt_offsets[(size_t)b * Np + 1] - off);
+    const int n = min(n_tt[(size_t)b * Np], cap);
+    const double* tv = ttv + off;
+    const double a0 = c0[b], a1 = c1[b];
+    bool ok = true;
+    for (int i = 0; i < n_data; i++) { const int k = (int)x[i]; if (k >= n || k < -n) ok = false; }
+    double s = 0.0;
+    if (ok) {
+        for (int i = 0; i < n_data; i++) {
+            int k = (int)x[i]; if (k < 0) k += n;
+            const double r = (y[i] - (a1 * x[i] + a0) - tv[k]) / yerr[i];
+            s = fma(r, r, s);
+        }
+        loglike[b] = -0.5 * s;
+    } else { // IndexError branch: -10 * sum over the ttv that exist, paired index-for-index
+        for (int i = 0; i < n && i < n_data; i++) {
+            const double r = (y[i] - (a1 * x[i] + a0) - tv[i]) / yerr[i];
+            s = fma(r, r, s);
+        }
+        loglike[b] = -10.0 * s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_dfma_peak: 8 independent DFMA chains per thread — the measured FP64 roofline denominator
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+    double v0 = threadIdx.x * 1e-9, v1 = v0 + 1e-3, v2 = v0 + 2e-3, v3 = v0 + 3e-3, v4 = v0 + 4e-3,
+           v5 = v0 + 5e-3, v6 = v0 + 6e-3, v7 = v0 + 7e-3;
+    for (int i = 0; i < iters; i++) {
+        v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+        v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+    }
+    const double r = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+    if (r == 12345.678) out[0] = r; // never true; keeps the chains alive
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------
+static int scheme_stages(int id) {
+    switch (id) {
+    case NBT_SCHEME_WH2: return 1;
+    case NBT_SCHEME_Y4: return 3;
+    case NBT_SCHEME_SABA4: return 4;
+    case NBT_SCHEME_M64: return 4;
+    default: return -1;
+    }
+}
+
+static int check_cfg(const nbt_config* cfg) {
+    if (!cfg) return nbt_fail(-1, "cfg is NULL");
+    if (cfg->struct_size != (int32_t)sizeof(nbt_config))
+        return nbt_fail(-2, "nbt_config.struct_size %d != %d (ABI mismatch)", cfg->struct_size, (int)sizeof(nbt_config));
+    if (cfg->n_systems < 0) return nbt_fail(-3, "n_systems < 0");
+    if (cfg->n_bodies < 2 || cfg->n_bodies > NBT_MAX_BODIES) return nbt_fail(-4, "n_bodies must be in 2..%d", NBT_MAX_BODIES);
+    if (cfg->n_outputs < 2) return nbt_fail(-5, "n_outputs must be >= 2");
+    if (!(cfg->n_days > 0.0)) return nbt_fail(-6, "n_days must be > 0");
+    if (scheme_stages(cfg->scheme) < 0) return nbt_fail(-7, "unknown scheme %d", cfg->scheme);
+    if (cfg->tt_mode != NBT_TT_GRID_LINEAR && cfg->tt_mode != NBT_TT_REFINED) return nbt_fail(-8, "unknown tt_mode");
+    return 0;
+}
+
+template <int NP>
+static cudaError_t launch_integrate(const nbt_run_args& A, cudaStream_t st) {
+    const int grid = (A.B + NBT_BLOCK - 1) / NBT_BLOCK;
+    k_integrate<NP><<<grid, NBT_BLOCK, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_integrate_np(int np, const nbt_run_args& A, cudaStream_t st) {
+    switch (np) {
+    case 1: return launch_integrate<1>(A, st);
+    case 2: return launch_integrate<2>(A, st);
+    case 3: return launch_integrate<3>(A, st);
+    case 4: return launch_integrate<4>(A, st);
+    case 5: return launch_integrate<5>(A, st);
+    case 6: return launch_integrate<6>(A, st);
+    case 7: return launch_integrate<7>(A, st);
+    case 8: return launch_integrate<8>(A, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+static std::mutex g_pool_mu;
+static bool g_pool_ready[64] = {false};
+
+static void ensure_pool(int dev) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (dev < 0 || dev >= 64 || g_pool_ready[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX; // keep freed blocks: repeated calls (sampler callbacks) reuse them
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    g_pool_ready[dev] = true;
+}
+
+// Optional in-stream kernel timing (cfg.flags & NBT_F_TIMING): CUDA events recorded on the launch
+// stream around each stage of the last nbt_run of this thread; read back with nbt_timing().
+struct TimingState {
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool have = false; int device = -1;
+};
+static thread_local TimingState g_timing;
+
+static void timing_mark(int i, bool on, cudaStream_t st) {
+    if (!on) return;
+    if (!g_timing.ev[i]) cudaEventCreate(&g_timing.ev[i]);
+    cudaEventRecord(g_timing.ev[i], st);
+}
+
+// bump allocator over one stream-ordered allocation
+struct Arena {
+    char* base = nullptr; size_t size = 0, used = 0;
+    size_t reserve(size_t bytes) { size_t o = size; size += (bytes + 255) & ~(size_t)255; return o; }
+};
+
+// Enqueue every kernel of the path on `st`.  All pointers are device pointers.
+// scan_series/scan_times != NULL: analyze() mode — the front end scans a recorded series
+// (k_scan_series) instead of integrating (k_integrate).
+static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, const nbt_outputs* out,
+                                double* rv_sm_ws, cudaStream_t st, const double* scan_series = nullptr,
+                                const double* scan_times = nullptr, double scan_dt = 0.0) {
+    const int B = cfg->n_systems, Np = cfg->n_bodies - 1, NO = cfg->n_outputs;
+    if (B == 0) return cudaSuccess;
+    cudaError_t e;
+    const bool tim = (cfg->flags & NBT_F_TIMING) != 0;
+    if (tim) { g_timing.have = true; g_timing.device = cfg->device; }
+    timing_mark(0, tim, st);
+    if (scan_series == nullptr) {
+        nbt_run_args A;
+        memset(&A, 0, sizeof A);
+        A.params = in->params; A.substeps = (cfg->substeps > 0) ? nullptr : in->substeps; A.order = in->order;
+        A.tt_offsets = in->tt_offsets;
+        A.tt = out->tt; A.n_tt = out->n_tt; A.mean_a = out->mean_a; A.mean_e = out->mean_e;
+        A.mean_inc = out->mean_inc; A.mean_omega = out->mean_omega; A.status = out->status;
+        A.rv = out->rv; A.orbit_xz = out->orbit_xz; A.series = out->series;
+        A.B = B; A.n_outputs = NO; A.substeps_all = cfg->substeps; A.tt_mode = cfg->tt_mode; A.flags = cfg->flags;
+        A.orbit_stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
+        A.n_days = cfg->n_days; A.scheme = nbt_make_scheme(cfg->scheme);
+        e = launch_integrate_np(Np, A, st);
+        if (e != cudaSuccess) return e;
+    } else {
+        nbt_scan_args S;
+        memset(&S, 0, sizeof S);
+        S.series = scan_series; S.times = scan_times; S.tt_offsets = in->tt_offsets;
+        S.tt = out->tt; S.n_tt = out->n_tt; S.mean_a = out->mean_a; S.mean_e = out->mean_e;
+        S.mean_inc = out->mean_inc; S.mean_omega = out->mean_omega; S.status = out->status;
+        S.rv = out->rv; S.orbit_xz = out->orbit_xz;
+        S.B = B; S.Np = Np; S.n_outputs = NO; S.flags = cfg->flags;
+        S.orbit_stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
+        S.rv_scale = 1.496e11 * scan_dt; // simulation.py:186
+        if ((e = cudaMemsetAsync(out->status, 0, (size_t)B * 4, st)) != cudaSuccess) return e;
+        const long long nt = (long long)B * Np;
+        k_scan_series<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(S);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+
+    timing_mark(1, tim, st);
+    const long long nw = (long long)B * Np;
+    const int fit_grid = (int)((nw * 32 + 127) / 128);
+    nbt_fit_args F;
+    F.params = in->params; F.tt_offsets = in->tt_offsets; F.tt = out->tt; F.n_tt = out->n_tt;
+    F.ttv = out->ttv; F.period = out->period; F.t0 = out->t0; F.ttv_max = out->ttv_max; F.status = out->status;
+    F.B = B; F.Np = Np; F.flags = cfg->flags;
+    k_fit<<<fit_grid, 128, 0, st>>>(F);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    timing_mark(2, tim, st);
+
+    if ((cfg->flags & NBT_F_LS_OC) && out->ls_oc_power && in->ls_offsets) {
+        nbt_lsoc_args L;
+        L.tt_offsets = in->tt_offsets; L.ls_offsets = in->ls_offsets; L.ttv = out->ttv; L.n_tt = out->n_tt;
+        L.power = out->ls_oc_power; L.nfreq = out->ls_oc_nfreq; L.B = B; L.Np = Np; L.flags = cfg->flags;
+        L.spp = cfg->ls_samples_per_peak; L.fmin = cfg->ls_oc_minfreq; L.fmax = cfg->ls_oc_maxfreq;
+        k_ls_oc<<<fit_grid, 128, 0, st>>>(L);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    timing_mark(3, tim, st);
+    if ((cfg->flags & NBT_F_RV) && out->rv && rv_sm_ws && (out->rv_max || ((cfg->flags & NBT_F_LS_RV) && out->ls_rv_power))) {
+        const int n = NO - 1;
+        dim3 tb(32, 8), tg((B + 31) / 32, (n + 31) / 32);
+        k_transpose<<<tg, tb, 0, st>>>(out->rv, rv_sm_ws, n, B);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (out->rv_max) {
+            k_rv_max<<<(int)(((long long)B * 32 + 127) / 128), 128, 0, st>>>(rv_sm_ws, B, n, out->rv_max);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+        if ((cfg->flags & NBT_F_LS_RV) && out->ls_rv_power) {
+            // times[1:] is uniform with spacing `step`; the periodogram is invariant under a time
+            // shift, so t_i = i*step and nu = f*step cycles per sample (simulation.py:186-188).
+            // (analyze mode makes the same assumption: cfg.n_days / n_outputs describe m['times'].)
+            const double step = cfg->n_days / (double)(NO - 1);
+            const double T = cfg->n_days - 1.0 * step;
+            const double df = 1.0 / T / (double)cfg->ls_samples_per_peak;
+            const long long nf = nbt_ls_nfreq(T, cfg->ls_rv_minfreq, cfg->ls_rv_maxfreq, cfg->ls_samples_per_peak);
+            const long long chunks = (nf + 31) / 32;
+            const long long warps = (long long)B * chunks;
+            k_ls_series<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(nullptr, rv_sm_ws, B, n, cfg->ls_rv_minfreq,
+                                                                            df, nf, step, out->ls_rv_power);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+    }
+    timing_mark(4, tim, st);
+    return cudaSuccess;
+}
+
+extern "C" {
+
+int nbt_abi_version(void) { return NBT_ABI_VERSION; }
+
+int nbt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* nbt_last_error(void) { return g_err.c_str(); }
+
+int64_t nbt_ls_nfreq(double baseline, double minfreq, double maxfreq, int spp) {
+    if (!(baseline > 0.0) || spp <= 0) return 0;
+    const double df = 1.0 / baseline / (double)spp;
+    return 1 + (int64_t)rint((maxfreq - minfreq) / df);
+}
+
+int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!params || !tt_offsets) return nbt_fail(-10, "nbt_plan_tt: NULL argument");
+    const int B = cfg->n_systems, N = cfg->n_bodies, Np = N - 1;
+    int64_t off = 0, capmax = 1;
+    for (int b = 0; b < B; b++)
+        for (int j = 0; j < Np; j++) {
+            tt_offsets[(size_t)b * Np + j] = off;
+            const double P = params[((size_t)b * N + j + 1) * NBT_NPAR + NBT_P_P];
+            int64_t cap = 3;
+            if (P > 0.0 && std::isfinite(P)) {
+                double c = ceil(1.05 * cfg->n_days / P) + 3.0;
+                if (c > (double)cfg->n_outputs) c = (double)cfg->n_outputs; // at most one transit per interval
+                cap = (int64_t)c;
+            }
+            if ((cfg->flags & NBT_F_PLANET1_ONLY) && j > 0) cap = 1;
+            off += cap;
+            capmax = std::max(capmax, cap);
+        }
+    tt_offsets[(size_t)B * Np] = off;
+    if (capmax > INT32_MAX) return nbt_fail(-11, "tt capacity overflow");
+    return (int)capmax;
+}
+
+int nbt_plan_order(const nbt_config* cfg, const int32_t* substeps, int32_t* order) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!substeps || !order) return nbt_fail(-10, "nbt_plan_order: NULL argument");
+    std::iota(order, order + cfg->n_systems, 0);
+    std::stable_sort(order, order + cfg->n_systems, [&](int32_t a, int32_t b) { return substeps[a] > substeps[b]; });
+    return 0;
+}
+
+int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!tt_offsets || !ls_offsets) return nbt_fail(-10, "nbt_plan_ls: NULL argument");
+    const int64_t n = (int64_t)cfg->n_systems * (cfg->n_bodies - 1);
+    int64_t off = 0;
+    for (int64_t i = 0; i < n; i++) {
+        ls_offsets[i] = off;
+        const int64_t cap = tt_offsets[i + 1] - tt_offsets[i];
+        off += (cap >= 3) ? nbt_ls_nfreq((double)(cap - 1), cfg->ls_oc_minfreq, cfg->ls_oc_maxfreq, cfg->ls_samples_per_peak) : 0;
+    }
+    ls_offsets[n] = off;
+    return 0;
+}
+
+/* Sub-step rule, calibrated against the oracle (tools/calibrate_substeps.py).
+ * The binding tolerance is the orbit-averaged e to 1e-8 relative.  The composition error scales
+ * with (dt_sub / P_innermost)^order and with the interaction strength, so
+ *     k = ceil(step * R(scheme) * g / P_min),   g = 2 if any adjacent pair is closer than
+ * 6 mutual Hill radii (strongly interacting, mostly short-lived systems), else 1. */
+int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* substeps) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!params || !substeps) return nbt_fail(-10, "nbt_plan_substeps: NULL argument");
+    static const double R[NBT_SCHEME_COUNT] = {8000.0, 400.0, 800.0, 60.0}; /* P_min / dt_sub */
+    const int B = cfg->n_systems, N = cfg->n_bodies;
+    const double step = cfg->n_days / (double)(cfg->n_outputs - 1);
+    for (int b = 0; b < B; b++) {
+        const double* par = params + (size_t)b * N * NBT_NPAR;
+        const double Ms = par[NBT_P_M];
+        double pmin = INFINITY, g = 1.0;
+        for (int j = 1; j < N; j++) {
+            const double P = par[j * NBT_NPAR + NBT_P_P];
+            if (P > 0.0 && P < pmin) pmin = P;
+            for (int i = 1; i < j; i++) { /* mutual Hill separation of every pair (a ~ P^(2/3)) */
+                const double Pi = par[i * NBT_NPAR + NBT_P_P];
+                if (!(P > 0.0) || !(Pi > 0.0) || !(Ms > 0.0)) continue;
+                const double ai = cbrt(Pi * Pi), aj = cbrt(P * P);
+                const double rh = cbrt((par[i * NBT_NPAR + NBT_P_M] + par[j * NBT_NPAR + NBT_P_M]) / (3.0 * Ms)) * 0.5 * (ai + aj);
+                if (fabs(aj - ai) < 6.0 * rh) g = 2.0;
+            }
+        }
+        double k = std::isfinite(pmin) ? ceil(step * R[cfg->scheme] * g / pmin) : 1.0;
+        if (!(k >= 1.0)) k = 1.0;
+        if (k > 65536.0) k = 65536.0;
+        substeps[b] = (int32_t)k;
+    }
+    return 0;
+}
+
+int64_t nbt_count_steps(const nbt_config* cfg, const int32_t* substeps) {
+    if (check_cfg(cfg)) return -1;
+    const int64_t S = scheme_stages(cfg->scheme), per = (int64_t)cfg->n_outputs - 1;
+    if (cfg->substeps > 0 || !substeps) return (int64_t)cfg->n_systems * per * S * std::max(cfg->substeps, 1);
+    int64_t tot = 0;
+    for (int b = 0; b < cfg->n_systems; b++) tot += (int64_t)substeps[b];
+    return tot * per * S;
+}
+
+static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, void* cuda_stream,
+                    const double* scan_series, const double* scan_times, double scan_dt) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!in || !out) return nbt_fail(-10, "nbt_run: NULL inputs/outputs");
+    const bool scan = scan_series != nullptr;
+    if (scan && !scan_times) return nbt_fail(-10, "nbt_analyze: times is required");
+    if (!in->params || !in->tt_offsets) return nbt_fail(-10, "nbt_run: params and tt_offsets are required");
+    if (!out->tt || !out->ttv || !out->n_tt || !out->period || !out->t0 || !out->ttv_max || !out->status)
+        return nbt_fail(-10, "nbt_run: tt, ttv, n_tt, period, t0, ttv_max, status are required");
+    if ((cfg->flags & NBT_F_MEANS) && (!out->mean_a || !out->mean_e || !out->mean_inc))
+        return nbt_fail(-10, "nbt_run: NBT_F_MEANS needs mean_a, mean_e, mean_inc");
+    if (!scan && cfg->substeps <= 0 && !in->substeps) return nbt_fail(-12, "nbt_run: cfg.substeps <= 0 needs inputs.substeps");
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_run: no CUDA device (there is no CPU fallback)");
+    const int B = cfg->n_systems, N = cfg->n_bodies, Np = N - 1, NO = cfg->n_outputs;
+    if (B == 0) return 0;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamPerThread;
+    char* arena = nullptr;
+    double* rv_ws = nullptr;
+    NBT_CUDA(cudaSetDevice(cfg->device));
+    ensure_pool(cfg->device);
+    {
+        const bool need_rv_ws = (cfg->flags & NBT_F_RV) && out->rv && (out->rv_max || ((cfg->flags & NBT_F_LS_RV) && out->ls_rv_power));
+        const size_t rv_elems = (size_t)(NO - 1) * B;
+        if (cfg->flags & NBT_F_DEVICE_PTRS) {
+            if (need_rv_ws) NBT_CUDA(cudaMallocAsync((void**)&rv_ws, rv_elems * 8, st));
+            NBT_CUDA(enqueue_path(cfg, in, out, rv_ws, st, scan_series, scan_times, scan_dt));
+            if (rv_ws) NBT_CUDA(cudaFreeAsync(rv_ws, st));
+            rv_ws = nullptr;
+            goto done;
+        }
+        // host pointers: stage through one stream-ordered arena
+        const int64_t nsp = (int64_t)B * Np;
+        const int64_t ntt = in->tt_offsets[nsp];
+        const int64_t nls = (in->ls_offsets && (cfg->flags & NBT_F_LS_OC)) ? in->ls_offsets[nsp] : 0;
+        const int W = 3 + 10 * Np;
+        const int stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
+        const size_t nq = (size_t)(NO + stride - 1) / stride;
+        const int64_t nf_rv = (cfg->flags & NBT_F_LS_RV)
+                                  ? nbt_ls_nfreq(cfg->n_days - cfg->n_days / (double)(NO - 1), cfg->ls_rv_minfreq,
+                                                 cfg->ls_rv_maxfreq, cfg->ls_samples_per_peak) : 0;
+        Arena ar;
+        struct Buf { size_t off, bytes; const void* h_in; void* h_out; };
+        auto mk = [&](size_t bytes, const void* hin, void* hout, bool enabled) {
+            Buf b{0, 0, nullptr, nullptr};
+            if (enabled && bytes > 0) { b.off = ar.reserve(bytes); b.bytes = bytes; b.h_in = hin; b.h_out = hout; }
+            return b;
+        };
+        const int fl = cfg->flags;
+        Buf b_params = mk((size_t)B * N * NBT_NPAR * 8, in->params, nullptr, true);
+        Buf b_sub = mk((size_t)B * 4, in->substeps, nullptr, !scan && cfg->substeps <= 0);
+        Buf b_order = mk((size_t)B * 4, in->order, nullptr, !scan && in->order != nullptr);
+        Buf b_times = mk((size_t)NO * 8, scan_times, nullptr, scan);
+        Buf b_tto = mk((size_t)(nsp + 1) * 8, in->tt_offsets, nullptr, true);
+        Buf b_lso = mk((size_t)(nsp + 1) * 8, in->ls_offsets, nullptr, nls > 0);
+        Buf b_tt = mk((size_t)ntt * 8, nullptr, out->tt, true);
+        Buf b_ttv = mk((size_t)ntt * 8, nullptr, out->ttv, true);
+        Buf b_ntt = mk((size_t)nsp * 4, nullptr, out->n_tt, true);
+        Buf b_per = mk((size_t)nsp * 8, nullptr, out->period, true);
+        Buf b_t0 = mk((size_t)nsp * 8, nullptr, out->t0, true);
+        Buf b_max = mk((size_t)nsp * 8, nullptr, out->ttv_max, true);
+        const bool means = (fl & (NBT_F_MEANS | NBT_F_SERIES)) != 0;
+        Buf b_ma = mk((size_t)nsp * 8, nullptr, out->mean_a, means && out->mean_a);
+        Buf b_me = mk((size_t)nsp * 8, nullptr, out->mean_e, means && out->mean_e);
+        Buf b_mi = mk((size_t)nsp * 8, nullptr, out->mean_inc, means && out->mean_inc);
+        Buf b_mo = mk((size_t)nsp * 8, nullptr, out->mean_omega, ((fl & NBT_F_MEAN_OMEGA) || (fl & NBT_F_SERIES)) && out->mean_omega);
+        Buf b_stat = mk((size_t)B * 4, nullptr, out->status, true);
+        Buf b_rv = mk(rv_elems * 8, nullptr, out->rv, (fl & NBT_F_RV) && out->rv);
+        Buf b_rvmax = mk((size_t)B * 8, nullptr, out->rv_max, (fl & NBT_F_RV) && out->rv && out->rv_max);
+        Buf b_rvws = mk(rv_elems * 8, nullptr, nullptr, need_rv_ws);
+        Buf b_orb = mk(nq * B * Np * 2 * 8, nullptr, out->orbit_xz, (fl & NBT_F_ORBIT) && out->orbit_xz);
+        Buf b_ser = scan ? mk((size_t)NO * B * W * 8, scan_series, nullptr, true)
+                         : mk((size_t)NO * B * W * 8, nullptr, out->series, (fl & NBT_F_SERIES) && out->series);
+        Buf b_lsp = mk((size_t)nls * 8, nullptr, out->ls_oc_power, nls > 0 && out->ls_oc_power);
+        Buf b_lsn = mk((size_t)nsp * 4, nullptr, out->ls_oc_nfreq, nls > 0 && out->ls_oc_nfreq);
+        Buf b_lsrv = mk((size_t)B * nf_rv * 8, nullptr, out->ls_rv_power, need_rv_ws && (fl & NBT_F_LS_RV) && out->ls_rv_power);
+        NBT_CUDA(cudaMallocAsync((void**)&arena, ar.size ? ar.size : 256, st));
+        auto dp = [&](const Buf& b) -> void* { return b.bytes ? (void*)(arena + b.off) : nullptr; };
+        Buf* ins[] = {&b_params, &b_sub, &b_order, &b_tto, &b_lso, &b_times, &b_ser};
+        for (Buf* b : ins)
+            if (b->bytes && b->h_in) NBT_CUDA(cudaMemcpyAsync(dp(*b), b->h_in, b->bytes, cudaMemcpyHostToDevice, st));
+        // NaN-fill the CSR transit buffers (all-ones bytes are a NaN): unused capacity reads as NaN
+        if (b_tt.bytes) NBT_CUDA(cudaMemsetAsync(dp(b_tt), 0xFF, b_tt.bytes, st));
+        if (b_ttv.bytes) NBT_CUDA(cudaMemsetAsync(dp(b_ttv), 0xFF, b_ttv.bytes, st));
+        if (b_lsp.bytes) NBT_CUDA(cudaMemsetAsync(dp(b_lsp), 0xFF, b_lsp.bytes, st));
+        nbt_inputs din;
+        din.params = (const double*)dp(b_params); din.substeps = (const int32_t*)dp(b_sub);
+        din.order = (const int32_t*)dp(b_order); din.tt_offsets = (const int64_t*)dp(b_tto);
+        din.ls_offsets = (const int64_t*)dp(b_lso);
+        nbt_outputs dout;
+        memset(&dout, 0, sizeof dout);
+        dout.tt = (double*)dp(b_tt); dout.ttv = (double*)dp(b_ttv); dout.n_tt = (int32_t*)dp(b_ntt);
+        dout.period = (double*)dp(b_per); dout.t0 = (double*)dp(b_t0); dout.ttv_max = (double*)dp(b_max);
+        dout.mean_a = (double*)dp(b_ma); dout.mean_e = (double*)dp(b_me); dout.mean_inc = (double*)dp(b_mi);
+        dout.mean_omega = (double*)dp(b_mo); dout.status = (int32_t*)dp(b_stat);
+        dout.rv = (double*)dp(b_rv); dout.rv_max = (double*)dp(b_rvmax); dout.orbit_xz = (double*)dp(b_orb);
+        dout.series = (double*)dp(b_ser); dout.ls_oc_power = (double*)dp(b_lsp); dout.ls_oc_nfreq = (int32_t*)dp(b_lsn);
+        dout.ls_rv_power = (double*)dp(b_lsrv);
+        NBT_CUDA(enqueue_path(cfg, &din, &dout, (double*)dp(b_rvws), st, scan ? (const double*)dp(b_ser) : nullptr,
+                              (const double*)dp(b_times), scan_dt));
+        Buf* outs[] = {&b_tt, &b_ttv, &b_ntt, &b_per, &b_t0, &b_max, &b_ma, &b_me, &b_mi, &b_mo, &b_stat,
+                       &b_rv, &b_rvmax, &b_orb, &b_ser, &b_lsp, &b_lsn, &b_lsrv};
+        for (Buf* b : outs)
+            if (b->bytes && b->h_out) NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, st));
+        NBT_CUDA(cudaStreamSynchronize(st));
+    }
+done:
+    if (arena) cudaFreeAsync(arena, st);
+    if (rv_ws) cudaFreeAsync(rv_ws, st);
+    if (rc != 0) cudaGetLastError();
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return rc;
+}
+
+int nbt_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, void* cuda_stream) {
+    return run_impl(cfg, in, out, cuda_stream, nullptr, nullptr, 0.0);
+}
+
+int nbt_analyze(const nbt_config* cfg, const double* series, const double* times, double dt,
+                const nbt_inputs* in, nbt_outputs* out, void* cuda_stream) {
+    if (!series) return nbt_fail(-10, "nbt_analyze: series is required");
+    return run_impl(cfg, in, out, cuda_stream, series, times, dt);
+}
+
+int nbt_lomb_scargle(const double* t, const double* y, int64_t n_series, int64_t n, double f0, double df,
+                     int64_t n_freq, double* power, int device, int device_ptrs, void* cuda_stream) {
+    int rc = 0;
+    if (!y || !power) return nbt_fail(-10, "nbt_lomb_scargle: NULL y/power");
+    if (n_series < 0 || n < 1 || n > INT32_MAX || n_freq < 0) return nbt_fail(-11, "nbt_lomb_scargle: bad sizes");
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_lomb_scargle: no CUDA device (there is no CPU fallback)");
+    if (n_series == 0 || n_freq == 0) return 0;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamPerThread;
+    double *dt = nullptr, *dy = nullptr, *dpw = nullptr;
+    const size_t ny = (size_t)n_series * n * 8, npw = (size_t)n_series * n_freq * 8;
+    NBT_CUDA(cudaSetDevice(device));
+    ensure_pool(device);
+    {
+        const double *kt = t, *ky = y;
+        double* kp = power;
+        if (!device_ptrs) {
+            NBT_CUDA(cudaMallocAsync((void**)&dy, ny, st));
+            NBT_CUDA(cudaMallocAsync((void**)&dpw, npw, st));
+            NBT_CUDA(cudaMemcpyAsync(dy, y, ny, cudaMemcpyHostToDevice, st));
+            if (t) {
+                NBT_CUDA(cudaMallocAsync((void**)&dt, ny, st));
+                NBT_CUDA(cudaMemcpyAsync(dt, t, ny, cudaMemcpyHostToDevice, st));
+            }
+            kt = dt; ky = dy; kp = dpw;
+        }
+        const long long chunks = (n_freq + 31) / 32, warps = n_series * chunks;
+        k_ls_series<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(kt, ky, n_series, (int)n, f0, df, n_freq, 1.0, kp);
+        NBT_CUDA(cudaGetLastError());
+        if (!device_ptrs) {
+            NBT_CUDA(cudaMemcpyAsync(power, dpw, npw, cudaMemcpyDeviceToHost, st));
+            NBT_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+done:
+    if (dt) cudaFreeAsync(dt, st);
+    if (dy) cudaFreeAsync(dy, st);
+    if (dpw) cudaFreeAsync(dpw, st);
+    if (rc != 0) cudaGetLastError();
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return rc;
+}
+
+int nbt_chi2(const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt, int32_t n_systems,
+             int32_t n_planets, const double* c0, const double* c1, const double* x, const double* y,
+             const double* yerr, int32_t n_data, double* loglike, int device, int device_ptrs,
+             void* cuda_stream) {
+    int rc = 0;
+    if (!ttv || !tt_offsets || !n_tt || !c0 || !c1 || !x || !y || !yerr || !loglike)
+        return nbt_fail(-10, "nbt_chi2: NULL argument");
+    if (n_systems < 0 || n_planets < 1 || n_data < 0) return nbt_fail(-11, "nbt_chi2: bad sizes");
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_chi2: no CUDA device (there is no CPU fallback)");
+    if (n_systems == 0) return 0;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamPerThread;
+    char* arena = nullptr;
+    NBT_CUDA(cudaSetDevice(device));
+    ensure_pool(device);
+    {
+        const int64_t nsp = (int64_t)n_systems * n_planets;
+        const double *k_ttv = ttv, *k_c0 = c0, *k_c1 = c1, *k_x = x, *k_y = y, *k_e = yerr;
+        const int64_t* k_off = tt_offsets; const int32_t* k_n = n_tt; double* k_ll = loglike;
+        if (!device_ptrs) {
+            const int64_t ntt = tt_offsets[nsp];
+            Arena ar;
+            const size_t o_ttv = ar.reserve((size_t)ntt * 8), o_off = ar.reserve((size_t)(nsp + 1) * 8),
+                         o_n = ar.reserve((size_t)nsp * 4), o_c0 = ar.reserve((size_t)n_systems * 8),
+                         o_c1 = ar.reserve((size_t)n_systems * 8), o_x = ar.reserve((size_t)n_data * 8),
+                         o_y = ar.reserve((size_t)n_data * 8), o_e = ar.reserve((size_t)n_data * 8),
+                         o_ll = ar.reserve((size_t)n_systems * 8);
+            NBT_CUDA(cudaMallocAsync((void**)&arena, ar.size, st));
+            NBT_CUDA(cudaMemcpyAsync(arena + o_ttv, ttv, (size_t)ntt * 8, cudaMemcpyHostToDevice, st));
+            NBT_CUDA(cudaMemcpyAsync(arena + o_off, tt_offsets, (size_t)(nsp + 1) * 8, cudaMemcpyHostToDevice, st));
+            NBT_CUDA(cudaMemcpyAsync(arena + o_n, n_tt, (size_t)nsp * 4, cudaMemcpyHostToDevice, st));
+            NBT_CUDA(cudaMemcpyAsync(arena + o_c0, c0, (size_t)n_systems * 8, cudaMemcpyHostToDevice, st));
+            NBT_CUDA(cudaMemcpyAsync(arena + o_c1, c1, (size_t)n_systems * 8, cudaMemcpyHostToDevice, st));
+            if (n_data) {
+                NBT_CUDA(cudaMemcpyAsync(arena + o_x, x, (size_t)n_data * 8, cudaMemcpyHostToDevice, st));
+                NBT_CUDA(cudaMemcpyAsync(arena + o_y, y, (size_t)n_data * 8, cudaMemcpyHostToDevice, st));
+                NBT_CUDA(cudaMemcpyAsync(arena + o_e, yerr, (size_t)n_data * 8, cudaMemcpyHostToDevice, st));
+            }
+            k_ttv = (double*)(arena + o_ttv); k_off = (int64_t*)(arena + o_off); k_n = (int32_t*)(arena + o_n);
+            k_c0 = (double*)(arena + o_c0); k_c1 = (double*)(arena + o_c1); k_x = (double*)(arena + o_x);
+            k_y = (double*)(arena + o_y); k_e = (double*)(arena + o_e); k_ll = (double*)(arena + o_ll);
+        }
+        k_chi2<<<(n_systems + 127) / 128, 128, 0, st>>>(k_ttv, k_off, k_n, n_systems, n_planets, k_c0, k_c1, k_x, k_y, k_e,
+                                                       n_data, k_ll);
+        NBT_CUDA(cudaGetLastError());
+        if (!device_ptrs) {
+            NBT_CUDA(cudaMemcpyAsync(loglike, k_ll, (size_t)n_systems * 8, cudaMemcpyDeviceToHost, st));
+            NBT_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+done:
+    if (arena) cudaFreeAsync(arena, st);
+    if (rc != 0) cudaGetLastError();
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return rc;
+}
+
+
+} // extern "C"
+
+// Stages the host arrays of a small stand-alone entry point onto the device (or passes device
+// pointers through), copies the outputs back and restores the caller's current device.
+struct Stage {
+    cudaStream_t st; bool dev_ptrs; int prev_dev = -1; int rc = 0;
+    std::vector<void*> allocs;
+    struct Out { void* h; void* d; size_t bytes; };
+    std::vector<Out> outs;
+    Stage(int device, int device_ptrs, void* stream) : st(stream ? (cudaStream_t)stream : cudaStreamPerThread), dev_ptrs(device_ptrs != 0) {
+        cudaGetDevice(&prev_dev);
+        check(cudaSetDevice(device), "cudaSetDevice");
+        if (!rc) ensure_pool(device);
+    }
+    void check(cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == 0) rc = nbt_fail((int)e, "%s failed: %s", what, cudaGetErrorString(e));
+    }
+    template <class T> const T* in(const T* h, size_t count) {
+        if (dev_ptrs || h == nullptr || rc) return h;
+        void* d = nullptr;
+        check(cudaMallocAsync(&d, std::max<size_t>(count * sizeof(T), 8), st), "cudaMallocAsync");
+        if (rc) return nullptr;
+        allocs.push_back(d);
+        check(cudaMemcpyAsync(d, h, count * sizeof(T), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(H2D)");
+        return (const T*)d;
+    }
+    template <class T> T* out(T* h, size_t count) {
+        if (dev_ptrs || h == nullptr || rc) return h;
+        void* d = nullptr;
+        check(cudaMallocAsync(&d, std::max<size_t>(count * sizeof(T), 8), st), "cudaMallocAsync");
+        if (rc) return nullptr;
+        allocs.push_back(d);
+        outs.push_back({h, d, count * sizeof(T)});
+        return (T*)d;
+    }
+    int finish() {
+        if (!rc) check(cudaGetLastError(), "kernel launch");
+        if (!dev_ptrs && !rc) {
+            for (auto& o : outs) check(cudaMemcpyAsync(o.h, o.d, o.bytes, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(D2H)");
+            check(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+        }
+        for (void* d : allocs) cudaFreeAsync(d, st);
+        if (rc) cudaGetLastError();
+        if (prev_dev >= 0) cudaSetDevice(prev_dev);
+        return rc;
+    }
+};
+
+extern "C" {
+
+int nbt_transit_times(const double* xp, const double* xs, const double* times, int64_t n_series, int64_t n,
+                      double* tt, int32_t* n_tt, int64_t cap, int times_shared, int device, int device_ptrs,
+                      void* cuda_stream) {
+    if (!xp || !xs || !times || !tt || !n_tt) return nbt_fail(-10, "nbt_transit_times: NULL argument");
+    if (n_series < 0 || n < 1 || cap < 0) return nbt_fail(-11, "nbt_transit_times: bad sizes");
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_transit_times: no CUDA device (there is no CPU fallback)");
+    if (n_series == 0) return 0;
+    Stage S(device, device_ptrs, cuda_stream);
+    const double* dxp = S.in(xp, (size_t)n_series * n);
+    const double* dxs = S.in(xs, (size_t)n_series * n);
+    const double* dt = S.in(times, (size_t)(times_shared ? n : n_series * n));
+    double* dtt = S.out(tt, (size_t)n_series * cap);
+    int32_t* dn = S.out(n_tt, (size_t)n_series);
+    if (!S.rc) k_transit_times<<<(unsigned)((n_series + 127) / 128), 128, 0, S.st>>>(dxp, dxs, dt, n_series, n, dtt, dn, cap, times_shared);
+    return S.finish();
+}
+
+int nbt_find_zero(const double* t1, const double* dx1, const double* t2, const double* dx2, int64_t n,
+                  double* t0, int device, int device_ptrs, void* cuda_stream) {
+    if (!t1 || !dx1 || !t2 || !dx2 || !t0) return nbt_fail(-10, "nbt_find_zero: NULL argument");
+    if (n < 0) return nbt_fail(-11, "nbt_find_zero: bad size");
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_find_zero: no CUDA device (there is no CPU fallback)");
+    if (n == 0) return 0;
+    Stage S(device, device_ptrs, cuda_stream);
+    const double *a = S.in(t1, n), *b = S.in(dx1, n), *c = S.in(t2, n), *d = S.in(dx2, n);
+    double* o = S.out(t0, n);
+    if (!S.rc) k_find_zero<<<(unsigned)((n + 127) / 128), 128, 0, S.st>>>(a, b, c, d, n, o);
+    return S.finish();
+}
+
+int nbt_ttv_fit(const double* epochs, const double* tt, int64_t n_series, int64_t n, double* ttv,
+                double* slope, double* intercept, int device, int device_ptrs, void* cuda_stream) {
+    if (!tt || !ttv || !slope || !intercept) return nbt_fail(-10, "nbt_ttv_fit: NULL argument");
+    if (n_series < 0 || n < 1 || n > INT32_MAX) return nbt_fail(-11, "nbt_ttv_fit: bad sizes");
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_ttv_fit: no CUDA device (there is no CPU fallback)");
+    if (n_series == 0) return 0;
+    Stage S(device, device_ptrs, cuda_stream);
+    const double* de = S.in(epochs, (size_t)n_series * n);
+    const double* dt = S.in(tt, (size_t)n_series * n);
+    double* dv = S.out(ttv, (size_t)n_series * n);
+    double* dm = S.out(slope, (size_t)n_series);
+    double* db = S.out(intercept, (size_t)n_series);
+    if (!S.rc) k_ttv_fit<<<(unsigned)((n_series * 32 + 127) / 128), 128, 0, S.st>>>(de, dt, n_series, (int)n, dv, dm, db);
+    return S.finish();
+}
+
+int nbt_maxavg(const double* x, int64_t n_series, int64_t n, double* out, int device, int device_ptrs,
+               void* cuda_stream) {
+    if (!x || !out) return nbt_fail(-10, "nbt_maxavg: NULL argument");
+    if (n_series < 0 || n < 1 || n > INT32_MAX) return nbt_fail(-11, "nbt_maxavg: bad sizes");
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_maxavg: no CUDA device (there is no CPU fallback)");
+    if (n_series == 0) return 0;
+    Stage S(device, device_ptrs, cuda_stream);
+    const double* dx = S.in(x, (size_t)n_series * n);
+    double* dout = S.out(out, (size_t)n_series);
+    if (!S.rc) k_maxavg<<<(unsigned)((n_series * 32 + 127) / 128), 128, 0, S.st>>>(dx, n_series, (int)n, dout);
+    return S.finish();
+}
+
+int nbt_timing(double* ms4) {
+    if (!ms4) return nbt_fail(-10, "nbt_timing: NULL argument");
+    if (!g_timing.have) return nbt_fail(-13, "nbt_timing: no nbt_run with NBT_F_TIMING on this thread yet");
+    for (int i = 0; i < 4; i++) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(g_timing.ev[i + 1]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_timing.ev[i], g_timing.ev[i + 1]);
+        if (e != cudaSuccess) { cudaGetLastError(); return nbt_fail((int)e, "nbt_timing: %s", cudaGetErrorString(e)); }
+        ms4[i] = (double)ms;
+    }
+    return 0;
+}
+
+int nbt_fp64_peak(int device, int iters, double* tflops_out, double* ms_out) {
+    int rc = 0;
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_fp64_peak: no CUDA device");
+    if (iters <= 0) iters = 1 << 16;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double* d = nullptr;
+    NBT_CUDA(cudaSetDevice(device));
+    {
+        cudaDeviceProp prop;
+        NBT_CUDA(cudaGetDeviceProperties(&prop, device));
+        const int blocks = prop.multiProcessorCount * 8, threads = 256;
+        NBT_CUDA(cudaMalloc((void**)&d, 8));
+        NBT_CUDA(cudaEventCreate(&e0));
+        NBT_CUDA(cudaEventCreate(&e1));
+        k_dfma_peak<<<blocks, threads>>>(d, iters / 8, 0.999999, 1e-7); // warm-up
+        NBT_CUDA(cudaGetLastError());
+        NBT_CUDA(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+        NBT_CUDA(cudaEventRecord(e1));
+        NBT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        NBT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)blocks * threads * 8.0 * (double)iters * 2.0;
+        if (tflops_out) *tflops_out = flops / ((double)ms * 1e-3) * 1e-12;
+        if (ms_out) *ms_out = (double)ms;
+    }
+done:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (d) cudaFree(d);
+    if (rc != 0) cudaGetLastError();
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,571 @@
+// nbt_core.cuh — per-system FP64 math of the batched TTV engine (sm_100a device code).
+//
+// One system = star + NP planets in JACOBI coordinates, all state in registers of one thread.
+// The integrator is a symmetric BAB composition of the Wisdom-Holman map
+//     K(b0 dt) D(a1 dt) K(b1 dt) ... D(aS dt) K(bS dt)
+// with D = exact Kepler drift of every Jacobi coordinate (universal variables, Stumpff series)
+// and K = kick from the interaction Hamiltonian (direct pairs minus the star-planet-1 pair,
+// plus the Jacobi indirect term).  Replaces what the reference gets from REBOUND through
+// sim.integrate(time) in nbody/simulation.py:141-150.
+//
+// Every function is __host__ __device__ so that tests/hostsim can run the *same* arithmetic on
+// the CPU for numerics checks in the GPU-less container.  That host build is test
+// infrastructure only; the product library (nbt_capi.cu) has no CPU path.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/nbt.h"
+
+#if defined(__CUDACC__)
+#define NBT_HD __host__ __device__ __forceinline__
+#else
+#define NBT_HD inline
+#endif
+
+#define NBT_PI 3.14159265358979323846264338327950288
+#define NBT_MAX_STAGES 8
+
+// ---------------------------------------------------------------------------------------------
+// reciprocal / reciprocal square root: MUFU seed (rsqrt.approx.f64 / rcp.approx.f64, ~2^-20) +
+// one cubic (Halley) correction in DFMA -> ~2^-60, i.e. correctly rounded to within 1 ulp.
+// This is what keeps FP64 div/sqrt (10+ instructions each in libdevice) off the hot loop.
+// ---------------------------------------------------------------------------------------------
+NBT_HD double nbt_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);           // 1 - x y^2
+    double p = fma(0.375, e, 0.5);            // 1/2 + 3/8 e
+    return fma(y * e, p, y);                  // y (1 + e/2 + 3/8 e^2)
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+NBT_HD double nbt_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);               // 1 - x y
+    double p = fma(e, e, e);                  // e + e^2
+    return fma(y, p, y);                      // y (1 + e + e^2)
+#else
+    return 1.0 / x;
+#endif
+}
+
+// refine a reciprocal from a nearby guess y0 ~ 1/x (relative error <~ 1e-5): one cubic step
+NBT_HD double nbt_rcp_from(double x, double y0) {
+    const double e = fma(-x, y0, 1.0);
+    return fma(y0, fma(e, e, e), y0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kepler drift of one Jacobi coordinate by h (either sign) under mu = G M_i.
+//   universal Kepler equation  F(X) = r0 X + eta G2 + zeta G3 - h = 0,   G_k = X^k c_k(beta X^2)
+//   beta = 2 mu / r0 - v0^2,  eta = r0 . v0,  zeta = mu - beta r0
+// Solve: X0 = cubic series reversion at X = 0 (no Stumpff needed), then ONE quartically
+// convergent step (same reversion, now with the full F, F', F'', F''' at X0) and a 3rd-order
+// Taylor shift of G1..G3 to the corrected X.  If the correction is not small the (warp-
+// divergent, rare) safe loop below iterates to convergence and flags NBT_S_KEPLER on failure.
+// ---------------------------------------------------------------------------------------------
+NBT_HD void nbt_stumpff(double z, double& c2, double& c3) {
+    // c2 = 1/2! - z/4! + z^2/6! - ...,  c3 = 1/3! - z/5! + z^2/7! - ...   (|z| <~ 0.5)
+    c2 = fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, 1.0 / 87178291200.0, -1.0 / 479001600.0),
+         1.0 / 3628800.0), -1.0 / 40320.0), 1.0 / 720.0), -1.0 / 24.0), 0.5);
+    c3 = fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, 1.0 / 1307674368000.0, -1.0 / 6227020800.0),
+         1.0 / 39916800.0), -1.0 / 362880.0), 1.0 / 5040.0), -1.0 / 120.0), 1.0 / 6.0);
+}
+
+// general-|z| Stumpff via argument quartering (only used by the safe path)
+NBT_HD void nbt_stumpff_big(double z, double& c0, double& c1, double& c2, double& c3) {
+    int n = 0;
+    while (fabs(z) > 0.1 && n < 40) { z *= 0.25; n++; }
+    nbt_stumpff(z, c2, c3);
+    c1 = 1.0 - z * c3;
+    c0 = 1.0 - z * c2;
+    for (; n > 0; n--) {
+        c3 = 0.25 * (c2 + c0 * c3);
+        c2 = 0.5 * c1 * c1;
+        c1 = c0 * c1;
+        c0 = 2.0 * c0 * c0 - 1.0;
+    }
+}
+
+NBT_HD void nbt_kepler_safe(double mu, double h, double r0, double eta, double beta, double zeta,
+                            double& X, double& G1, double& G2, double& G3, double& r, int& status) {
+    // Newton with bisection-style damping on the monotone F (F' = r > 0)
+    double Xc = X;
+    bool ok = false;
+    for (int it = 0; it < 60; it++) {
+        double c0, c1, c2, c3;
+        double X2 = Xc * Xc;
+        nbt_stumpff_big(beta * X2, c0, c1, c2, c3);
+        G1 = Xc * c1; G2 = X2 * c2; G3 = X2 * Xc * c3;
+        double F = fma(r0, Xc, fma(eta, G2, zeta * G3)) - h;
+        r = fma(eta, G1, fma(zeta, G2, r0));
+        double d = -F / r;
+        Xc += d;
+        if (fabs(d) <= 1e-15 * fabs(Xc) || d == 0.0) { ok = true; break; }
+    }
+    double c0, c1, c2, c3;
+    double X2 = Xc * Xc;
+    nbt_stumpff_big(beta * X2, c0, c1, c2, c3);
+    G1 = Xc * c1; G2 = X2 * c2; G3 = X2 * Xc * c3;
+    r = fma(eta, G1, fma(zeta, G2, r0));
+    X = Xc;
+    if (!ok || !(r > 0.0)) status |= NBT_S_KEPLER;
+}
+
+NBT_HD void nbt_kepler_drift(double mu, double h, double& x, double& y, double& z, double& vx,
+                             double& vy, double& vz, int& status) {
+    const double r02 = fma(x, x, fma(y, y, z * z));
+    const double v02 = fma(vx, vx, fma(vy, vy, vz * vz));
+    const double eta = fma(x, vx, fma(y, vy, z * vz));
+    const double ir0 = nbt_rsqrt(r02);
+    const double r0 = r02 * ir0;
+    const double beta = fma(2.0 * mu, ir0, -v02);
+    const double zeta = fma(-beta, r0, mu);
+
+    // X0: reversion of h = r0 X + eta X^2/2 + zeta X^3/6 - beta eta X^4/24 ...
+    const double s = h * ir0;
+    const double A = 0.5 * eta * ir0, Bc = (1.0 / 6.0) * zeta * ir0;
+    const double Cc = (-1.0 / 24.0) * beta * eta * ir0;
+    const double AA = A * A;
+    //   X = s - A s^2 + (2A^2 - B) s^3 + (-5A^3 + 5AB - C) s^4
+    double X = s * fma(s, fma(s, fma(s, fma(A, fma(-5.0, AA, 5.0 * Bc), -Cc), fma(2.0, AA, -Bc)), -A), 1.0);
+
+    double X2 = X * X;
+    const double zz = beta * X2;
+    double c2, c3;
+    nbt_stumpff(zz, c2, c3);
+    const double c1 = fma(-zz, c3, 1.0), c0 = fma(-zz, c2, 1.0);
+    double G0 = c0, G1 = X * c1, G2 = X2 * c2, G3 = X2 * X * c3;
+    const double F = fma(r0, X, fma(eta, G2, zeta * G3)) - h;
+    double r = fma(eta, G1, fma(zeta, G2, r0));                 // F'
+    const double Fpp = fma(eta, G0, zeta * G1);                 // F''
+    const double Fppp = fma(zeta, G0, -beta * eta * G1);        // F'''
+    double ir = nbt_rcp(r);
+    const double u = -F * ir;
+    const double a2 = 0.5 * Fpp * ir, a3 = (1.0 / 6.0) * Fppp * ir;
+    const double d = u * fma(u, fma(u, fma(2.0 * a2, a2, -a3), -a2), 1.0);
+
+    if (fabs(d) <= 2e-4 * fabs(X) && zz < 0.5 && zz > -0.5) {
+        // shift G1..G3 from X to X + d:  dG_k/dX = G_{k-1},  dG0/dX = -beta G1
+        const double d2 = 0.5 * d * d, d3 = (1.0 / 3.0) * d2 * d;
+        const double bG1 = beta * G1, bG0 = beta * G0;
+        const double nG3 = fma(d, G2, fma(d2, G1, fma(d3, G0, G3)));
+        const double nG2 = fma(d, G1, fma(d2, G0, fma(-d3, bG1, G2)));
+        const double nG1 = fma(d, G0, fma(-d2, bG1, fma(-d3, bG0, G1)));
+        G1 = nG1; G2 = nG2; G3 = nG3;
+        r = fma(eta, G1, fma(zeta, G2, r0));
+        ir = nbt_rcp_from(r, ir);
+    } else {
+        X += d;
+        nbt_kepler_safe(mu, h, r0, eta, beta, zeta, X, G1, G2, G3, r, status);
+        ir = 1.0 / r;
+    }
+    // Gauss f, g in the round-off-friendly "minus one" form
+    const double fm1 = -mu * G2 * ir0;
+    const double g = fma(-mu, G3, h);
+    const double fd = -mu * G1 * ir0 * ir;
+    const double gdm1 = -mu * G2 * ir;
+    const double nx = fma(fm1, x, fma(g, vx, x)), ny = fma(fm1, y, fma(g, vy, y)),
+                 nz = fma(fm1, z, fma(g, vz, z));
+    vx = fma(fd, x, fma(gdm1, vx, vx));
+    vy = fma(fd, y, fma(gdm1, vy, vy));
+    vz = fma(fd, z, fma(gdm1, vz, vz));
+    x = nx; y = ny; z = nz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// System state (structure of small fixed arrays -> registers after full unrolling)
+// ---------------------------------------------------------------------------------------------
+template <int NP>
+struct nbt_state {
+    double x[NP], y[NP], z[NP], vx[NP], vy[NP], vz[NP]; // Jacobi coordinates of planets 1..NP
+};
+
+template <int NP>
+struct nbt_consts {
+    double GM[NP];     // G * M_i, M_i = m_0 + ... + m_i          (Kepler mu of Jacobi coordinate i)
+    double mr[NP];     // m_i / M_i                               (Jacobi <-> heliocentric shifts)
+    double Gm[NP + 1]; // G * m_k for k = 0..NP                   (pair forces)
+};
+
+// Jacobi accelerations from the interaction Hamiltonian
+//   H_int = sum_{i>=2} G m_i M_{i-1} / r'_i  -  sum_{i>=2} G m_0 m_i / |q_i|  -  sum_{1<=i<j} G m_i m_j / |q_i - q_j|
+// (q = heliocentric position; the star-planet-1 pair is the i=1 Kepler term and cancels).
+template <int NP>
+NBT_HD void nbt_accel(const nbt_state<NP>& s, const nbt_consts<NP>& c, double (&ax)[NP],
+                      double (&ay)[NP], double (&az)[NP]) {
+    if (NP == 1) { ax[0] = ay[0] = az[0] = 0.0; return; }
+    double qx[NP], qy[NP], qz[NP];
+    {   // heliocentric positions: q_i = r'_i + S_{i-1},  S_i = S_{i-1} + (m_i/M_i) r'_i
+        double Sx = 0.0, Sy = 0.0, Sz = 0.0;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            qx[i] = s.x[i] + Sx; qy[i] = s.y[i] + Sy; qz[i] = s.z[i] + Sz;
+            Sx = fma(c.mr[i], s.x[i], Sx); Sy = fma(c.mr[i], s.y[i], Sy); Sz = fma(c.mr[i], s.z[i], Sz);
+        }
+    }
+    double a0x = 0.0, a0y = 0.0, a0z = 0.0; // star
+    double px[NP], py[NP], pz[NP];          // planets (inertial accelerations, included pairs only)
+#pragma unroll
+    for (int i = 0; i < NP; i++) px[i] = py[i] = pz[i] = 0.0;
+#pragma unroll
+    for (int i = 1; i < NP; i++) { // star - planet i (i >= 2 in 1-based numbering)
+        const double r2 = fma(qx[i], qx[i], fma(qy[i], qy[i], qz[i] * qz[i]));
+        const double ir = nbt_rsqrt(r2);
+        const double ir3 = ir * ir * ir;
+        const double fs = c.Gm[i + 1] * ir3, fp = -c.Gm[0] * ir3;
+        a0x = fma(fs, qx[i], a0x); a0y = fma(fs, qy[i], a0y); a0z = fma(fs, qz[i], a0z);
+        px[i] = fp * qx[i]; py[i] = fp * qy[i]; pz[i] = fp * qz[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NP; i++)
+#pragma unroll
+        for (int j = i + 1; j < NP; j++) {
+            const double dx = qx[j] - qx[i], dy = qy[j] - qy[i], dz = qz[j] - qz[i];
+            const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+            const double ir = nbt_rsqrt(r2);
+            const double ir3 = ir * ir * ir;
+            const double fi = c.Gm[j + 1] * ir3, fj = -c.Gm[i + 1] * ir3;
+            px[i] = fma(fi, dx, px[i]); py[i] = fma(fi, dy, py[i]); pz[i] = fma(fi, dz, pz[i]);
+            px[j] = fma(fj, dx, px[j]); py[j] = fma(fj, dy, py[j]); pz[j] = fma(fj, dz, pz[j]);
+        }
+    // inertial -> Jacobi: a'_i = a_i - A_{i-1},  A_i = A_{i-1} + (m_i/M_i) a'_i,  A_0 = a_0
+    double Ax = a0x, Ay = a0y, Az = a0z;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        double jx = px[i] - Ax, jy = py[i] - Ay, jz = pz[i] - Az;
+        Ax = fma(c.mr[i], jx, Ax); Ay = fma(c.mr[i], jy, Ay); Az = fma(c.mr[i], jz, Az);
+        if (i >= 1) { // + G M_i r'_i / r'_i^3
+            const double r2 = fma(s.x[i], s.x[i], fma(s.y[i], s.y[i], s.z[i] * s.z[i]));
+            const double ir = nbt_rsqrt(r2);
+            const double f = c.GM[i] * ir * ir * ir;
+            jx = fma(f, s.x[i], jx); jy = fma(f, s.y[i], jy); jz = fma(f, s.z[i], jz);
+        }
+        ax[i] = jx; ay[i] = jy; az[i] = jz;
+    }
+}
+
+// composition coefficients: K(b[0]) D(a[0]) K(b[1]) ... D(a[S-1]) K(b[S])
+struct nbt_scheme {
+    int S;
+    double a[NBT_MAX_STAGES];
+    double b[NBT_MAX_STAGES + 1];
+};
+
+NBT_HD nbt_scheme nbt_make_scheme(int id) {
+    nbt_scheme s;
+    for (int i = 0; i < NBT_MAX_STAGES; i++) s.a[i] = 0.0;
+    for (int i = 0; i <= NBT_MAX_STAGES; i++) s.b[i] = 0.0;
+    switch (id) {
+    case NBT_SCHEME_Y4: { // Yoshida (1990) triple jump of kick-drift-kick
+        const double w1 = 1.351207191959657634047688, w0 = -1.702414383919315268095376;
+        s.S = 3;
+        s.a[0] = w1; s.a[1] = w0; s.a[2] = w1;
+        s.b[0] = 0.5 * w1; s.b[1] = 0.5 * (w0 + w1); s.b[2] = 0.5 * (w0 + w1); s.b[3] = 0.5 * w1;
+    } break;
+    case NBT_SCHEME_SABA4: { // Laskar & Robutel (2001) SBAB_4 = 5-point Lobatto: O(eps dt^8 + eps^2 dt^2)
+        const double c1 = 0.1726731646460114281008538, c2 = 0.3273268353539885718991462;
+        s.S = 4;
+        s.a[0] = c1; s.a[1] = c2; s.a[2] = c2; s.a[3] = c1;
+        s.b[0] = 1.0 / 20.0; s.b[1] = 49.0 / 180.0; s.b[2] = 16.0 / 45.0; s.b[3] = 49.0 / 180.0; s.b[4] = 1.0 / 20.0;
+    } break;
+    case NBT_SCHEME_M64: { // order (6,4): O(eps dt^6 + eps^2 dt^4); tools/derive_schemes.py
+        const double t1 = -0.0437514219173741137407351, t2 = 0.5437514219173741137407351;
+        s.S = 4;
+        s.a[0] = t1; s.a[1] = t2; s.a[2] = t2; s.a[3] = t1;
+        s.b[0] = 0.5316386245813511790852625; s.b[1] = -0.3086019704406066393237719;
+        s.b[2] = 0.5539266917185109204770189; s.b[3] = -0.3086019704406066393237719;
+        s.b[4] = 0.5316386245813511790852625;
+    } break;
+    default: // NBT_SCHEME_WH2 kick-drift-kick leapfrog
+        s.S = 1; s.a[0] = 1.0; s.b[0] = 0.5; s.b[1] = 0.5;
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// set-up: rebound.Simulation.add(**obj) in Jacobi fashion (nbody/simulation.py:45-47).  The
+// orbital elements of body i are relative to the centre of mass of bodies 0..i-1 with
+// mu = G M_i, so they ARE the Jacobi coordinates; move_to_com() only fixes the barycentre,
+// which the Jacobi set does not carry.
+// ---------------------------------------------------------------------------------------------
+template <int NP>
+NBT_HD void nbt_setup(const double* par, nbt_state<NP>& s, nbt_consts<NP>& c) {
+    double M = par[NBT_P_M];
+    c.Gm[0] = NBT_G * M;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        const double* p = par + (i + 1) * NBT_NPAR;
+        const double m = p[NBT_P_M];
+        M += m;
+        const double mu = NBT_G * M;
+        c.GM[i] = mu; c.mr[i] = m / M; c.Gm[i + 1] = NBT_G * m;
+        const double P = p[NBT_P_P], e = p[NBT_P_E];
+        const double a = cbrt(P * P * mu / (4.0 * NBT_PI * NBT_PI));
+        const double cf = cos(p[NBT_P_F]), sf = sin(p[NBT_P_F]);
+        const double r = a * (1.0 - e * e) / (1.0 + e * cf);
+        const double v0 = sqrt(mu / (a * (1.0 - e * e)));
+        const double cO = cos(p[NBT_P_OMEGA_NODE]), sO = sin(p[NBT_P_OMEGA_NODE]);
+        const double co = cos(p[NBT_P_OMEGA_PERI]), so = sin(p[NBT_P_OMEGA_PERI]);
+        const double ci = cos(p[NBT_P_INC]), si = sin(p[NBT_P_INC]);
+        const double cwf = co * cf - so * sf, swf = so * cf + co * sf;
+        s.x[i] = r * (cO * cwf - sO * swf * ci);
+        s.y[i] = r * (sO * cwf + cO * swf * ci);
+        s.z[i] = r * (swf * si);
+        const double vp = -(swf + e * so), vq = (cwf + e * co);
+        s.vx[i] = v0 * (cO * vp - sO * vq * ci);
+        s.vy[i] = v0 * (sO * vp + cO * vq * ci);
+        s.vz[i] = v0 * (vq * si);
+    }
+}
+
+// one composition step of size dt; (ax,ay,az) holds the acceleration at the current positions
+// on entry and on exit (shared between the last kick of a step and the first of the next)
+template <int NP>
+NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme& sc, double dt,
+                     double (&ax)[NP], double (&ay)[NP], double (&az)[NP], int& status) {
+    {
+        const double kb = sc.b[0] * dt;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            s.vx[i] = fma(kb, ax[i], s.vx[i]); s.vy[i] = fma(kb, ay[i], s.vy[i]); s.vz[i] = fma(kb, az[i], s.vz[i]);
+        }
+    }
+    for (int st = 0; st < sc.S; st++) {
+        const double h = sc.a[st] * dt;
+#pragma unroll
+        for (int i = 0; i < NP; i++)
+            nbt_kepler_drift(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], status);
+        nbt_accel<NP>(s, c, ax, ay, az);
+        const double kb = sc.b[st + 1] * dt;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            s.vx[i] = fma(kb, ax[i], s.vx[i]); s.vy[i] = fma(kb, ay[i], s.vy[i]); s.vz[i] = fma(kb, az[i], s.vz[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jacobi osculating elements with REBOUND's conventions [3P] (primary = COM of lower-index
+// bodies, mu = G M_i): what ps[j].P/a/e/inc/Omega/omega/M return at nbody/simulation.py:150.
+// ---------------------------------------------------------------------------------------------
+NBT_HD double nbt_acos2(double num, double den, double disamb) {
+    const double cth = num / den;
+    double val;
+    if (cth > -1.0 && cth < 1.0) val = acos(cth);
+    else val = (cth <= -1.0) ? NBT_PI : 0.0;
+    return (disamb < 0.0) ? -val : val;
+}
+
+struct nbt_orbit { double P, a, e, inc, Omega, omega, M; };
+
+// a, e, inc only (the analyze() means); full = also P, Omega, omega, M
+template <bool FULL>
+NBT_HD nbt_orbit nbt_elements(double mu, double x, double y, double z, double vx, double vy, double vz) {
+    nbt_orbit o;
+    const double hx = y * vz - z * vy, hy = z * vx - x * vz, hz = x * vy - y * vx;
+    const double h2 = fma(hx, hx, fma(hy, hy, hz * hz));
+    const double v2 = fma(vx, vx, fma(vy, vy, vz * vz));
+    const double r2 = fma(x, x, fma(y, y, z * z));
+    const double r = sqrt(r2);
+    const double h = sqrt(h2);
+    const double vc2 = mu / r;
+    o.a = -mu / (v2 - 2.0 * vc2);
+    const double rv = fma(x, vx, fma(y, vy, z * vz));
+    const double vd2 = v2 - vc2;
+    const double imu = 1.0 / mu;
+    const double ex = imu * (vd2 * x - rv * vx), ey = imu * (vd2 * y - rv * vy), ez = imu * (vd2 * z - rv * vz);
+    o.e = sqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
+    o.inc = nbt_acos2(hz, h, 1.0);
+    o.P = o.Omega = o.omega = o.M = 0.0;
+    if (FULL) {
+        const double vr = rv / r;
+        const double nmm = o.a / fabs(o.a) * sqrt(fabs(mu / (o.a * o.a * o.a)));
+        o.P = 2.0 * NBT_PI / nmm;
+        const double nx = -hy, ny = hx, nn = sqrt(nx * nx + ny * ny);
+        o.Omega = nbt_acos2(nx, nn, ny);
+        if (o.e < 1.0) {
+            const double ea = nbt_acos2(1.0 - r / o.a, o.e, vr);
+            o.M = ea - o.e * sin(ea);
+        } else {
+            double ea = acosh((1.0 - r / o.a) / o.e);
+            if (vr < 0.0) ea = -ea;
+            o.M = o.e * sinh(ea) - ea;
+        }
+        if (o.inc < 1e-8 || o.inc > NBT_PI - 1e-8) {
+            const double pomega = nbt_acos2(ex, o.e, ey);
+            o.omega = (o.inc < 0.5 * NBT_PI) ? pomega - o.Omega : o.Omega - pomega;
+        } else {
+            o.omega = nbt_acos2(nx * ex + ny * ey, nn * o.e, ez);
+        }
+        if (o.e <= 1e-8) o.omega = 0.0;
+    }
+    return o;
+}
+
+// omega alone (for NBT_F_MEAN_OMEGA without the full set)
+NBT_HD double nbt_omega_only(double mu, double x, double y, double z, double vx, double vy, double vz) {
+    return nbt_elements<true>(mu, x, y, z, vx, vy, vz).omega;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole-system driver: integrate + sample on np.linspace(0, Ndays, Noutputs) + transit detection
+// (nbody/simulation.py:131-170 fused; trajectories never reach memory unless asked for).
+// ---------------------------------------------------------------------------------------------
+struct nbt_run_args {
+    // inputs
+    const double* params;      // [B][NP+1][NBT_NPAR]
+    const int32_t* substeps;   // [B] or nullptr
+    const int32_t* order;      // [B] launch order (systems sorted by substeps) or nullptr
+    const int64_t* tt_offsets; // [B*NP+1]
+    // outputs
+    double* tt; int32_t* n_tt;
+    double* mean_a; double* mean_e; double* mean_inc; double* mean_omega;
+    int32_t* status;
+    double* rv; double* orbit_xz; double* series;
+    // config
+    int32_t B, n_outputs, substeps_all, tt_mode, flags, orbit_stride;
+    double n_days;
+    nbt_scheme scheme;
+};
+
+template <int NP>
+NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
+    nbt_state<NP> s;
+    nbt_consts<NP> c;
+    const double* par = A.params + (size_t)sys * (NP + 1) * NBT_NPAR;
+    nbt_setup<NP>(par, s, c);
+    int status = 0;
+    const int NO = A.n_outputs, B = A.B;
+    const int k = (A.substeps != nullptr) ? A.substeps[sys] : A.substeps_all;
+    const double step = A.n_days / (double)(NO - 1);
+    const double dt = step / (double)k;
+    const bool want_means = (A.flags & NBT_F_MEANS) != 0;
+    const bool want_omega = (A.flags & NBT_F_MEAN_OMEGA) != 0;
+    const bool want_rv = (A.flags & NBT_F_RV) != 0 && A.rv != nullptr;
+    const bool want_orbit = (A.flags & NBT_F_ORBIT) != 0 && A.orbit_xz != nullptr;
+    const bool want_series = (A.flags & NBT_F_SERIES) != 0 && A.series != nullptr;
+    const int n_tt_planets = (A.flags & NBT_F_PLANET1_ONLY) ? 1 : NP;
+    const double rv_scale = 1.496e11 * ((double)NO / (A.n_days * 24.0 * 60.0 * 60.0)); // simulation.py:157,186
+    const int W = 3 + 10 * NP;
+
+    double ax[NP], ay[NP], az[NP];
+    nbt_accel<NP>(s, c, ax, ay, az);
+
+    double dx_prev[NP], dvx_prev[NP];
+    double sum_a[NP], sum_e[NP], sum_i[NP], sum_o[NP];
+    int cnt[NP];
+    double xs_prev = 0.0, t_prev = 0.0;
+#pragma unroll
+    for (int j = 0; j < NP; j++) { sum_a[j] = sum_e[j] = sum_i[j] = sum_o[j] = 0.0; cnt[j] = 0; dx_prev[j] = dvx_prev[j] = 0.0; }
+
+    for (int o = 0; o < NO; o++) {
+        if (o > 0) {
+            for (int sub = 0; sub < k; sub++) nbt_step<NP>(s, c, A.scheme, dt, ax, ay, az, status);
+        }
+        const double t = (o == NO - 1) ? A.n_days : (double)o * step;
+        // heliocentric x (= x_planet - x_star) and star barycentric position
+        double dx[NP], dvx[NP];
+        double Sx = 0.0, Svx = 0.0;
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            dx[j] = s.x[j] + Sx; dvx[j] = s.vx[j] + Svx;
+            Sx = fma(c.mr[j], s.x[j], Sx); Svx = fma(c.mr[j], s.vx[j], Svx);
+        }
+        const double xs = -Sx;
+        if (o > 0) {
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                if (j < n_tt_planets && dx_prev[j] >= 0.0 && dx[j] <= 0.0) { // simulation.py:168
+                    double t0;
+                    if (A.tt_mode == NBT_TT_GRID_LINEAR) {                   // tools.py:61-65
+                        const double m = (dx[j] - dx_prev[j]) / (t - t_prev);
+                        t0 = -dx_prev[j] / m + t_prev;
+                    } else { // Newton on the cubic Hermite interpolant of dx over the interval
+                        const double hh = t - t_prev;
+                        const double p0 = dx_prev[j], p1 = dx[j], m0 = dvx_prev[j] * hh, m1 = dvx[j] * hh;
+                        double u = p0 / (p0 - p1);
+                        if (!(u >= 0.0 && u <= 1.0)) u = 0.5;
+                        for (int it = 0; it < 6; it++) {
+                            const double u2 = u * u, u3 = u2 * u;
+                            const double f = (2 * u3 - 3 * u2 + 1) * p0 + (u3 - 2 * u2 + u) * m0 + (-2 * u3 + 3 * u2) * p1 + (u3 - u2) * m1;
+                            const double fp = (6 * u2 - 6 * u) * p0 + (3 * u2 - 4 * u + 1) * m0 + (-6 * u2 + 6 * u) * p1 + (3 * u2 - 2 * u) * m1;
+                            u -= f / fp;
+                        }
+                        t0 = t_prev + u * hh;
+                    }
+                    const int64_t off = A.tt_offsets[(size_t)sys * NP + j];
+                    const int64_t cap = A.tt_offsets[(size_t)sys * NP + j + 1] - off;
+                    if (cnt[j] < cap) A.tt[off + cnt[j]] = t0; else status |= NBT_S_TT_OVERFLOW;
+                    cnt[j]++;
+                }
+            }
+            if (want_rv) A.rv[(size_t)(o - 1) * B + sys] = (xs - xs_prev) * rv_scale;             // simulation.py:186
+        }
+#pragma unroll
+        for (int j = 0; j < NP; j++) { dx_prev[j] = dx[j]; dvx_prev[j] = dvx[j]; }
+        xs_prev = xs; t_prev = t;
+
+        if (want_means && !want_series) {
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                const nbt_orbit ob = nbt_elements<false>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+                sum_a[j] += ob.a; sum_e[j] += ob.e; sum_i[j] += ob.inc;
+                if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
+                if (want_omega) sum_o[j] += nbt_omega_only(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+            }
+        }
+        if (want_orbit || want_series) {
+            // barycentric positions: r_0 = -S_NP, r_j = r_0 + q_j
+            double Ty = 0.0, Tz = 0.0, qy[NP], qz[NP];
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                qy[j] = s.y[j] + Ty; qz[j] = s.z[j] + Tz;
+                Ty = fma(c.mr[j], s.y[j], Ty); Tz = fma(c.mr[j], s.z[j], Tz);
+            }
+            if (want_orbit && (o % A.orbit_stride) == 0) {                                       // simulation.py:227-228
+                const int q = o / A.orbit_stride;
+#pragma unroll
+                for (int j = 0; j < NP; j++) {
+                    double* dst = A.orbit_xz + (((size_t)q * B + sys) * NP + j) * 2;
+                    dst[0] = dx[j] + xs; dst[1] = qz[j] - Tz;
+                }
+            }
+            if (want_series) {                                                                   // simulation.py:141-150
+                double* row = A.series + ((size_t)o * B + sys) * W;
+                row[0] = xs; row[1] = -Ty; row[2] = -Tz;
+#pragma unroll
+                for (int j = 0; j < NP; j++) {
+                    const nbt_orbit ob = nbt_elements<true>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+                    double* p = row + 3 + 10 * j;
+                    p[0] = dx[j] + xs; p[1] = qy[j] - Ty; p[2] = qz[j] - Tz;
+                    p[3] = ob.P; p[4] = ob.a; p[5] = ob.e; p[6] = ob.inc; p[7] = ob.Omega; p[8] = ob.omega; p[9] = ob.M;
+                    sum_a[j] += ob.a; sum_e[j] += ob.e; sum_i[j] += ob.inc; sum_o[j] += ob.omega;
+                    if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
+                }
+            }
+        }
+    }
+    bool finite = true;
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        const size_t sp = (size_t)sys * NP + j;
+        finite = finite && isfinite(s.x[j] + s.vx[j] + s.y[j] + s.vy[j] + s.z[j] + s.vz[j]);
+        A.n_tt[sp] = cnt[j];
+        if (want_means || want_series) {
+            const double inv = 1.0 / (double)NO;
+            if (A.mean_a) A.mean_a[sp] = sum_a[j] * inv;
+            if (A.mean_e) A.mean_e[sp] = sum_e[j] * inv;
+            if (A.mean_inc) A.mean_inc[sp] = sum_i[j] * inv;
+            if (A.mean_omega && (want_omega || want_series)) A.mean_omega[sp] = sum_o[j] * inv;
+        }
+    }
+    if (!finite) status |= NBT_S_NONFINITE;
+    A.status[sys] = status;
+}

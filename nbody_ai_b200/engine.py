@@ -1,0 +1,303 @@
+"""Host side of the batched TTV engine: planning, caller-owned buffers and the nbt_run call.
+
+This file holds no arithmetic of the path — every number comes out of libnbt.so (CUDA,
+sm_100a).  It sizes the CSR buffers with the library's own host helpers (nbt_plan_*), owns
+the numpy / torch storage the C ABI writes into, and shards batches by system index over
+the ranks of a torch.distributed job (no collective on the data path).
+
+Reference path replaced: the per-simulation Python loops around nbody/simulation.py:27-52
+(generate), :131-160 (integrate), :163-177 (transit_times, TTV), :179-231 (analyze), as
+driven by simulations/generate_simulations.py:41-110, simulations/simulation_grid.py:136-153
+and nbody/nested.py:85-95.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import (F_DEVICE_PTRS, F_LS_OC, F_LS_RV, F_MEAN_OMEGA, F_MEANS, F_ORBIT, F_PLANET1_ONLY,
+                   F_RV, F_SERIES, NBT_NPAR, SCHEME_M64, SCHEMES, TT_GRID_LINEAR, TT_REFINED)
+
+
+def _as_params(params):
+    p = np.ascontiguousarray(params, dtype=np.float64)
+    if p.ndim == 2:
+        p = p[None]
+    if p.ndim != 3 or p.shape[2] != NBT_NPAR:
+        raise ValueError("params must be [B, n_bodies, %d] (m, P, e, inc, Omega, omega, f)" % NBT_NPAR)
+    if not (2 <= p.shape[1] <= _abi.NBT_MAX_BODIES):
+        raise ValueError("n_bodies must be in 2..%d" % _abi.NBT_MAX_BODIES)
+    return p
+
+
+class Plan:
+    """Configuration + CSR layout of one nbt_run call (host planning through libnbt's helpers)."""
+
+    def __init__(self, params, n_days, n_outputs, substeps=None, scheme=SCHEME_M64,
+                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True):
+        lib = _abi.load()
+        self.params = _as_params(params)
+        B, N, _ = self.params.shape
+        if isinstance(scheme, str):
+            scheme = SCHEMES[scheme]
+        if int(n_outputs) < 2:
+            raise ValueError("Noutputs must be >= 2")
+        self.cfg = _abi.make_config(B, N, n_days, n_outputs, substeps=0, scheme=scheme,
+                                    tt_mode=tt_mode, flags=flags, device=device)
+        self.B, self.N, self.Np = B, N, N - 1
+        # composition steps per output interval
+        if substeps is None:
+            self.substeps = np.zeros(B, dtype=np.int32)
+            _abi.check(lib.nbt_plan_substeps(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.substeps, C.c_int32)), lib)
+        elif np.isscalar(substeps):
+            self.cfg.substeps = int(substeps)
+            self.substeps = None
+        else:
+            self.substeps = np.ascontiguousarray(substeps, dtype=np.int32)
+            assert self.substeps.shape == (B,)
+        # launch order: equal trip counts within a warp
+        self.order = None
+        if sort and self.substeps is not None and B > 1 and self.substeps.min() != self.substeps.max():
+            self.order = np.zeros(B, dtype=np.int32)
+            _abi.check(lib.nbt_plan_order(C.byref(self.cfg), _abi.ptr(self.substeps, C.c_int32), _abi.ptr(self.order, C.c_int32)), lib)
+        # CSR capacities of the transit products
+        self.tt_offsets = np.zeros(B * self.Np + 1, dtype=np.int64)
+        cap = lib.nbt_plan_tt(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.tt_offsets, C.c_int64))
+        if cap < 0:
+            _abi.check(cap, lib)
+        self.cfg.tt_cap_max = cap
+        self.ls_offsets = None
+        if flags & F_LS_OC:
+            self.ls_offsets = np.zeros(B * self.Np + 1, dtype=np.int64)
+            _abi.check(lib.nbt_plan_ls(C.byref(self.cfg), _abi.ptr(self.tt_offsets, C.c_int64), _abi.ptr(self.ls_offsets, C.c_int64)), lib)
+        self.n_steps = int(lib.nbt_count_steps(C.byref(self.cfg), _abi.ptr(self.substeps, C.c_int32)))
+        self.rv_nfreq = 0
+        if flags & F_LS_RV:
+            step = float(n_days) / (int(n_outputs) - 1)
+            self.rv_nfreq = int(lib.nbt_ls_nfreq(float(n_days) - step, self.cfg.ls_rv_minfreq, self.cfg.ls_rv_maxfreq,
+                                                 self.cfg.ls_samples_per_peak))
+
+    @property
+    def times(self):
+        return np.linspace(0.0, self.cfg.n_days, self.cfg.n_outputs)  # simulation.py:135
+
+
+class Buffers:
+    """Caller-owned host output buffers of one Plan (numpy; pinned when torch+CUDA is present)."""
+
+    def __init__(self, plan, pinned=False):
+        self.plan = plan
+        B, Np, NO = plan.B, plan.Np, plan.cfg.n_outputs
+        fl = plan.cfg.flags
+        self._keep = []
+        z = lambda shape, dt=np.float64: self._alloc(shape, dt, pinned)
+        ntot = int(plan.tt_offsets[-1])
+        self.tt = z(ntot); self.ttv = z(ntot)
+        self.n_tt = z(B * Np, np.int32)
+        self.period = z(B * Np); self.t0 = z(B * Np); self.ttv_max = z(B * Np)
+        self.mean_a = z(B * Np); self.mean_e = z(B * Np); self.mean_inc = z(B * Np)
+        self.mean_omega = z(B * Np)
+        self.status = z(B, np.int32)
+        self.rv = z((NO - 1, B)) if fl & F_RV else None
+        self.rv_max = z(B) if fl & F_RV else None
+        nq = (NO + plan.cfg.orbit_stride - 1) // plan.cfg.orbit_stride
+        self.orbit_xz = z((nq, B, Np, 2)) if fl & F_ORBIT else None
+        self.series = z((NO, B, 3 + 10 * Np)) if fl & F_SERIES else None
+        self.ls_oc_power = z(int(plan.ls_offsets[-1])) if fl & F_LS_OC else None
+        self.ls_oc_nfreq = z(B * Np, np.int32) if fl & F_LS_OC else None
+        self.ls_rv_power = z((B, plan.rv_nfreq)) if fl & F_LS_RV else None
+
+    def _alloc(self, shape, dtype, pinned):
+        if pinned:
+            import torch
+            t = torch.zeros(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32, pin_memory=True)
+            self._keep.append(t)
+            return t.numpy()
+        return np.zeros(shape, dtype=dtype)
+
+    def as_structs(self, params=None):
+        p = self.plan
+        par = p.params if params is None else _as_params(params)
+        inp = _abi.nbt_inputs()
+        inp.params = _abi.ptr(par)
+        inp.substeps = _abi.ptr(p.substeps, C.c_int32)
+        inp.order = _abi.ptr(p.order, C.c_int32)
+        inp.tt_offsets = _abi.ptr(p.tt_offsets, C.c_int64)
+        inp.ls_offsets = _abi.ptr(p.ls_offsets, C.c_int64)
+        out = _abi.nbt_outputs()
+        for name, ct in (("tt", C.c_double), ("ttv", C.c_double), ("n_tt", C.c_int32), ("period", C.c_double),
+                         ("t0", C.c_double), ("ttv_max", C.c_double), ("mean_a", C.c_double),
+                         ("mean_e", C.c_double), ("mean_inc", C.c_double), ("mean_omega", C.c_double),
+                         ("status", C.c_int32), ("rv", C.c_double), ("rv_max", C.c_double),
+                         ("orbit_xz", C.c_double), ("series", C.c_double), ("ls_oc_power", C.c_double),
+                         ("ls_oc_nfreq", C.c_int32), ("ls_rv_power", C.c_double)):
+            setattr(out, name, _abi.ptr(getattr(self, name), ct))
+        self._structs = (inp, out, par)  # keep alive
+        return inp, out
+
+    # ---- views -------------------------------------------------------------------------
+    def n_transits(self, b, j):
+        p = self.plan
+        sp = b * p.Np + j
+        cap = int(p.tt_offsets[sp + 1] - p.tt_offsets[sp])
+        return min(int(self.n_tt[sp]), cap)
+
+    def tt_of(self, b, j):
+        off = int(self.plan.tt_offsets[b * self.plan.Np + j])
+        return self.tt[off:off + self.n_transits(b, j)]
+
+    def ttv_of(self, b, j):
+        """O-C of planet j; the reference's `<3 transits` fallback is ttv=[0] (simulation.py:207-210)."""
+        off = int(self.plan.tt_offsets[b * self.plan.Np + j])
+        n = self.n_transits(b, j)
+        return self.ttv[off:off + (n if n >= 3 else 1)]
+
+    def ls_oc_of(self, b, j):
+        """(freq, power) of the O-C periodogram of planet j (tools.py:97-104 on arange(n), ttv)."""
+        p = self.plan
+        sp = b * p.Np + j
+        nf = int(self.ls_oc_nfreq[sp])
+        off = int(p.ls_offsets[sp])
+        n = max(self.n_transits(b, j), 2)
+        df = 1.0 / (n - 1.0) / p.cfg.ls_samples_per_peak
+        return p.cfg.ls_oc_minfreq + df * np.arange(nf), self.ls_oc_power[off:off + nf]
+
+    def ls_rv_of(self, b):
+        p = self.plan
+        step = p.cfg.n_days / (p.cfg.n_outputs - 1)
+        T = p.cfg.n_days - step
+        df = 1.0 / T / p.cfg.ls_samples_per_peak
+        return p.cfg.ls_rv_minfreq + df * np.arange(p.rv_nfreq), self.ls_rv_power[b]
+
+
+def run(plan, buffers=None, stream=None):
+    """One nbt_run over host buffers (H2D + kernels + D2H inside the call).  Raises without CUDA."""
+    lib = _abi.load()
+    if buffers is None:
+        buffers = Buffers(plan)
+    inp, out = buffers.as_structs()
+    cfg = plan.cfg
+    cfg.flags &= ~F_DEVICE_PTRS
+    rc = lib.nbt_run(C.byref(cfg), C.byref(inp), C.byref(out), C.c_void_p(stream or 0))
+    _abi.check(rc, lib)
+    return buffers
+
+
+def run_batch(params, n_days, n_outputs, **kw):
+    plan = Plan(params, n_days, n_outputs, **kw)
+    return run(plan)
+
+
+# -------------------------------------------------------------------------------------------
+# Multi-GPU: shard by system index, one process per GPU, no collective on the data path.
+# -------------------------------------------------------------------------------------------
+def shard_range(n_systems, rank, world_size):
+    """Contiguous, balanced [lo, hi) slice of the batch owned by `rank`."""
+    base, rem = divmod(int(n_systems), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_results(local, n_systems, group=None):
+    """Final host gather of per-rank result dicts (arrays whose first axis is the local system
+    index) onto every rank, via torch.distributed.all_gather_object (gloo or nccl groups)."""
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    parts = [None] * ws
+    dist.all_gather_object(parts, local, group=group)
+    out = {}
+    for k in local:
+        out[k] = np.concatenate([p[k] for p in parts], axis=0)
+        assert out[k].shape[0] == n_systems
+    return out
+
+
+# -------------------------------------------------------------------------------------------
+# Device-resident form: inputs and outputs live in HBM as torch tensors, nbt_run only enqueues
+# kernels on torch's current stream (NBT_F_DEVICE_PTRS).  torch is plumbing here (memory + streams).
+# -------------------------------------------------------------------------------------------
+class DeviceBuffers:
+    _OUT = (("tt", "f8", "ntt"), ("ttv", "f8", "ntt"), ("n_tt", "i4", "nsp"), ("period", "f8", "nsp"),
+            ("t0", "f8", "nsp"), ("ttv_max", "f8", "nsp"), ("mean_a", "f8", "nsp"), ("mean_e", "f8", "nsp"),
+            ("mean_inc", "f8", "nsp"), ("mean_omega", "f8", "nsp"), ("status", "i4", "B"))
+
+    def __init__(self, plan, device=None):
+        import torch
+        self.torch = torch
+        self.plan = plan
+        self.device = torch.device("cuda", plan.cfg.device) if device is None else torch.device(device)
+        B, Np, NO = plan.B, plan.Np, plan.cfg.n_outputs
+        fl = plan.cfg.flags
+        sizes = {"ntt": int(plan.tt_offsets[-1]), "nsp": B * Np, "B": B}
+        dev = self.device
+        up = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+        self.params, self.substeps, self.order = up(plan.params), up(plan.substeps), up(plan.order)
+        self.tt_offsets, self.ls_offsets = up(plan.tt_offsets), up(plan.ls_offsets)
+        for name, dt, key in self._OUT:
+            setattr(self, name, torch.zeros(max(sizes[key], 1), dtype=torch.float64 if dt == "f8" else torch.int32, device=dev))
+        f8 = lambda *shape: torch.zeros(*shape, dtype=torch.float64, device=dev)
+        self.rv = f8(NO - 1, B) if fl & F_RV else None
+        self.rv_max = f8(B) if fl & F_RV else None
+        nq = (NO + plan.cfg.orbit_stride - 1) // plan.cfg.orbit_stride
+        self.orbit_xz = f8(nq, B, Np, 2) if fl & F_ORBIT else None
+        self.series = f8(NO, B, 3 + 10 * Np) if fl & F_SERIES else None
+        self.ls_oc_power = f8(max(int(plan.ls_offsets[-1]), 1)) if fl & F_LS_OC else None
+        self.ls_oc_nfreq = torch.zeros(B * Np, dtype=torch.int32, device=dev) if fl & F_LS_OC else None
+        self.ls_rv_power = f8(B, plan.rv_nfreq) if fl & F_LS_RV else None
+
+    @staticmethod
+    def _p(t, ct):
+        return C.cast(C.c_void_p(0 if t is None else t.data_ptr()), C.POINTER(ct))
+
+    def as_structs(self):
+        inp = _abi.nbt_inputs()
+        inp.params = self._p(self.params, C.c_double)
+        inp.substeps = self._p(self.substeps, C.c_int32)
+        inp.order = self._p(self.order, C.c_int32)
+        inp.tt_offsets = self._p(self.tt_offsets, C.c_int64)
+        inp.ls_offsets = self._p(self.ls_offsets, C.c_int64)
+        out = _abi.nbt_outputs()
+        for name, ct in (("tt", C.c_double), ("ttv", C.c_double), ("n_tt", C.c_int32), ("period", C.c_double),
+                         ("t0", C.c_double), ("ttv_max", C.c_double), ("mean_a", C.c_double),
+                         ("mean_e", C.c_double), ("mean_inc", C.c_double), ("mean_omega", C.c_double),
+                         ("status", C.c_int32), ("rv", C.c_double), ("rv_max", C.c_double),
+                         ("orbit_xz", C.c_double), ("series", C.c_double), ("ls_oc_power", C.c_double),
+                         ("ls_oc_nfreq", C.c_int32), ("ls_rv_power", C.c_double)):
+            setattr(out, name, self._p(getattr(self, name), ct))
+        return inp, out
+
+    def to_host(self):
+        """Copy every output into a host Buffers (for checks)."""
+        hb = Buffers(self.plan)
+        for name in ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega",
+                     "status", "rv", "rv_max", "orbit_xz", "series", "ls_oc_power", "ls_oc_nfreq", "ls_rv_power"):
+            t = getattr(self, name)
+            h = getattr(hb, name)
+            if t is not None and h is not None:
+                h[...] = t.cpu().numpy().reshape(-1)[:h.size].reshape(h.shape)
+        return hb
+
+
+def run_device(plan, dbuf, timing=False):
+    """Enqueue the whole path on torch's current stream over device-resident buffers (no copies,
+    no synchronisation)."""
+    lib = _abi.load()
+    inp, out = dbuf.as_structs()
+    cfg = plan.cfg
+    saved = cfg.flags
+    cfg.flags = saved | F_DEVICE_PTRS | (_abi.F_TIMING if timing else 0)
+    try:
+        stream = dbuf.torch.cuda.current_stream(dbuf.device).cuda_stream
+        rc = lib.nbt_run(C.byref(cfg), C.byref(inp), C.byref(out), C.c_void_p(stream))
+    finally:
+        cfg.flags = saved
+    _abi.check(rc, lib)
+    return dbuf
+
+
+def stage_timing():
+    """Device milliseconds of the last timed nbt_run on this thread: (front end, fit, ls_oc, rv)."""
+    lib = _abi.load()
+    ms = np.zeros(4)
+    _abi.check(lib.nbt_timing(_abi.ptr(ms)), lib)
+    return ms

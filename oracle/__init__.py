@@ -98,7 +98,7 @@ def lomb_scargle(t, y, minfreq=1.0 / 365, maxfreq=0.5, samples_per_peak=10):
     y = np.ascontiguousarray(y, dtype=np.float64)
     T = t.max() - t.min()
     nf = lib().nbo_ls_nfreq(T, minfreq, maxfreq, samples_per_peak)
-    df = 1.0 / (samples_per_peak * T)
+    df = 1.0 / T / samples_per_peak
     power = np.zeros(nf)
     lib().nbo_lomb_scargle(_abi.ptr(t), _abi.ptr(y), len(t), minfreq, df, nf, _abi.ptr(power))
     return minfreq + df * np.arange(nf), power

@@ -215,7 +215,12 @@ static int ias15_step(ias15_t* I, double dt) {
     accel(&I->s, x0, a0); I->n_force++;
 
     /* predict b for this step from the previous step's b (ratio q), plus the last correction */
-    if (I->have_b) {
+    if (I->have_b && dt / I->dt_last > 20.0) {
+        /* a very large step-size increase (e.g. the step after a short landing step): do not
+         * extrapolate the old series by q^7, start the predictor-corrector from zero */
+        for (int i = 0; i < n3; i++)
+            for (int k = 0; k < 7; k++) I->b[k][i] = I->e[k][i] = 0.0;
+    } else if (I->have_b) {
         double q = dt / I->dt_last, q2 = q * q, q3 = q2 * q, q4 = q2 * q2, q5 = q4 * q, q6 = q3 * q3,
                q7 = q6 * q;
         for (int i = 0; i < n3; i++) {
@@ -505,10 +510,13 @@ double nbo_maxavg(const double* x, int n) {
     return r;
 }
 
-/* astropy autofrequency grid size (tools.py:104): Nf = 1 + round((fmax - fmin) * spp * T) */
+/* astropy autofrequency grid (tools.py:104) [3P]: df = 1.0 / baseline / samples_per_peak;
+ * Nf = 1 + int(np.round((fmax - fmin) / df)) (np.round = round-half-even = rint);
+ * freq = fmin + df * arange(Nf). */
+double nbo_ls_df(double baseline, int spp) { return 1.0 / baseline / (double)spp; }
 int64_t nbo_ls_nfreq(double baseline, double minfreq, double maxfreq, int spp) {
-    double df = 1.0 / (spp * baseline);
-    return 1 + (int64_t)llround((maxfreq - minfreq) / df);
+    double df = nbo_ls_df(baseline, spp);
+    return 1 + (int64_t)rint((maxfreq - minfreq) / df);
 }
 
 /* Generalised (floating-mean) Lomb-Scargle, standard normalisation, unit weights:
@@ -610,7 +618,7 @@ static void run_one(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
                 double T = times[NO - 1] - times[1];
                 int64_t nf = nbo_ls_nfreq(T, cfg->ls_rv_minfreq, cfg->ls_rv_maxfreq, cfg->ls_samples_per_peak);
                 nbo_lomb_scargle(times + 1, rvs, NO - 1, cfg->ls_rv_minfreq,
-                                 1.0 / (cfg->ls_samples_per_peak * T), nf, out->ls_rv_power + (size_t)b * nf);
+                                 nbo_ls_df(T, cfg->ls_samples_per_peak), nf, out->ls_rv_power + (size_t)b * nf);
             }
             free(rvs);
         }
@@ -651,7 +659,7 @@ static void run_one(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
             } else { /* simulation.py:207-210 fallback: per = objects P, t0 = 0, ttv = [0] */
                 status |= NBT_S_FEW_TRANSITS;
                 out->period[sp] = par[(j + 1) * NBT_NPAR + NBT_P_P]; out->t0[sp] = 0.0;
-                if (cap > 0) out->ttv[off] = 0.0;
+                for (int k = 0; k < (n > 1 ? n : 1) && k < cap; k++) out->ttv[off + k] = 0.0;
                 out->ttv_max[sp] = 0.0;
             }
             if ((cfg->flags & NBT_F_LS_OC) && out->ls_oc_power && in->ls_offsets) {
@@ -664,7 +672,7 @@ static void run_one(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
                     double* ep = (double*)malloc(sizeof(double) * n);
                     for (int k = 0; k < n; k++) ep[k] = k;
                     nbo_lomb_scargle(ep, out->ttv + off, n, cfg->ls_oc_minfreq,
-                                     1.0 / (cfg->ls_samples_per_peak * T), nf, out->ls_oc_power + loff);
+                                     nbo_ls_df(T, cfg->ls_samples_per_peak), nf, out->ls_oc_power + loff);
                     free(ep);
                 }
                 out->ls_oc_nfreq[sp] = (int32_t)nf;

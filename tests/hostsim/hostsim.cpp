@@ -1,0 +1,71 @@
+// hostsim.cpp — TEST INFRASTRUCTURE.  Compiles nbody_ai_b200/csrc/nbt_core.cuh for the host so
+// that the integrator's arithmetic (the exact functions the CUDA kernel calls per thread) can be
+// checked against the oracle in the GPU-less container (pytest -m "not gpu") and used to
+// calibrate the sub-step rule.  Never loaded by the product package.
+#include <cstring>
+#include <vector>
+
+#include "../../nbody_ai_b200/csrc/nbt_core.cuh"
+
+template <int NP>
+static void run_np(const nbt_run_args& A) {
+    for (int g = 0; g < A.B; g++) nbt_simulate_system<NP>(A, A.order ? A.order[g] : g);
+}
+
+extern "C" int hostsim_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out) {
+    nbt_run_args A;
+    std::memset(&A, 0, sizeof A);
+    A.params = in->params; A.substeps = (cfg->substeps > 0) ? nullptr : in->substeps; A.order = in->order;
+    A.tt_offsets = in->tt_offsets;
+    A.tt = out->tt; A.n_tt = out->n_tt; A.mean_a = out->mean_a; A.mean_e = out->mean_e;
+    A.mean_inc = out->mean_inc; A.mean_omega = out->mean_omega; A.status = out->status;
+    A.rv = out->rv; A.orbit_xz = out->orbit_xz; A.series = out->series;
+    A.B = cfg->n_systems; A.n_outputs = cfg->n_outputs; A.substeps_all = cfg->substeps;
+    A.tt_mode = cfg->tt_mode; A.flags = cfg->flags; A.orbit_stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
+    A.n_days = cfg->n_days; A.scheme = nbt_make_scheme(cfg->scheme);
+    switch (cfg->n_bodies - 1) {
+    case 1: run_np<1>(A); break;
+    case 2: run_np<2>(A); break;
+    case 3: run_np<3>(A); break;
+    case 4: run_np<4>(A); break;
+    case 5: run_np<5>(A); break;
+    case 6: run_np<6>(A); break;
+    case 7: run_np<7>(A); break;
+    case 8: run_np<8>(A); break;
+    default: return -1;
+    }
+    return 0;
+}
+
+// custom scheme (for calibration sweeps): a[S], b[S+1]
+extern "C" int hostsim_run_scheme(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, int S,
+                                  const double* a, const double* b) {
+    nbt_run_args A;
+    std::memset(&A, 0, sizeof A);
+    A.params = in->params; A.substeps = (cfg->substeps > 0) ? nullptr : in->substeps; A.order = in->order;
+    A.tt_offsets = in->tt_offsets;
+    A.tt = out->tt; A.n_tt = out->n_tt; A.mean_a = out->mean_a; A.mean_e = out->mean_e;
+    A.mean_inc = out->mean_inc; A.mean_omega = out->mean_omega; A.status = out->status;
+    A.rv = out->rv; A.orbit_xz = out->orbit_xz; A.series = out->series;
+    A.B = cfg->n_systems; A.n_outputs = cfg->n_outputs; A.substeps_all = cfg->substeps;
+    A.tt_mode = cfg->tt_mode; A.flags = cfg->flags; A.orbit_stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
+    A.n_days = cfg->n_days;
+    A.scheme.S = S;
+    for (int i = 0; i < NBT_MAX_STAGES; i++) A.scheme.a[i] = i < S ? a[i] : 0.0;
+    for (int i = 0; i <= NBT_MAX_STAGES; i++) A.scheme.b[i] = i <= S ? b[i] : 0.0;
+    switch (cfg->n_bodies - 1) {
+    case 1: run_np<1>(A); break;
+    case 2: run_np<2>(A); break;
+    case 3: run_np<3>(A); break;
+    case 4: run_np<4>(A); break;
+    default: return -1;
+    }
+    return 0;
+}
+
+// single Kepler drift, for unit tests against the closed-form two-body solution
+extern "C" int hostsim_kepler(double mu, double h, double* state6) {
+    int status = 0;
+    nbt_kepler_drift(mu, h, state6[0], state6[1], state6[2], state6[3], state6[4], state6[5], status);
+    return status;
+}
