@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""Benchmark of the batched TTV hot path (BASELINE.json metric: FP64 N-body system-steps/s and
+TTV sims/s at 1/2/4/8 B200 beside the host CPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (config C2 of BASELINE.json): random 2-planet systems from the priors of
+randomize() (nbody/simulation.py:54-129) with the omega sweep of
+simulations/generate_simulations.py:83-107 — 10 000 draws x (1 + 6 omega variants) = 70 000
+simulations per GPU per step; 365 d sampled hourly (8760 outputs); products per planet: transit
+times, linear ephemeris, O-C, maxavg, O-C periodogram, means of a/e/inc/omega.  A step is one
+pass of the whole path over that batch.  Weak scaling: every rank owns its own 70 000 systems.
+
+`value` is whole-job TTV sims/s with inputs resident in HBM (torch device tensors, kernels enqueued
+through the C ABI with NBT_F_DEVICE_PTRS); `e2e` is the same through nbt_run with HOST buffers
+(H2D of the parameter block and plan, D2H of every product inside the timed call);
+`system_steps_per_s` counts kick+drift stages.  The roofline is the FP64 vector pipe, measured
+live with a DFMA-chain kernel (MEASURED_PEAKS.json has no FP64 figure).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DAYS, N_OUTPUTS = 365.0, 8760
+WORKLOAD = ("C2: random 2-planet systems (randomize() priors, generate_simulations.py omega sweep), "
+            "365 d @ 1 h, tt + ephemeris + O-C + maxavg + O-C periodogram + element means")
+
+
+def f_step(np_):
+    """Algorithmic FLOPs per system-step (FMA = 2, div/sqrt = 1)."""
+    return 272 * np_ + 12.5 * np_ * (np_ + 1) - 40
+
+
+F_OUT = 100  # per planet per output sample (Jacobi a, e, inc + crossing test)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.rows, self.stop_flag, self.gpu = [], False, gpu_index
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def cpu_path(params, n_threads=0):
+    """The reference algorithm on host cores: oracle (IAS15 restatement + analyze semantics)."""
+    import oracle
+    from nbody_ai_b200 import _abi, engine
+    plan = engine.Plan(params, N_DAYS, N_OUTPUTS, substeps=1, flags=_abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC)
+    buf = engine.Buffers(plan)
+    nt = n_threads or oracle.max_threads()
+    t0 = time.perf_counter()
+    ias_steps = oracle.run(plan.cfg, plan.params, buf, n_threads=nt)
+    return time.perf_counter() - t0, nt, ias_steps
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  rebound/astropy are not
+    installable here, so this is the oracle port (cpu_baseline.kind = "port"), all host threads."""
+    if rank != 0:
+        return
+    from nbody_ai_b200 import workloads
+    per_step = args.ref_sample
+    need = per_step * (args.steps + args.warmup)
+    params = workloads.c2_params(max(1, (need + 6) // 7), 6, seed=0)[:need]
+    times, nt = [], 0
+    for s in range(args.steps + args.warmup):
+        dt, nt, _ = cpu_path(params[s * per_step:(s + 1) * per_step])
+        if s >= args.warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    sims = per_step * args.steps / total
+    line = {
+        "impl": "reference", "metric": "ttv_sims_per_sec", "value": sims, "unit": "sims/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_systems_per_step": per_step, "n_days": N_DAYS, "n_outputs": N_OUTPUTS},
+        "system_steps_per_s": sims * (N_OUTPUTS - 1),
+        "cpu_baseline": {"value": sims, "unit": "sims/s", "cores": nt, "kind": "port",
+                         "sample": "%d systems of the C2 batch per step, oracle (IAS15 + analyze) on %d host threads" % (per_step, nt)},
+        "e2e": {"value": sims, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from nbody_ai_b200 import _abi, engine, workloads
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _abi.load()
+    dev = torch.device("cuda", local_rank)
+
+    params = workloads.c2_params(args.draws, args.omegas, seed=rank)
+    B, Np = params.shape[0], params.shape[1] - 1
+    flags = _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC
+    plan = engine.Plan(params, N_DAYS, N_OUTPUTS, flags=flags, device=local_rank)
+    plan.pin()
+    dbuf = engine.DeviceBuffers(plan)
+    hbuf = engine.Buffers(plan, pinned=True)
+
+    # FP64 roofline denominator, measured on this GPU right now
+    tf, ms = C.c_double(0), C.c_double(0)
+    _abi.check(lib.nbt_fp64_peak(local_rank, 1 << 16, C.byref(tf), C.byref(ms)), lib)
+    fp64_peak = tf.value
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        engine.run_device(plan, dbuf)
+    torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+
+    # ---- timed region: K steps, device-resident ------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_ms = np.zeros(4)
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                       # L2 flush, outside the event pair
+        ev[k][0].record()
+        engine.run_device(plan, dbuf, timing=True)
+        ev[k][1].record()
+        ev[k][1].synchronize()
+        stage_ms += engine.stage_timing()
+    barrier()
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    clocks = sampler.finish()
+
+    # ---- end to end through the host-pointer C ABI ---------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        engine.run(plan, hbuf)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        engine.run(plan, hbuf)                      # H2D + kernels + D2H + stream sync inside
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    h2d = sum(a.nbytes for a in (plan.params, plan.substeps, plan.order, plan.tt_offsets, plan.ls_offsets) if a is not None)
+    d2h = sum(getattr(hbuf, n).nbytes for n in ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e",
+                                               "mean_inc", "mean_omega", "status", "ls_oc_power", "ls_oc_nfreq"))
+
+    # sanity: the timed device path and the host path produced the same transits
+    chk = dbuf.to_host()
+    assert np.array_equal(chk.n_tt, hbuf.n_tt), "device-resident and host-pointer paths disagree"
+    n_tt_total = int(np.minimum(hbuf.n_tt, np.diff(plan.tt_offsets)).sum())
+
+    t = torch.tensor([dev_ms, e2e_ms, stage_ms[0]], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(B), float(plan.n_steps), float(n_tt_total)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, integ_ms = (float(x) for x in t.cpu())
+    sims_all, steps_all, ntt_all = (float(x) for x in tot.cpu())
+
+    if rank == 0:
+        sims_per_s = sims_all * args.steps / (dev_ms * 1e-3)
+        steps_per_s = steps_all * args.steps / (dev_ms * 1e-3)
+        # roofline of the dominant kernel (k_integrate), per launch on this rank
+        flops = plan.n_steps * f_step(Np) + B * N_OUTPUTS * F_OUT * Np
+        integ_launch_ms = stage_ms[0] / args.steps
+        achieved = flops / (integ_launch_ms * 1e-3) * 1e-12
+        line = {
+            "metric": "ttv_sims_per_sec", "value": sims_per_s, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "systems_per_gpu": B, "draws": args.draws, "omega_variants": args.omegas,
+                       "n_planets": Np, "n_days": N_DAYS, "n_outputs": N_OUTPUTS, "scheme": "m64 (4-stage order (6,4) WH composition)",
+                       "substeps_hist": np.bincount(plan.substeps).tolist(), "parallelism": "shard-by-system x%d" % world,
+                       "l2": "256 MiB device fill between steps, outside the per-step event pairs"},
+            "system_steps_per_s": steps_per_s,
+            "system_steps_per_step": steps_all,
+            "transits_per_step": ntt_all,
+            "stage_ms_per_step": {"k_integrate": stage_ms[0] / args.steps, "k_fit": stage_ms[1] / args.steps,
+                                  "k_ls_oc": stage_ms[2] / args.steps},
+            "roofline": {"bound": "fp64", "kernel": "k_integrate<%d>" % Np, "achieved": achieved, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None,
+                         "peak_source": "nbt_fp64_peak DFMA-chain kernel measured in this run (nominal 37.2 at 1965 MHz)",
+                         "flops_per_launch": flops, "launch_ms": integ_launch_ms, "traffic": None},
+            "e2e": {"value": sims_all * args.steps / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": 3 * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            n_s = min(args.cpu_sample, B)
+            dt, nt, _ = cpu_path(params[:n_s])
+            line["cpu_baseline"] = {"value": n_s / dt, "unit": "sims/s", "cores": nt, "kind": "port",
+                                    "sample": "first %d systems of the same batch, oracle (IAS15 + analyze) on %d host threads, %.1f s" % (n_s, nt, dt)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--draws", type=int, default=10000)
+    ap.add_argument("--omegas", type=int, default=6)
+    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

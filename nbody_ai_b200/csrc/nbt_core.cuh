@@ -95,22 +95,33 @@ NBT_HD void nbt_stumpff_big(double z, double& c0, double& c1, double& c2, double
 
 NBT_HD void nbt_kepler_safe(double mu, double h, double r0, double eta, double beta, double zeta,
                             double& X, double& G1, double& G2, double& G3, double& r, int& status) {
-    // Newton with bisection-style damping on the monotone F (F' = r > 0)
+    // Newton on the monotone F (F' = r > 0), safeguarded by a bracket that every iterate tightens;
+    // a step that leaves the bracket is replaced by its midpoint.  Converged when the step drops
+    // to round-off (a few ulp of X) or F vanishes.
+    (void)mu;
     double Xc = X;
+    double lo = -INFINITY, hi = INFINITY;
     bool ok = false;
-    for (int it = 0; it < 60; it++) {
+    for (int it = 0; it < 80; it++) {
         double c0, c1, c2, c3;
-        double X2 = Xc * Xc;
+        const double X2 = Xc * Xc;
         nbt_stumpff_big(beta * X2, c0, c1, c2, c3);
         G1 = Xc * c1; G2 = X2 * c2; G3 = X2 * Xc * c3;
-        double F = fma(r0, Xc, fma(eta, G2, zeta * G3)) - h;
+        const double F = fma(r0, Xc, fma(eta, G2, zeta * G3)) - h;
         r = fma(eta, G1, fma(zeta, G2, r0));
-        double d = -F / r;
-        Xc += d;
-        if (fabs(d) <= 1e-15 * fabs(Xc) || d == 0.0) { ok = true; break; }
+        if (F > 0.0) hi = Xc; else lo = Xc;
+        if (F == 0.0) { ok = true; break; }
+        double Xn = Xc - F / r;
+        if (!(r > 0.0) || !(Xn > lo && Xn < hi)) {
+            if (isfinite(lo) && isfinite(hi)) Xn = 0.5 * (lo + hi);
+            else Xn = (F > 0.0) ? Xc - fmax(fabs(Xc), fabs(h) / r0) : Xc + fmax(fabs(Xc), fabs(h) / r0);
+        }
+        const double d = Xn - Xc;
+        Xc = Xn;
+        if (fabs(d) <= 8.0 * 2.220446049250313e-16 * fabs(Xc)) { ok = true; break; }
     }
     double c0, c1, c2, c3;
-    double X2 = Xc * Xc;
+    const double X2 = Xc * Xc;
     nbt_stumpff_big(beta * X2, c0, c1, c2, c3);
     G1 = Xc * c1; G2 = X2 * c2; G3 = X2 * Xc * c3;
     r = fma(eta, G1, fma(zeta, G2, r0));

@@ -77,6 +77,19 @@ class Plan:
             self.rv_nfreq = int(lib.nbt_ls_nfreq(float(n_days) - step, self.cfg.ls_rv_minfreq, self.cfg.ls_rv_maxfreq,
                                                  self.cfg.ls_samples_per_peak))
 
+    def pin(self):
+        """Move the plan's input arrays into page-locked host memory (torch), so that the H2D
+        copies inside nbt_run are true asynchronous DMA."""
+        import torch
+        self._pinned = []
+        for name in ("params", "substeps", "order", "tt_offsets", "ls_offsets"):
+            a = getattr(self, name)
+            if a is not None:
+                t = torch.from_numpy(a).pin_memory()
+                self._pinned.append(t)
+                setattr(self, name, t.numpy())
+        return self
+
     @property
     def times(self):
         return np.linspace(0.0, self.cfg.n_days, self.cfg.n_outputs)  # simulation.py:135

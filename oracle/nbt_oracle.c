@@ -187,8 +187,8 @@ typedef struct {
     double a0[3 * MAXN];
     double b[7][3 * MAXN], e[7][3 * MAXN], g[7][3 * MAXN];
     double csx[3 * MAXN], csv[3 * MAXN]; /* compensated-summation carries */
-    int have_b;
-    long n_steps, n_force;
+    int have_b, gave_up;
+    long n_steps, n_force, n_reject, max_steps;
 } ias15_t;
 
 static void ias15_init(ias15_t* I, const sys_t* s) {
@@ -196,6 +196,7 @@ static void ias15_init(ias15_t* I, const sys_t* s) {
     memset(I, 0, sizeof *I);
     I->s = *s;
     I->dt = 1e-3; /* REBOUND's default initial dt */
+    I->max_steps = 2000000000L;
 }
 
 static inline void add_cs(double* sum, double* carry, double inc) {
@@ -295,6 +296,7 @@ static int ias15_step(ias15_t* I, double dt) {
     double dt_new = (err > 0 && isfinite(err)) ? dt * pow(eps_b / err, 1.0 / 7.0) : dt / safety;
     if (fabs(dt_new / dt) < safety) { /* reject and retry with the smaller step */
         I->dt = dt_new;
+        I->n_reject++;
         if (I->have_b) { /* undo prediction: restore b as of the end of the last step */
             for (int i = 0; i < n3; i++)
                 for (int k = 0; k < 7; k++) I->b[k][i] = I->e[k][i] = 0.0;
@@ -327,6 +329,9 @@ static int ias15_step(ias15_t* I, double dt) {
 /* sim.integrate(t_end) with exact_finish_time=1: the last step is shortened to land on t_end */
 static void ias15_integrate_to(ias15_t* I, double t_end) {
     while (I->t < t_end) {
+        /* step budget: a close encounter drives the adaptive step towards zero (REBOUND would
+         * crawl through it too); the oracle gives up and the caller marks the run non-finite */
+        if (I->n_steps + I->n_reject > I->max_steps) { I->gave_up = 1; return; }
         double remaining = t_end - I->t;
         if (remaining <= 1e-14 * fabs(t_end)) { I->t = t_end; break; }
         double dt = I->dt, keep = I->dt;
@@ -441,11 +446,13 @@ long nbo_integrate_series(const double* params, int n_bodies, double n_days, int
     build_system(params, n_bodies, &s);
     ias15_t* I = (ias15_t*)malloc(sizeof(ias15_t));
     ias15_init(I, &s);
+    I->max_steps = 200L * n_outputs + 100000L;
     int W = 3 + 10 * (n_bodies - 1);
     double step = n_days / (double)(n_outputs - 1); /* np.linspace(0, Ndays, Noutputs) */
     for (int o = 0; o < n_outputs; o++) {
         double t = (o == n_outputs - 1) ? n_days : o * step;
-        ias15_integrate_to(I, t);
+        if (!I->gave_up) ias15_integrate_to(I, t);
+        if (I->gave_up) { for (int k = 0; k < W; k++) series[(size_t)o * W + k] = NAN; continue; }
         sample_row(&I->s, series + (size_t)o * W);
     }
     if (final_state)

@@ -1,0 +1,102 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/nbt.h declares, plans on
+the host, and FAILS LOUDLY (no CPU fallback) when asked to compute without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nbody_ai_b200 import _abi, engine, workloads
+from conftest import ROOT
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "nbt.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(nbt_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_exports_every_declared_symbol(nbt):
+    syms = declared_symbols()
+    assert len(syms) >= 17
+    for s in syms:
+        assert hasattr(nbt, s), "libnbt.so does not export %s" % s
+    assert nbt.nbt_abi_version() == _abi.NBT_ABI_VERSION
+
+
+def test_struct_layout_matches_header(nbt):
+    # nbt_run rejects a config whose struct_size disagrees with the C side
+    cfg = _abi.make_config(1, 3, 10.0, 11, substeps=1)
+    off = np.zeros(3, dtype=np.int64)
+    par = workloads.c1_params(1)[:, :3].copy()
+    assert nbt.nbt_plan_tt(C.byref(cfg), _abi.ptr(par), _abi.ptr(off, C.c_int64)) > 0
+    cfg.struct_size += 4
+    assert nbt.nbt_plan_tt(C.byref(cfg), _abi.ptr(par), _abi.ptr(off, C.c_int64)) == -2
+    assert b"struct_size" in nbt.nbt_last_error()
+
+
+def test_plan_helpers(nbt):
+    par = workloads.c2_params(50, 2, seed=3)
+    plan = engine.Plan(par, 365.0, 8760, flags=_abi.F_MEANS | _abi.F_LS_OC)
+    B, Np = plan.B, plan.Np
+    cap = np.diff(plan.tt_offsets)
+    want = np.minimum(np.ceil(1.05 * 365.0 / par[:, 1:, 1]) + 3, 8760).astype(np.int64).ravel()
+    assert np.array_equal(cap, want) and plan.cfg.tt_cap_max == cap.max()
+    # launch order: a permutation sorted by decreasing substeps
+    if plan.order is not None:
+        assert sorted(plan.order) == list(range(B))
+        assert np.all(np.diff(plan.substeps[plan.order]) <= 0)
+    # O-C periodogram capacity = astropy grid for the largest possible transit count
+    lcap = np.diff(plan.ls_offsets)
+    for c, l in zip(cap[:20], lcap[:20]):
+        assert l == (1 + int(np.round((0.5 - 1 / 180.) / (1.0 / (c - 1.0) / 10))) if c >= 3 else 0)
+    assert plan.n_steps == int(plan.substeps.sum()) * 8759 * 4
+    # sub-step rule: P_min / dt_sub >= 60 for the M64 scheme
+    step = 365.0 / 8759
+    assert np.all(par[:, 1:, 1].min(1) / (step / plan.substeps) >= 60 - 1e-9)
+
+
+def test_invalid_arguments(nbt):
+    cfg = _abi.make_config(1, 1, 10.0, 11, substeps=1)
+    assert nbt.nbt_count_steps(C.byref(cfg), None) == -1          # n_bodies < 2
+    cfg = _abi.make_config(1, 3, 10.0, 1, substeps=1)
+    assert nbt.nbt_count_steps(C.byref(cfg), None) == -1          # n_outputs < 2
+    with pytest.raises(ValueError):
+        _abi.objects_to_params([{'m': 1.0}, {'m': 1e-3}])          # planet without a period
+    with pytest.raises(ValueError):
+        _abi.objects_to_params([{'m': 1.0}, {'m': 1e-3, 'P': 3.0, 'a': 0.04}])  # unsupported key
+
+
+def test_objects_to_params_defaults():
+    p = _abi.objects_to_params(workloads.c1_objects())
+    assert p.shape == (4, 7) and p[1, _abi.P_P] == 3.2888 and p[1, _abi.P_INC] == 3.14159 / 2
+    assert np.all(p[:, _abi.P_OMEGA_NODE] == 0) and np.all(p[:, _abi.P_F] == 0)
+
+
+@pytest.mark.skipif(_abi.load().nbt_device_count() > 0, reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly(nbt):
+    """Without a CUDA device every compute entry returns an error; the Python layer raises."""
+    par = workloads.c1_params(2)
+    plan = engine.Plan(par, 10.0, 241, flags=_abi.F_MEANS)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        engine.run(plan)
+    from nbody_ai_b200 import simulation, tools
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        simulation.generate(workloads.c1_objects(), 10, 241)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        tools.lomb_scargle(np.arange(10.0), np.arange(10.0) ** 2)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        tools.maxavg(np.arange(5.0))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        tools.TTV(np.arange(5.0), np.arange(5.0))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under nbody_ai_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "nbody_ai_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "libnbt_oracle" not in txt, fn

@@ -1,0 +1,67 @@
+"""Multi-GPU host logic on CPU: world_size-2 gloo job, shard by system index, final host gather.
+The per-shard compute here is the host build of the device integrator (tests/hostsim) standing in
+for the GPU — what is under test is the partition + gather, which must reproduce the unsharded
+result bit for bit (systems are independent, no data-path collective)."""
+import ctypes as C
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from nbody_ai_b200 import _abi, engine, workloads
+from conftest import ROOT
+
+
+def test_shard_range_partition():
+    for n in (0, 1, 7, 64, 70001):
+        for ws in (1, 2, 3, 8):
+            parts = [engine.shard_range(n, r, ws) for r in range(ws)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _host_products(par):
+    hs = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
+    plan = engine.Plan(par, 40.0, 961, substeps=1, flags=_abi.F_MEANS)
+    buf = engine.Buffers(plan)
+    inp, out = buf.as_structs()
+    assert hs.hostsim_run(C.byref(plan.cfg), C.byref(inp), C.byref(out)) == 0
+    B, Np = plan.B, plan.Np
+    first_tt = np.array([[buf.tt_of(b, j)[0] if buf.n_transits(b, j) else np.nan for j in range(Np)] for b in range(B)])
+    return {"n_tt": buf.n_tt.reshape(B, Np).copy(), "mean_a": buf.mean_a.reshape(B, Np).copy(),
+            "mean_e": buf.mean_e.reshape(B, Np).copy(), "first_tt": first_tt, "status": buf.status.copy()}
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    par = workloads.c2_params(3, 2, seed=21)           # 9 systems: uneven split over 2 ranks
+    lo, hi = engine.shard_range(len(par), rank, world)
+    local = _host_products(par[lo:hi])
+    full = engine.gather_results(local, len(par))
+    if rank == 0:
+        q.put({k: v for k, v in full.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_and_gather(built):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _host_products(workloads.c2_params(3, 2, seed=21))
+    for k in want:
+        assert np.array_equal(got[k], want[k], equal_nan=True), k
