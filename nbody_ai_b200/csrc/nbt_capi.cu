@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(128) k_fit(const nbt_fit_args F) {
 // (2 DMUL + 2 DFMA) and are re-seeded exactly every NBT_LS_RESYNC samples.
 // ---------------------------------------------------------------------------------------------
 #define NBT_LS_RESYNC 64
+#define NBT_LS_TINY 1e-14
 
 __device__ __forceinline__ double ls_finish(double C, double S, double C2, double S2, double YC, double YS,
                                             double invn, double YY) {
@@ -191,7 +192,11 @@ __device__ __forceinline__ double ls_finish(double C, double S, double C2, doubl
     const double rot = C2 * c2t + S2 * s2t;
     const double CC = 0.5 * (1.0 + rot) - Ct * Ct;
     const double SS = 0.5 * (1.0 - rot) - St * St;
-    return (YCt * YCt / CC + YSt * YSt / SS) / YY;
+    // A vanishing normalisation (e.g. the sine term at exactly the Nyquist frequency of integer
+    // epochs) carries no power: the term is dropped instead of returning round-off / round-off.
+    const double pc = (CC > NBT_LS_TINY) ? YCt * YCt / CC : 0.0;
+    const double ps = (SS > NBT_LS_TINY) ? YSt * YSt / SS : 0.0;
+    return (pc + ps) / YY;
 }
 
 // y: n samples at t_i = i (arbitrary origin/scale folded into nu = cycles per sample)

@@ -102,6 +102,11 @@ NBT_HD void nbt_kepler_safe(double mu, double h, double r0, double eta, double b
     double Xc = X;
     double lo = -INFINITY, hi = INFINITY;
     bool ok = false;
+    if (!(r0 > 0.0) || !isfinite(r0 + eta + beta + X)) { // broken state (collision / overflow): do not iterate
+        status |= NBT_S_KEPLER | NBT_S_NONFINITE;
+        G1 = G2 = G3 = r = NAN;
+        return;
+    }
     for (int it = 0; it < 80; it++) {
         double c0, c1, c2, c3;
         const double X2 = Xc * Xc;
@@ -376,53 +381,59 @@ NBT_HD double nbt_acos2(double num, double den, double disamb) {
 
 struct nbt_orbit { double P, a, e, inc, Omega, omega, M; };
 
-// a, e, inc only (the analyze() means); full = also P, Omega, omega, M
-template <bool FULL>
+// MODE 0: a, e, inc (the analyze() means); 1: + omega; 2: the full set P, Omega, omega, M.
+// Reciprocals / square roots go through the MUFU-seeded helpers (<= 1 ulp); the acos calls are
+// libdevice's.
+template <int MODE>
 NBT_HD nbt_orbit nbt_elements(double mu, double x, double y, double z, double vx, double vy, double vz) {
     nbt_orbit o;
     const double hx = y * vz - z * vy, hy = z * vx - x * vz, hz = x * vy - y * vx;
     const double h2 = fma(hx, hx, fma(hy, hy, hz * hz));
     const double v2 = fma(vx, vx, fma(vy, vy, vz * vz));
     const double r2 = fma(x, x, fma(y, y, z * z));
-    const double r = sqrt(r2);
-    const double h = sqrt(h2);
-    const double vc2 = mu / r;
-    o.a = -mu / (v2 - 2.0 * vc2);
+    const double ir = nbt_rsqrt(r2), r = r2 * ir;
+    const double ih = nbt_rsqrt(h2), h = h2 * ih;
+    const double vc2 = mu * ir;
+    o.a = -mu * nbt_rcp(v2 - 2.0 * vc2);
     const double rv = fma(x, vx, fma(y, vy, z * vz));
     const double vd2 = v2 - vc2;
-    const double imu = 1.0 / mu;
+    const double imu = nbt_rcp(mu);
     const double ex = imu * (vd2 * x - rv * vx), ey = imu * (vd2 * y - rv * vy), ez = imu * (vd2 * z - rv * vz);
-    o.e = sqrt(fma(ex, ex, fma(ey, ey, ez * ez)));
-    o.inc = nbt_acos2(hz, h, 1.0);
+    const double e2 = fma(ex, ex, fma(ey, ey, ez * ez));
+    o.e = (e2 > 0.0) ? e2 * nbt_rsqrt(e2) : 0.0;
+    {
+        const double ci = hz * ih;
+        o.inc = (ci > -1.0 && ci < 1.0) ? acos(ci) : ((ci <= -1.0) ? NBT_PI : 0.0);
+        if (!(h2 > 0.0)) o.inc = NAN;
+    }
     o.P = o.Omega = o.omega = o.M = 0.0;
-    if (FULL) {
-        const double vr = rv / r;
-        const double nmm = o.a / fabs(o.a) * sqrt(fabs(mu / (o.a * o.a * o.a)));
-        o.P = 2.0 * NBT_PI / nmm;
+    if (MODE >= 1) {
         const double nx = -hy, ny = hx, nn = sqrt(nx * nx + ny * ny);
-        o.Omega = nbt_acos2(nx, nn, ny);
-        if (o.e < 1.0) {
-            const double ea = nbt_acos2(1.0 - r / o.a, o.e, vr);
-            o.M = ea - o.e * sin(ea);
-        } else {
-            double ea = acosh((1.0 - r / o.a) / o.e);
-            if (vr < 0.0) ea = -ea;
-            o.M = o.e * sinh(ea) - ea;
-        }
         if (o.inc < 1e-8 || o.inc > NBT_PI - 1e-8) {
+            const double Omega = nbt_acos2(nx, nn, ny);
             const double pomega = nbt_acos2(ex, o.e, ey);
-            o.omega = (o.inc < 0.5 * NBT_PI) ? pomega - o.Omega : o.Omega - pomega;
+            o.omega = (o.inc < 0.5 * NBT_PI) ? pomega - Omega : Omega - pomega;
         } else {
             o.omega = nbt_acos2(nx * ex + ny * ey, nn * o.e, ez);
         }
         if (o.e <= 1e-8) o.omega = 0.0;
+        if (MODE >= 2) {
+            const double vr = rv * ir;
+            const double nmm = o.a / fabs(o.a) * sqrt(fabs(mu / (o.a * o.a * o.a)));
+            o.P = 2.0 * NBT_PI / nmm;
+            o.Omega = nbt_acos2(nx, nn, ny);
+            if (o.e < 1.0) {
+                const double ea = nbt_acos2(1.0 - r / o.a, o.e, vr);
+                o.M = ea - o.e * sin(ea);
+            } else {
+                double ea = acosh((1.0 - r / o.a) / o.e);
+                if (vr < 0.0) ea = -ea;
+                o.M = o.e * sinh(ea) - ea;
+            }
+        }
     }
+    (void)h;
     return o;
-}
-
-// omega alone (for NBT_F_MEAN_OMEGA without the full set)
-NBT_HD double nbt_omega_only(double mu, double x, double y, double z, double vx, double vy, double vz) {
-    return nbt_elements<true>(mu, x, y, z, vx, vy, vz).omega;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,6 +501,12 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
             Sx = fma(c.mr[j], s.x[j], Sx); Svx = fma(c.mr[j], s.vx[j], Svx);
         }
         const double xs = -Sx;
+        // a system whose state broke (collision, overflow, failed Kepler solve) stops here: its
+        // lane idles instead of dragging the warp through the slow fallback for the rest of the run
+        if (!isfinite(Sx + Svx) || (status & (NBT_S_KEPLER | NBT_S_NONFINITE))) {
+            status |= NBT_S_NONFINITE;
+            break;
+        }
         if (o > 0) {
 #pragma unroll
             for (int j = 0; j < NP; j++) {
@@ -524,12 +541,20 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
         xs_prev = xs; t_prev = t;
 
         if (want_means && !want_series) {
+            if (want_omega) {
 #pragma unroll
-            for (int j = 0; j < NP; j++) {
-                const nbt_orbit ob = nbt_elements<false>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
-                sum_a[j] += ob.a; sum_e[j] += ob.e; sum_i[j] += ob.inc;
-                if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
-                if (want_omega) sum_o[j] += nbt_omega_only(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+                for (int j = 0; j < NP; j++) {
+                    const nbt_orbit ob = nbt_elements<1>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+                    sum_a[j] += ob.a; sum_e[j] += ob.e; sum_i[j] += ob.inc; sum_o[j] += ob.omega;
+                    if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NP; j++) {
+                    const nbt_orbit ob = nbt_elements<0>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+                    sum_a[j] += ob.a; sum_e[j] += ob.e; sum_i[j] += ob.inc;
+                    if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
+                }
             }
         }
         if (want_orbit || want_series) {
@@ -553,7 +578,7 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
                 row[0] = xs; row[1] = -Ty; row[2] = -Tz;
 #pragma unroll
                 for (int j = 0; j < NP; j++) {
-                    const nbt_orbit ob = nbt_elements<true>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+                    const nbt_orbit ob = nbt_elements<2>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
                     double* p = row + 3 + 10 * j;
                     p[0] = dx[j] + xs; p[1] = qy[j] - Ty; p[2] = qz[j] - Tz;
                     p[3] = ob.P; p[4] = ob.a; p[5] = ob.e; p[6] = ob.inc; p[7] = ob.Omega; p[8] = ob.omega; p[9] = ob.M;

@@ -556,7 +556,9 @@ void nbo_lomb_scargle(const double* t, const double* y, int n, double f0, double
             Ct += w * cst; St += w * snt;
         }
         Cc -= Ct * Ct; Ss -= St * St;
-        power[k] = (YC * YC / Cc + YS * YS / Ss) / YY;
+        /* a vanishing normalisation (sine term at the Nyquist frequency of integer epochs) is
+         * round-off / round-off in astropy; both oracle and product drop that term instead */
+        power[k] = ((Cc > 1e-14 ? YC * YC / Cc : 0.0) + (Ss > 1e-14 ? YS * YS / Ss : 0.0)) / YY;
     }
 }
 

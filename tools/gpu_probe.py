@@ -1,0 +1,65 @@
+"""GPU probe: device-resident timings of k_integrate for a few batch shapes / flag sets.
+usage: python tools/gpu_probe.py [case ...]   (cases: c1, c1means, c1omega, c2, c2k1, c5, peak)"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from nbody_ai_b200 import _abi, engine, workloads  # noqa: E402
+from bench import f_step  # noqa: E402
+
+
+def timed(params, nd, no, flags, reps=2, **kw):
+    plan = engine.Plan(params, nd, no, flags=flags, **kw)
+    d = engine.DeviceBuffers(plan)
+    engine.run_device(plan, d)
+    torch.cuda.synchronize()
+    ms = np.zeros(4)
+    for _ in range(reps):
+        engine.run_device(plan, d, timing=True)
+        torch.cuda.synchronize()
+        ms += engine.stage_timing()
+    ms /= reps
+    h = d.to_host()
+    Np = plan.Np
+    fl = plan.n_steps * f_step(Np)
+    st = {int(s): int((h.status == s).sum()) for s in np.unique(h.status)}
+    print("  B=%d Np=%d steps=%.3g  integrate %.2f ms  fit %.3f ms  ls %.3f ms  -> %.3g steps/s  %.2f TF  status %s" % (
+        plan.B, Np, plan.n_steps, ms[0], ms[1], ms[2], plan.n_steps / (ms[0] * 1e-3), fl / (ms[0] * 1e-3) * 1e-12, st), flush=True)
+    return ms
+
+
+def main():
+    cases = sys.argv[1:] or ["peak", "c1", "c1means", "c1omega", "c2k1", "c2"]
+    lib = _abi.load()
+    for c in cases:
+        print(c, flush=True)
+        if c == "peak":
+            tf, ms = C.c_double(), C.c_double()
+            lib.nbt_fp64_peak(0, 1 << 16, C.byref(tf), C.byref(ms))
+            print("  DFMA peak %.2f TFLOP/s (%.2f ms)" % (tf.value, ms.value))
+        elif c == "c1":
+            timed(workloads.c1_params(65536), 30.0, 721, 0, substeps=1)
+        elif c == "c1means":
+            timed(workloads.c1_params(65536), 30.0, 721, _abi.F_MEANS, substeps=1)
+        elif c == "c1omega":
+            timed(workloads.c1_params(65536), 30.0, 721, _abi.F_MEANS | _abi.F_MEAN_OMEGA, substeps=1)
+        elif c == "c1small":
+            timed(workloads.c1_params(16384), 10.0, 241, _abi.F_MEANS, substeps=1, reps=1)
+        elif c == "c2k1":
+            timed(workloads.c2_params(10000, 6, 0), 30.0, 721, _abi.F_MEANS, substeps=1)
+        elif c == "c2":
+            timed(workloads.c2_params(10000, 6, 0), 30.0, 721, _abi.F_MEANS)
+        elif c == "c2full":
+            timed(workloads.c2_params(10000, 6, 0), 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, reps=1)
+        elif c == "c5":
+            timed(workloads.c5_params(65536), 30.0, 721, _abi.F_MEANS)
+
+
+if __name__ == "__main__":
+    main()
