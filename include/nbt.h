@@ -95,8 +95,8 @@ typedef struct nbt_config {
 typedef struct nbt_inputs {
     const double* params;      /* [B][n_bodies][NBT_NPAR] */
     const int32_t* substeps;   /* [B] or NULL (then cfg.substeps applies to all) */
-    const int32_t* order;      /* [B] launch order (nbt_plan_order: systems sorted by substeps so
-                                  that a warp's lanes run equal trip counts) or NULL */
+    const int32_t* order;      /* [B] launch order (nbt_plan_order: heavy systems first, equal trip
+                                  counts within a warp, unstable systems grouped) or NULL */
     const int64_t* tt_offsets; /* [B*Np + 1] CSR capacity offsets into tt/ttv (nbt_plan_tt) */
     const int64_t* ls_offsets; /* [B*Np + 1] CSR capacity offsets into ls_oc_power, or NULL */
 } nbt_inputs;
@@ -139,8 +139,10 @@ int64_t nbt_ls_nfreq(double baseline, double minfreq, double maxfreq, int sample
 /* Fill tt_offsets[B*Np+1] with CSR capacities ceil(1.05*Ndays/P)+3 per planet (host helper).
  * Returns the largest single capacity (>0), or <0 on error. */
 int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets);
-/* Fill order[B]: permutation of 0..B-1 sorted by decreasing substeps (host helper). */
-int nbt_plan_order(const nbt_config* cfg, const int32_t* substeps, int32_t* order);
+/* Fill order[B]: permutation of 0..B-1 sorted by decreasing substeps, Hill-unstable systems
+ * (mutual separation < 4 R_Hill, from params) first within equal substeps (host helper).
+ * params or substeps may be NULL (that key is skipped). */
+int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* substeps, int32_t* order);
 /* Fill ls_offsets[B*Np+1] from tt_offsets (capacity of the O-C periodogram). */
 int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets);
 

@@ -100,7 +100,8 @@ def ptr(a, ctype=C.c_double):
 
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnbt.so")
+# NBT_LIB_PATH: developer override used by tools/gpu_probe.py to compare kernel build variants
+_LIB_PATH = os.environ.get("NBT_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnbt.so")
 
 
 def lib_path():
@@ -123,7 +124,7 @@ def load():
     lib.nbt_ls_nfreq.restype = C.c_int64
     lib.nbt_ls_nfreq.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
     lib.nbt_plan_tt.argtypes = [C.POINTER(nbt_config), _dp, _lp]
-    lib.nbt_plan_order.argtypes = [C.POINTER(nbt_config), _ip, _ip]
+    lib.nbt_plan_order.argtypes = [C.POINTER(nbt_config), _dp, _ip, _ip]
     lib.nbt_plan_ls.argtypes = [C.POINTER(nbt_config), _lp, _lp]
     lib.nbt_plan_substeps.argtypes = [C.POINTER(nbt_config), _dp, _ip]
     lib.nbt_count_steps.restype = C.c_int64

@@ -105,10 +105,15 @@ __device__ double warp_maxavg(const double* x, int n, int lane) {
 // ---------------------------------------------------------------------------------------------
 // k_integrate: the hot kernel
 // ---------------------------------------------------------------------------------------------
+#ifndef NBT_BLOCK
 #define NBT_BLOCK 64
+#endif
+#ifndef NBT_MINBLOCKS
+#define NBT_MINBLOCKS 1
+#endif
 
 template <int NP>
-__global__ void __launch_bounds__(NBT_BLOCK) k_integrate(const nbt_run_args A) {
+__global__ void __launch_bounds__(NBT_BLOCK, NBT_MINBLOCKS) k_integrate(const nbt_run_args A) {
     const int g = blockIdx.x * NBT_BLOCK + threadIdx.x;
     if (g >= A.B) return;
     const int sys = (A.order != nullptr) ? A.order[g] : g;
@@ -511,6 +516,25 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 // ---------------------------------------------------------------------------------------------
 // host helpers
 // ---------------------------------------------------------------------------------------------
+/* Smallest mutual Hill separation (a_j - a_i) / R_H,ij over all planet pairs of one system,
+ * R_H,ij = ((m_i + m_j) / 3 M*)^(1/3) (a_i + a_j) / 2, a ~ P^(2/3).  Pairs inside 2 sqrt(3) are
+ * Hill-unstable: chaotic, mostly short-lived (every system the kernel flags as broken in the
+ * C2 priors has Delta < 4). */
+static double hill_separation(const double* par, int N) {
+    const double Ms = par[NBT_P_M];
+    double dmin = INFINITY;
+    for (int j = 1; j < N; j++)
+        for (int i = 1; i < j; i++) {
+            const double Pi = par[i * NBT_NPAR + NBT_P_P], Pj = par[j * NBT_NPAR + NBT_P_P];
+            if (!(Pi > 0.0) || !(Pj > 0.0) || !(Ms > 0.0)) continue;
+            const double ai = cbrt(Pi * Pi), aj = cbrt(Pj * Pj);
+            const double rh = cbrt((par[i * NBT_NPAR + NBT_P_M] + par[j * NBT_NPAR + NBT_P_M]) / (3.0 * Ms)) * 0.5 * (ai + aj);
+            const double d = fabs(aj - ai) / rh;
+            if (d < dmin) dmin = d;
+        }
+    return dmin;
+}
+
 static int scheme_stages(int id) {
     switch (id) {
     case NBT_SCHEME_WH2: return 1;
@@ -721,12 +745,25 @@ int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets
     return (int)capmax;
 }
 
-int nbt_plan_order(const nbt_config* cfg, const int32_t* substeps, int32_t* order) {
+int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* substeps, int32_t* order) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
-    if (!substeps || !order) return nbt_fail(-10, "nbt_plan_order: NULL argument");
-    std::iota(order, order + cfg->n_systems, 0);
-    std::stable_sort(order, order + cfg->n_systems, [&](int32_t a, int32_t b) { return substeps[a] > substeps[b]; });
+    if (!order) return nbt_fail(-10, "nbt_plan_order: NULL argument");
+    const int B = cfg->n_systems, N = cfg->n_bodies;
+    std::iota(order, order + B, 0);
+    // key 1: sub-steps, heaviest first (blocks are dispatched in index order, so the long
+    // systems start first and a warp's lanes run equal trip counts);
+    // key 2: Hill-unstable systems first within a group, so that the lanes that may break or
+    // fall back to the slow Kepler path share warps instead of each stalling a healthy warp.
+    std::vector<uint8_t> unstable(params ? B : 0);
+    if (params)
+        for (int b = 0; b < B; b++) unstable[b] = hill_separation(params + (size_t)b * N * NBT_NPAR, N) < 4.0 ? 1 : 0;
+    std::stable_sort(order, order + B, [&](int32_t a, int32_t b) {
+        const int ka = substeps ? substeps[a] : 1, kb = substeps ? substeps[b] : 1;
+        if (ka != kb) return ka > kb;
+        if (params && unstable[a] != unstable[b]) return unstable[a] > unstable[b];
+        return false;
+    });
     return 0;
 }
 
@@ -746,10 +783,9 @@ int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_of
 }
 
 /* Sub-step rule, calibrated against the oracle (tools/calibrate_substeps.py).
- * The binding tolerance is the orbit-averaged e to 1e-8 relative.  The composition error scales
- * with (dt_sub / P_innermost)^order and with the interaction strength, so
- *     k = ceil(step * R(scheme) * g / P_min),   g = 2 if any adjacent pair is closer than
- * 6 mutual Hill radii (strongly interacting, mostly short-lived systems), else 1. */
+ * The binding tolerance is the orbit-averaged e to 1e-8 relative; the composition error scales
+ * with (dt_sub / P_innermost)^order, so k = ceil(step * R(scheme) / P_min).  Hill-unstable pairs
+ * (Delta < 2 sqrt 3) get no extra resolution: they are chaotic and no step size gives parity. */
 int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* substeps) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
@@ -759,20 +795,12 @@ int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* subs
     const double step = cfg->n_days / (double)(cfg->n_outputs - 1);
     for (int b = 0; b < B; b++) {
         const double* par = params + (size_t)b * N * NBT_NPAR;
-        const double Ms = par[NBT_P_M];
-        double pmin = INFINITY, g = 1.0;
+        double pmin = INFINITY;
         for (int j = 1; j < N; j++) {
             const double P = par[j * NBT_NPAR + NBT_P_P];
             if (P > 0.0 && P < pmin) pmin = P;
-            for (int i = 1; i < j; i++) { /* mutual Hill separation of every pair (a ~ P^(2/3)) */
-                const double Pi = par[i * NBT_NPAR + NBT_P_P];
-                if (!(P > 0.0) || !(Pi > 0.0) || !(Ms > 0.0)) continue;
-                const double ai = cbrt(Pi * Pi), aj = cbrt(P * P);
-                const double rh = cbrt((par[i * NBT_NPAR + NBT_P_M] + par[j * NBT_NPAR + NBT_P_M]) / (3.0 * Ms)) * 0.5 * (ai + aj);
-                if (fabs(aj - ai) < 6.0 * rh) g = 2.0;
-            }
         }
-        double k = std::isfinite(pmin) ? ceil(step * R[cfg->scheme] * g / pmin) : 1.0;
+        double k = std::isfinite(pmin) ? ceil(step * R[cfg->scheme] / pmin) : 1.0;
         if (!(k >= 1.0)) k = 1.0;
         if (k > 65536.0) k = 65536.0;
         substeps[b] = (int32_t)k;

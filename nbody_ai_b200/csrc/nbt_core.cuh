@@ -372,7 +372,7 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
 // bodies, mu = G M_i): what ps[j].P/a/e/inc/Omega/omega/M return at nbody/simulation.py:150.
 // ---------------------------------------------------------------------------------------------
 NBT_HD double nbt_acos2(double num, double den, double disamb) {
-    const double cth = num / den;
+    const double cth = num * nbt_rcp(den);
     double val;
     if (cth > -1.0 && cth < 1.0) val = acos(cth);
     else val = (cth <= -1.0) ? NBT_PI : 0.0;
@@ -408,7 +408,8 @@ NBT_HD nbt_orbit nbt_elements(double mu, double x, double y, double z, double vx
     }
     o.P = o.Omega = o.omega = o.M = 0.0;
     if (MODE >= 1) {
-        const double nx = -hy, ny = hx, nn = sqrt(nx * nx + ny * ny);
+        const double nx = -hy, ny = hx, n2 = nx * nx + ny * ny;
+        const double nn = (n2 > 0.0) ? n2 * nbt_rsqrt(n2) : 0.0;
         if (o.inc < 1e-8 || o.inc > NBT_PI - 1e-8) {
             const double Omega = nbt_acos2(nx, nn, ny);
             const double pomega = nbt_acos2(ex, o.e, ey);

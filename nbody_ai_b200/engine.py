@@ -55,11 +55,14 @@ class Plan:
         else:
             self.substeps = np.ascontiguousarray(substeps, dtype=np.int32)
             assert self.substeps.shape == (B,)
-        # launch order: equal trip counts within a warp
+        # launch order: heavy systems first, equal trip counts within a warp, unstable ones grouped
         self.order = None
-        if sort and self.substeps is not None and B > 1 and self.substeps.min() != self.substeps.max():
+        if sort and B > 32:
             self.order = np.zeros(B, dtype=np.int32)
-            _abi.check(lib.nbt_plan_order(C.byref(self.cfg), _abi.ptr(self.substeps, C.c_int32), _abi.ptr(self.order, C.c_int32)), lib)
+            _abi.check(lib.nbt_plan_order(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.substeps, C.c_int32),
+                                          _abi.ptr(self.order, C.c_int32)), lib)
+            if np.array_equal(self.order, np.arange(B, dtype=np.int32)):
+                self.order = None
         # CSR capacities of the transit products
         self.tt_offsets = np.zeros(B * self.Np + 1, dtype=np.int64)
         cap = lib.nbt_plan_tt(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.tt_offsets, C.c_int64))

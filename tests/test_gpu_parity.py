@@ -105,7 +105,7 @@ def test_schemes_and_refined_mode(gpu_lib):
     for scheme, k in (("y4", 6), ("saba4", 10), ("wh2", 120)):
         got = engine.run(engine.Plan(P, 100, 2401, substeps=k, scheme=scheme, flags=_abi.F_MEANS))
         assert np.array_equal(got.n_tt, base.n_tt)
-        assert np.abs(got.tt - base.tt).max() * 86400 < (1.0 if scheme == "wh2" else 0.05)
+        assert np.nanmax(np.abs(got.tt - base.tt)) * 86400 < (1.0 if scheme == "wh2" else 0.05)
     ref = engine.run(engine.Plan(P, 100, 2401, flags=_abi.F_MEANS, tt_mode=_abi.TT_REFINED))
     d = np.abs(ref.tt_of(0, 0) - base.tt_of(0, 0)).max() * 86400
     assert 0.01 < d < 1.0      # refined roots differ from grid-linear ones by the interpolation error

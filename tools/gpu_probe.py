@@ -57,6 +57,19 @@ def main():
             timed(workloads.c2_params(10000, 6, 0), 30.0, 721, _abi.F_MEANS)
         elif c == "c2full":
             timed(workloads.c2_params(10000, 6, 0), 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, reps=1)
+        elif c.startswith("c2fullcap"):
+            cap = int(c[len("c2fullcap"):])
+            par = workloads.c2_params(10000, 6, 0)
+            pl = engine.Plan(par, 365.0, 8760, flags=_abi.F_MEANS)
+            timed(par, 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, reps=1, substeps=np.minimum(pl.substeps, cap))
+        elif c == "c1big":
+            timed(workloads.c1_params(227328), 30.0, 721, 0, substeps=1)
+        elif c == "c1bigomega":
+            timed(workloads.c1_params(227328), 30.0, 721, _abi.F_MEANS | _abi.F_MEAN_OMEGA, substeps=1)
+        elif c == "c2big":
+            par = workloads.c2_params(40000, 6, 0)
+            par = par[(par[:, 1, 1] > 2.6) & (par[:, 2, 1] / par[:, 1, 1] > 2.0)][:227328]
+            timed(par, 30.0, 721, _abi.F_MEANS | _abi.F_MEAN_OMEGA, substeps=1)
         elif c == "c5":
             timed(workloads.c5_params(65536), 30.0, 721, _abi.F_MEANS)
 
