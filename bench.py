@@ -134,7 +134,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": sims, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -253,13 +253,45 @@ def run_ours(args, rank, world, local_rank):
             dt, nt, _ = cpu_path(params[:n_s])
             line["cpu_baseline"] = {"value": n_s / dt, "unit": "sims/s", "cores": nt, "kind": "port",
                                     "sample": "first %d systems of the same batch, oracle (IAS15 + analyze) on %d host threads, %.1f s" % (n_s, nt, dt)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+class StdoutToStderr:
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr, so that the
+    ONE JSON line is the only thing on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+OUT = None
+
+
+def emit(line):
+    text = json.dumps(line)
+    if OUT is not None:
+        OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -272,10 +304,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_ours(args, rank, world, local_rank)
+    with StdoutToStderr() as OUT:
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":
