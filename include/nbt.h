@@ -90,6 +90,9 @@ typedef struct nbt_config {
     int32_t ls_samples_per_peak;         /* 10 (tools.py:104) */
     int32_t tt_cap_max;  /* largest per-planet CSR capacity (nbt_plan_tt returns it); 0 = derive
                             from host tt_offsets (required > 0 with NBT_F_DEVICE_PTRS) */
+    int32_t lanes_systems; /* leading launch-order slots integrated by the one-planet-per-lane
+                            kernel (nbt_plan_lanes); 0 = none, n_systems = all */
+    int32_t reserved;
 } nbt_config;
 
 typedef struct nbt_inputs {
@@ -143,6 +146,9 @@ int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets
  * (mutual separation < 4 R_Hill, from params) first within equal substeps (host helper).
  * params or substeps may be NULL (that key is skipped). */
 int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* substeps, int32_t* order);
+/* Number of leading launch-order slots for the one-planet-per-lane kernel (host helper); the
+ * caller stores it in cfg.lanes_systems.  substeps / order may be NULL. */
+int nbt_plan_lanes(const nbt_config* cfg, const int32_t* substeps, const int32_t* order);
 /* Fill ls_offsets[B*Np+1] from tt_offsets (capacity of the O-C periodogram). */
 int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets);
 

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "nbt_core.cuh"
+#include "nbt_lanes.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing
@@ -112,12 +113,29 @@ __device__ double warp_maxavg(const double* x, int n, int lane) {
 #define NBT_MINBLOCKS 1
 #endif
 
+// launch-order slots [first, first + count) of the batch, one system per thread
 template <int NP>
-__global__ void __launch_bounds__(NBT_BLOCK, NBT_MINBLOCKS) k_integrate(const nbt_run_args A) {
+__global__ void __launch_bounds__(NBT_BLOCK, NBT_MINBLOCKS) k_integrate(const nbt_run_args A, int first, int count) {
     const int g = blockIdx.x * NBT_BLOCK + threadIdx.x;
-    if (g >= A.B) return;
-    const int sys = (A.order != nullptr) ? A.order[g] : g;
+    if (g >= count) return;
+    const int sys = (A.order != nullptr) ? A.order[first + g] : first + g;
     nbt_simulate_system<NP>(A, sys);
+}
+
+// launch-order slots [first, first + count), one planet per lane (32 / NP systems per warp)
+#define NBT_LBLOCK 64
+template <int NP>
+__global__ void __launch_bounds__(NBT_LBLOCK) k_integrate_lanes(const nbt_run_args A, int first, int count) {
+    constexpr int SPW = 32 / NP;
+    const int warp = (int)((blockIdx.x * (unsigned)NBT_LBLOCK + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    const int g = lane / NP, j = lane - g * NP;
+    if (g >= SPW) return;                               // spare lanes (32 % NP)
+    const int idx = warp * SPW + g;
+    if (idx >= count) return;                           // whole group leaves together
+    const int sys = (A.order != nullptr) ? A.order[first + idx] : first + idx;
+    const int base = g * NP;
+    const unsigned gmask = ((NP == 32) ? 0xffffffffu : ((1u << NP) - 1u)) << base;
+    nbt_simulate_lane<NP>(A, sys, j, base, gmask, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -559,24 +577,52 @@ static int check_cfg(const nbt_config* cfg) {
 }
 
 template <int NP>
-static cudaError_t launch_integrate(const nbt_run_args& A, cudaStream_t st) {
-    const int grid = (A.B + NBT_BLOCK - 1) / NBT_BLOCK;
-    k_integrate<NP><<<grid, NBT_BLOCK, 0, st>>>(A);
+static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count, bool lanes, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    if (lanes) {
+        constexpr int SPW = 32 / NP;
+        const int warps = (count + SPW - 1) / SPW;
+        const int grid = (warps * 32 + NBT_LBLOCK - 1) / NBT_LBLOCK;
+        k_integrate_lanes<NP><<<grid, NBT_LBLOCK, 0, st>>>(A, first, count);
+    } else {
+        const int grid = (count + NBT_BLOCK - 1) / NBT_BLOCK;
+        k_integrate<NP><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
+    }
     return cudaGetLastError();
 }
 
-static cudaError_t launch_integrate_np(int np, const nbt_run_args& A, cudaStream_t st) {
+static cudaError_t launch_integrate_np(int np, const nbt_run_args& A, int first, int count, bool lanes, cudaStream_t st) {
     switch (np) {
-    case 1: return launch_integrate<1>(A, st);
-    case 2: return launch_integrate<2>(A, st);
-    case 3: return launch_integrate<3>(A, st);
-    case 4: return launch_integrate<4>(A, st);
-    case 5: return launch_integrate<5>(A, st);
-    case 6: return launch_integrate<6>(A, st);
-    case 7: return launch_integrate<7>(A, st);
-    case 8: return launch_integrate<8>(A, st);
+    case 1: return launch_integrate<1>(A, first, count, false, st);
+    case 2: return launch_integrate<2>(A, first, count, lanes, st);
+    case 3: return launch_integrate<3>(A, first, count, lanes, st);
+    case 4: return launch_integrate<4>(A, first, count, lanes, st);
+    case 5: return launch_integrate<5>(A, first, count, lanes, st);
+    case 6: return launch_integrate<6>(A, first, count, lanes, st);
+    case 7: return launch_integrate<7>(A, first, count, lanes, st);
+    case 8: return launch_integrate<8>(A, first, count, lanes, st);
     default: return cudaErrorInvalidValue;
     }
+}
+
+// side stream + fork/join events per device: the lanes kernel (long systems) runs concurrently
+// with the one-system-per-thread kernel (the bulk)
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static std::mutex g_side_mu;
+static SideStream g_side[64];
+
+static cudaError_t get_side(int dev, SideStream** out) {
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    SideStream& s = g_side[dev];
+    if (!s.st) {
+        cudaError_t e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    *out = &s;
+    return cudaSuccess;
 }
 
 static std::mutex g_pool_mu;
@@ -636,8 +682,22 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         A.B = B; A.n_outputs = NO; A.substeps_all = cfg->substeps; A.tt_mode = cfg->tt_mode; A.flags = cfg->flags;
         A.orbit_stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
         A.n_days = cfg->n_days; A.scheme = nbt_make_scheme(cfg->scheme);
-        e = launch_integrate_np(Np, A, st);
-        if (e != cudaSuccess) return e;
+        int nl = cfg->lanes_systems < 0 ? 0 : cfg->lanes_systems;   // leading launch-order slots on the lanes kernel
+        if (nl > B) nl = B;
+        if (Np == 1) nl = 0;
+        if (nl > 0 && nl < B) {   // both kernels: fork the long systems onto the side stream
+            SideStream* side = nullptr;
+            if ((e = get_side(cfg->device, &side)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(side->st, side->fork, 0)) != cudaSuccess) return e;
+            if ((e = launch_integrate_np(Np, A, 0, nl, true, side->st)) != cudaSuccess) return e;
+            if ((e = launch_integrate_np(Np, A, nl, B - nl, false, st)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(side->join, side->st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
+        } else {
+            e = launch_integrate_np(Np, A, 0, B, nl == B, st);
+            if (e != cudaSuccess) return e;
+        }
     } else {
         nbt_scan_args S;
         memset(&S, 0, sizeof S);
@@ -767,6 +827,22 @@ int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* s
     return 0;
 }
 
+/* How many leading launch-order slots go to the one-planet-per-lane kernel (nbt_config.lanes_systems).
+ * Measured on B200 (profiles/README.md): a lane's stage is latency-bound and no shorter than a
+ * thread's for Np = 2, so the lanes kernel only pays where one thread per system is issue-bound or
+ * spills: every system when Np >= 5 (k_integrate<5..8> spill), or when Np >= 3 and the batch leaves
+ * most SM sub-partitions empty (B <= 4096: single-system latency improves 1.7x at Np = 3). */
+int nbt_plan_lanes(const nbt_config* cfg, const int32_t* substeps, const int32_t* order) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    (void)substeps; (void)order;
+    const int B = cfg->n_systems, Np = cfg->n_bodies - 1;
+    if (Np <= 1 || B == 0) return 0;
+    if (Np >= 5) return B;
+    if (Np >= 3 && B <= 4096) return B;
+    return 0;
+}
+
 int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
@@ -790,7 +866,7 @@ int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* subs
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (!params || !substeps) return nbt_fail(-10, "nbt_plan_substeps: NULL argument");
-    static const double R[NBT_SCHEME_COUNT] = {8000.0, 400.0, 800.0, 60.0}; /* P_min / dt_sub */
+    static const double R[NBT_SCHEME_COUNT] = {8000.0, 400.0, 800.0, 57.5}; /* P_min / dt_sub */
     const int B = cfg->n_systems, N = cfg->n_bodies;
     const double step = cfg->n_days / (double)(cfg->n_outputs - 1);
     for (int b = 0; b < B; b++) {

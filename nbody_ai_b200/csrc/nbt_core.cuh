@@ -134,13 +134,16 @@ NBT_HD void nbt_kepler_safe(double mu, double h, double r0, double eta, double b
     if (!ok || !(r > 0.0)) status |= NBT_S_KEPLER;
 }
 
+// r0 / ir0 = |r| and 1/|r| of the incoming position, carried from the end of the previous drift
+// (a kick does not move positions) and refreshed from x, y, z at every output sample; on return they
+// hold the new radius and its reciprocal.  This removes a rsqrt chain per planet per stage here and
+// another in the indirect term of the kick.
 NBT_HD void nbt_kepler_drift(double mu, double h, double& x, double& y, double& z, double& vx,
-                             double& vy, double& vz, int& status) {
-    const double r02 = fma(x, x, fma(y, y, z * z));
+                             double& vy, double& vz, double& r0io, double& ir0io, int& status) {
     const double v02 = fma(vx, vx, fma(vy, vy, vz * vz));
     const double eta = fma(x, vx, fma(y, vy, z * vz));
-    const double ir0 = nbt_rsqrt(r02);
-    const double r0 = r02 * ir0;
+    const double ir0 = ir0io;
+    const double r0 = r0io;
     const double beta = fma(2.0 * mu, ir0, -v02);
     const double zeta = fma(-beta, r0, mu);
 
@@ -193,6 +196,14 @@ NBT_HD void nbt_kepler_drift(double mu, double h, double& x, double& y, double& 
     vy = fma(fd, y, fma(gdm1, vy, vy));
     vz = fma(fd, z, fma(gdm1, vz, vz));
     x = nx; y = ny; z = nz;
+    r0io = r; ir0io = ir;
+}
+
+// |r| and 1/|r| from the coordinates (start of a run and at every output sample)
+NBT_HD void nbt_radius(double x, double y, double z, double& r, double& ir) {
+    const double r2 = fma(x, x, fma(y, y, z * z));
+    ir = nbt_rsqrt(r2);
+    r = r2 * ir;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,6 +212,7 @@ NBT_HD void nbt_kepler_drift(double mu, double h, double& x, double& y, double& 
 template <int NP>
 struct nbt_state {
     double x[NP], y[NP], z[NP], vx[NP], vy[NP], vz[NP]; // Jacobi coordinates of planets 1..NP
+    double r[NP], ir[NP];                               // carried |r'| and 1/|r'| (see nbt_kepler_drift)
 };
 
 template <int NP>
@@ -258,8 +270,7 @@ NBT_HD void nbt_accel(const nbt_state<NP>& s, const nbt_consts<NP>& c, double (&
         double jx = px[i] - Ax, jy = py[i] - Ay, jz = pz[i] - Az;
         Ax = fma(c.mr[i], jx, Ax); Ay = fma(c.mr[i], jy, Ay); Az = fma(c.mr[i], jz, Az);
         if (i >= 1) { // + G M_i r'_i / r'_i^3
-            const double r2 = fma(s.x[i], s.x[i], fma(s.y[i], s.y[i], s.z[i] * s.z[i]));
-            const double ir = nbt_rsqrt(r2);
+            const double ir = s.ir[i];
             const double f = c.GM[i] * ir * ir * ir;
             jx = fma(f, s.x[i], jx); jy = fma(f, s.y[i], jy); jz = fma(f, s.z[i], jz);
         }
@@ -338,6 +349,7 @@ NBT_HD void nbt_setup(const double* par, nbt_state<NP>& s, nbt_consts<NP>& c) {
         s.vx[i] = v0 * (cO * vp - sO * vq * ci);
         s.vy[i] = v0 * (sO * vp + cO * vq * ci);
         s.vz[i] = v0 * (vq * si);
+        nbt_radius(s.x[i], s.y[i], s.z[i], s.r[i], s.ir[i]);
     }
 }
 
@@ -357,7 +369,7 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
         const double h = sc.a[st] * dt;
 #pragma unroll
         for (int i = 0; i < NP; i++)
-            nbt_kepler_drift(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], status);
+            nbt_kepler_drift(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
         nbt_accel<NP>(s, c, ax, ay, az);
         const double kb = sc.b[st + 1] * dt;
 #pragma unroll
@@ -493,6 +505,10 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
             for (int sub = 0; sub < k; sub++) nbt_step<NP>(s, c, A.scheme, dt, ax, ay, az, status);
         }
         const double t = (o == NO - 1) ? A.n_days : (double)o * step;
+        if (o > 0) { // refresh the carried radii from the coordinates (bounds their round-off drift)
+#pragma unroll
+            for (int j = 0; j < NP; j++) nbt_radius(s.x[j], s.y[j], s.z[j], s.r[j], s.ir[j]);
+        }
         // heliocentric x (= x_planet - x_star) and star barycentric position
         double dx[NP], dvx[NP];
         double Sx = 0.0, Svx = 0.0;

@@ -34,7 +34,7 @@ class Plan:
     """Configuration + CSR layout of one nbt_run call (host planning through libnbt's helpers)."""
 
     def __init__(self, params, n_days, n_outputs, substeps=None, scheme=SCHEME_M64,
-                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True):
+                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True, lanes=None):
         lib = _abi.load()
         self.params = _as_params(params)
         B, N, _ = self.params.shape
@@ -63,6 +63,12 @@ class Plan:
                                           _abi.ptr(self.order, C.c_int32)), lib)
             if np.array_equal(self.order, np.arange(B, dtype=np.int32)):
                 self.order = None
+        # which systems run one planet per lane (long ones / small batches), see nbt_plan_lanes
+        if lanes is None:
+            lanes = lib.nbt_plan_lanes(C.byref(self.cfg), _abi.ptr(self.substeps, C.c_int32), _abi.ptr(self.order, C.c_int32))
+            if lanes < 0:
+                _abi.check(lanes, lib)
+        self.cfg.lanes_systems = int(min(max(int(lanes), 0), B))
         # CSR capacities of the transit products
         self.tt_offsets = np.zeros(B * self.Np + 1, dtype=np.int64)
         cap = lib.nbt_plan_tt(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.tt_offsets, C.c_int64))

@@ -66,6 +66,8 @@ extern "C" int hostsim_run_scheme(const nbt_config* cfg, const nbt_inputs* in, n
 // single Kepler drift, for unit tests against the closed-form two-body solution
 extern "C" int hostsim_kepler(double mu, double h, double* state6) {
     int status = 0;
-    nbt_kepler_drift(mu, h, state6[0], state6[1], state6[2], state6[3], state6[4], state6[5], status);
+    double r, ir;
+    nbt_radius(state6[0], state6[1], state6[2], r, ir);
+    nbt_kepler_drift(mu, h, state6[0], state6[1], state6[2], state6[3], state6[4], state6[5], r, ir, status);
     return status;
 }

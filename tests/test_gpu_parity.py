@@ -262,7 +262,8 @@ def test_full_size_invariants(gpu_lib):
         assert np.array_equal(getattr(dev, k), getattr(host, k), equal_nan=True), k
     # shard / order invariance: an arbitrary subset, unsorted launch order, same bits
     idx = np.random.default_rng(5).choice(len(par), 500, replace=False)
-    sub = engine.run(engine.Plan(par[idx], 365.0, 8760, substeps=plan.substeps[idx], flags=FULL, sort=False))
+    assert plan.cfg.lanes_systems == 0
+    sub = engine.run(engine.Plan(par[idx], 365.0, 8760, substeps=plan.substeps[idx], flags=FULL, sort=False, lanes=0))
     for q, b in enumerate(idx):
         for j in range(2):
             assert np.array_equal(sub.tt_of(q, j), host.tt_of(b, j))
@@ -275,3 +276,61 @@ def test_full_size_invariants(gpu_lib):
     got, want = engine.run(p2), oracle_run(p2)
     ok = {b for b in range(p2.B) if not (want.status[b] & (_abi.S_NONFINITE | _abi.S_UNBOUND))}
     compare_products(got, want, p2, skip=set(range(p2.B)) - ok)
+
+
+@pytest.mark.parametrize("n_planets", [2, 3, 4])
+def test_lanes_kernel_matches_thread_kernel(gpu_lib, n_planets):
+    """One-planet-per-lane kernel (warp shuffles across bodies) vs one-system-per-thread kernel:
+    same arithmetic per body, sums over bodies in the same order -> agreement to round-off; also a
+    mixed launch (long systems on lanes, bulk on threads, two streams) and ragged group counts."""
+    par = regular(workloads.random_systems(75, n_planets, seed=200 + n_planets))[:53]
+    flags = FULL | _abi.F_RV | _abi.F_ORBIT
+    ref = engine.run(engine.Plan(par, 120.0, 2881, flags=flags, lanes=0))
+    for lanes in (len(par), 7):
+        plan = engine.Plan(par, 120.0, 2881, flags=flags, lanes=lanes)
+        assert plan.cfg.lanes_systems == lanes
+        got = engine.run(plan)
+        assert np.array_equal(got.n_tt, ref.n_tt) and np.array_equal(got.status, ref.status)
+        assert np.nanmax(np.abs(got.tt - ref.tt)) * 86400 < 1e-6
+        assert np.abs(got.mean_a / ref.mean_a - 1).max() < 1e-12 and np.abs(got.mean_e - ref.mean_e).max() < 1e-12
+        assert np.abs(got.mean_omega - ref.mean_omega).max() < 1e-6
+        assert np.abs(got.rv - ref.rv).max() < 1e-9 * np.abs(ref.rv).max() and np.abs(got.orbit_xz - ref.orbit_xz).max() < 1e-11
+
+
+def test_lanes_kernel_many_planets_and_series(gpu_lib):
+    """Np = 5 and 8 run entirely on the lanes kernel (thread-per-system would spill); checked against
+    the oracle, including the full sim_data series."""
+    for n_planets, seed in ((5, 31), (8, 32)):
+        rng = np.random.default_rng(seed)
+        B = 6
+        par = np.zeros((B, n_planets + 1, 7))
+        par[:, 0, 0] = rng.uniform(0.8, 1.2, B)
+        for j in range(1, n_planets + 1):
+            par[:, j, 0] = rng.uniform(1, 30, B) * 3e-6
+            par[:, j, 1] = 4.0 * 1.9 ** (j - 1) * rng.uniform(0.97, 1.03, B)
+            par[:, j, 2] = rng.uniform(0, 0.03, B)
+            par[:, j, 3] = np.pi / 2
+            par[:, j, 5] = rng.uniform(0, 2 * np.pi, B)
+            par[:, j, 6] = rng.uniform(0, 2 * np.pi, B)
+        plan = engine.Plan(par, 200.0, 4801, flags=FULL | _abi.F_SERIES)
+        assert plan.cfg.lanes_systems == B
+        got, want = engine.run(plan), oracle_run(plan)
+        compare_products(got, want, plan)
+        assert np.abs(got.series[:, :, :3] - want.series[:, :, :3]).max() < 1e-10
+        for j in range(n_planets):
+            c = 3 + 10 * j
+            assert np.abs(got.series[:, :, c:c + 3] - want.series[:, :, c:c + 3]).max() < 1e-8
+            assert np.abs(got.series[:, :, c + 4] / want.series[:, :, c + 4] - 1).max() < 1e-8
+
+
+def test_small_batch_and_single_system_use_lanes(gpu_lib):
+    """Planner policy: small 3-planet batches (and the single README system) run one planet per lane."""
+    plan = engine.Plan(workloads.c1_params(1), 365.0, 8760, flags=FULL)
+    assert plan.cfg.lanes_systems == 1
+    got, want = engine.run(plan), oracle_run(plan)
+    compare_products(got, want, plan)
+    par, meta = workloads.c3_params(300, seed=1)
+    plan = engine.Plan(par, meta["ndays"], meta["noutputs"], flags=_abi.F_PLANET1_ONLY | _abi.F_MEANS)
+    assert plan.cfg.lanes_systems == 0            # two planets: a lane's stage is no shorter than a thread's
+    got, want = engine.run(plan), oracle_run(plan)
+    compare_products(got, want, plan)

@@ -15,7 +15,11 @@ from bench import f_step  # noqa: E402
 
 
 def timed(params, nd, no, flags, reps=2, **kw):
+    env = os.environ.get("NBT_PROBE_LANES")          # all | none | <int>; default: planner's choice
+    if env:
+        kw["lanes"] = len(params) if env == "all" else (0 if env == "none" else int(env))
     plan = engine.Plan(params, nd, no, flags=flags, **kw)
+    print("  lanes_systems=%d" % plan.cfg.lanes_systems, end="")
     d = engine.DeviceBuffers(plan)
     engine.run_device(plan, d)
     torch.cuda.synchronize()
@@ -72,6 +76,11 @@ def main():
             timed(par, 30.0, 721, _abi.F_MEANS | _abi.F_MEAN_OMEGA, substeps=1)
         elif c == "c5":
             timed(workloads.c5_params(65536), 30.0, 721, _abi.F_MEANS)
+        elif c == "c3":
+            par, meta = workloads.c3_params(5000)
+            timed(par, meta["ndays"], meta["noutputs"], _abi.F_PLANET1_ONLY, reps=3)
+        elif c == "c1one":
+            timed(workloads.c1_params(1), 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, reps=3)
 
 
 if __name__ == "__main__":
