@@ -72,10 +72,19 @@ NBT_HD double nbt_rcp_from(double x, double y0) {
 // ---------------------------------------------------------------------------------------------
 NBT_HD void nbt_stumpff(double z, double& c2, double& c3) {
     // c2 = 1/2! - z/4! + z^2/6! - ...,  c3 = 1/3! - z/5! + z^2/7! - ...   (|z| <~ 0.5)
-    c2 = fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, 1.0 / 87178291200.0, -1.0 / 479001600.0),
-         1.0 / 3628800.0), -1.0 / 40320.0), 1.0 / 720.0), -1.0 / 24.0), 0.5);
-    c3 = fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, 1.0 / 1307674368000.0, -1.0 / 6227020800.0),
-         1.0 / 39916800.0), -1.0 / 362880.0), 1.0 / 5040.0), -1.0 / 120.0), 1.0 / 6.0);
+    // Estrin's scheme: dependency depth 3 instead of Horner's 6 (the stage is latency-bound when
+    // few warps are resident, e.g. the long systems at the tail of a launch)
+    const double z2 = z * z, z4 = z2 * z2;
+    {
+        const double p01 = fma(z, -1.0 / 24.0, 0.5), p23 = fma(z, -1.0 / 40320.0, 1.0 / 720.0),
+                     p45 = fma(z, -1.0 / 479001600.0, 1.0 / 3628800.0);
+        c2 = fma(z4, fma(z2, 1.0 / 87178291200.0, p45), fma(z2, p23, p01));
+    }
+    {
+        const double p01 = fma(z, -1.0 / 120.0, 1.0 / 6.0), p23 = fma(z, -1.0 / 362880.0, 1.0 / 5040.0),
+                     p45 = fma(z, -1.0 / 6227020800.0, 1.0 / 39916800.0);
+        c3 = fma(z4, fma(z2, 1.0 / 1307674368000.0, p45), fma(z2, p23, p01));
+    }
 }
 
 // general-|z| Stumpff via argument quartering (only used by the safe path)
@@ -140,45 +149,53 @@ NBT_HD void nbt_kepler_safe(double mu, double h, double r0, double eta, double b
 // another in the indirect term of the kick.
 NBT_HD void nbt_kepler_drift(double mu, double h, double& x, double& y, double& z, double& vx,
                              double& vy, double& vz, double& r0io, double& ir0io, int& status) {
+    // Written for a short dependency chain (see nbt_stumpff): everything that depends only on the
+    // carried radius and h is formed first, polynomials are evaluated Estrin/Horner-in-the-small-
+    // variable, and the post-correction radius is Taylor-shifted in parallel with G1..G3.
+    const double ir0 = ir0io, r0 = r0io;
+    const double s = h * ir0, s2 = s * s;
+    const double kA = 0.5 * ir0, kB = (1.0 / 6.0) * ir0, kB5 = (5.0 / 6.0) * ir0, kC = (-1.0 / 24.0) * ir0;
+    const double mi0 = -mu * ir0;
     const double v02 = fma(vx, vx, fma(vy, vy, vz * vz));
     const double eta = fma(x, vx, fma(y, vy, z * vz));
-    const double ir0 = ir0io;
-    const double r0 = r0io;
     const double beta = fma(2.0 * mu, ir0, -v02);
     const double zeta = fma(-beta, r0, mu);
+    const double be = beta * eta;
 
     // X0: reversion of h = r0 X + eta X^2/2 + zeta X^3/6 - beta eta X^4/24 ...
-    const double s = h * ir0;
-    const double A = 0.5 * eta * ir0, Bc = (1.0 / 6.0) * zeta * ir0;
-    const double Cc = (-1.0 / 24.0) * beta * eta * ir0;
-    const double AA = A * A;
     //   X = s - A s^2 + (2A^2 - B) s^3 + (-5A^3 + 5AB - C) s^4
-    double X = s * fma(s, fma(s, fma(s, fma(A, fma(-5.0, AA, 5.0 * Bc), -Cc), fma(2.0, AA, -Bc)), -A), 1.0);
+    const double A = eta * kA, AA = A * A;
+    const double Bc = zeta * kB, B5 = zeta * kB5, Cc = be * kC;
+    const double k3 = fma(2.0, AA, -Bc);
+    const double k4 = fma(A, fma(-5.0, AA, B5), -Cc);
+    double X = fma(s2, fma(s, fma(s, k4, k3), -A), s);
 
-    double X2 = X * X;
+    const double X2 = X * X, X3 = X2 * X;
     const double zz = beta * X2;
+    const double base = fma(r0, X, -h);
     double c2, c3;
     nbt_stumpff(zz, c2, c3);
-    const double c1 = fma(-zz, c3, 1.0), c0 = fma(-zz, c2, 1.0);
-    double G0 = c0, G1 = X * c1, G2 = X2 * c2, G3 = X2 * X * c3;
-    const double F = fma(r0, X, fma(eta, G2, zeta * G3)) - h;
-    double r = fma(eta, G1, fma(zeta, G2, r0));                 // F'
-    const double Fpp = fma(eta, G0, zeta * G1);                 // F''
-    const double Fppp = fma(zeta, G0, -beta * eta * G1);        // F'''
+    const double G0 = fma(-zz, c2, 1.0);
+    double G1 = X * fma(-zz, c3, 1.0), G2 = X2 * c2, G3 = X3 * c3;
+    const double F = fma(zeta, G3, fma(eta, G2, base));
+    double r = fma(eta, G1, fma(zeta, G2, r0));                 // dF/dX
+    const double Fpp = fma(eta, G0, zeta * G1);                 // d2F/dX2
+    const double Fppp = fma(zeta, G0, -be * G1);                // d3F/dX3
     double ir = nbt_rcp(r);
     const double u = -F * ir;
-    const double a2 = 0.5 * Fpp * ir, a3 = (1.0 / 6.0) * Fppp * ir;
+    const double a2 = (0.5 * ir) * Fpp, a3 = ((1.0 / 6.0) * ir) * Fppp;
     const double d = u * fma(u, fma(u, fma(2.0 * a2, a2, -a3), -a2), 1.0);
 
     if (fabs(d) <= 2e-4 * fabs(X) && zz < 0.5 && zz > -0.5) {
-        // shift G1..G3 from X to X + d:  dG_k/dX = G_{k-1},  dG0/dX = -beta G1
-        const double d2 = 0.5 * d * d, d3 = (1.0 / 3.0) * d2 * d;
-        const double bG1 = beta * G1, bG0 = beta * G0;
-        const double nG3 = fma(d, G2, fma(d2, G1, fma(d3, G0, G3)));
-        const double nG2 = fma(d, G1, fma(d2, G0, fma(-d3, bG1, G2)));
-        const double nG1 = fma(d, G0, fma(-d2, bG1, fma(-d3, bG0, G1)));
+        // shift G1..G3 and r from X to X + d (Horner in d):  dG_k/dX = G_{k-1},  dG0/dX = -beta G1,
+        // dr/dX = Fpp, d2r/dX2 = Fppp, d3r/dX3 = -beta Fpp
+        const double nb6 = (-1.0 / 6.0) * beta;
+        const double hG0 = 0.5 * G0, hG1 = 0.5 * G1;
+        const double nG3 = fma(d, fma(d, fma(d, (1.0 / 6.0) * G0, hG1), G2), G3);
+        const double nG2 = fma(d, fma(d, fma(d, nb6 * G1, hG0), G1), G2);
+        const double nG1 = fma(d, fma(d, fma(d, nb6 * G0, -beta * hG1), G0), G1);
+        r = fma(d, fma(d, fma(d, nb6 * Fpp, 0.5 * Fppp), Fpp), r);
         G1 = nG1; G2 = nG2; G3 = nG3;
-        r = fma(eta, G1, fma(zeta, G2, r0));
         ir = nbt_rcp_from(r, ir);
     } else {
         X += d;
@@ -186,10 +203,10 @@ NBT_HD void nbt_kepler_drift(double mu, double h, double& x, double& y, double& 
         ir = 1.0 / r;
     }
     // Gauss f, g in the round-off-friendly "minus one" form
-    const double fm1 = -mu * G2 * ir0;
+    const double fm1 = mi0 * G2;
     const double g = fma(-mu, G3, h);
-    const double fd = -mu * G1 * ir0 * ir;
-    const double gdm1 = -mu * G2 * ir;
+    const double fd = (mi0 * G1) * ir;
+    const double gdm1 = (-mu * G2) * ir;
     const double nx = fma(fm1, x, fma(g, vx, x)), ny = fma(fm1, y, fma(g, vy, y)),
                  nz = fma(fm1, z, fma(g, vz, z));
     vx = fma(fd, x, fma(gdm1, vx, vx));
@@ -246,8 +263,8 @@ NBT_HD void nbt_accel(const nbt_state<NP>& s, const nbt_consts<NP>& c, double (&
     for (int i = 1; i < NP; i++) { // star - planet i (i >= 2 in 1-based numbering)
         const double r2 = fma(qx[i], qx[i], fma(qy[i], qy[i], qz[i] * qz[i]));
         const double ir = nbt_rsqrt(r2);
-        const double ir3 = ir * ir * ir;
-        const double fs = c.Gm[i + 1] * ir3, fp = -c.Gm[0] * ir3;
+        const double ir2 = ir * ir;
+        const double fs = (c.Gm[i + 1] * ir) * ir2, fp = (-c.Gm[0] * ir) * ir2;
         a0x = fma(fs, qx[i], a0x); a0y = fma(fs, qy[i], a0y); a0z = fma(fs, qz[i], a0z);
         px[i] = fp * qx[i]; py[i] = fp * qy[i]; pz[i] = fp * qz[i];
     }
@@ -258,8 +275,8 @@ NBT_HD void nbt_accel(const nbt_state<NP>& s, const nbt_consts<NP>& c, double (&
             const double dx = qx[j] - qx[i], dy = qy[j] - qy[i], dz = qz[j] - qz[i];
             const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
             const double ir = nbt_rsqrt(r2);
-            const double ir3 = ir * ir * ir;
-            const double fi = c.Gm[j + 1] * ir3, fj = -c.Gm[i + 1] * ir3;
+            const double ir2 = ir * ir;
+            const double fi = (c.Gm[j + 1] * ir) * ir2, fj = (-c.Gm[i + 1] * ir) * ir2;
             px[i] = fma(fi, dx, px[i]); py[i] = fma(fi, dy, py[i]); pz[i] = fma(fi, dz, pz[i]);
             px[j] = fma(fj, dx, px[j]); py[j] = fma(fj, dy, py[j]); pz[j] = fma(fj, dz, pz[j]);
         }
@@ -271,7 +288,7 @@ NBT_HD void nbt_accel(const nbt_state<NP>& s, const nbt_consts<NP>& c, double (&
         Ax = fma(c.mr[i], jx, Ax); Ay = fma(c.mr[i], jy, Ay); Az = fma(c.mr[i], jz, Az);
         if (i >= 1) { // + G M_i r'_i / r'_i^3
             const double ir = s.ir[i];
-            const double f = c.GM[i] * ir * ir * ir;
+            const double f = (c.GM[i] * ir) * (ir * ir);
             jx = fma(f, s.x[i], jx); jy = fma(f, s.y[i], jy); jz = fma(f, s.z[i], jz);
         }
         ax[i] = jx; ay[i] = jy; az[i] = jz;
