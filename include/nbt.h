@@ -200,6 +200,19 @@ int nbt_chi2(const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt, 
              const double* yerr, int32_t n_data, double* loglike, int device, int device_ptrs,
              void* cuda_stream);
 
+/* Grid-cell post-processing of simulations/simulation_grid.py:33-69 for B systems (planet 1):
+ * exact periodogram of the O-C on the autofrequency grid (minfreq, maxfreq, samples_per_peak),
+ * scipy find_peaks(height=peak_height) sorted by height, top n_order (<= 8) peak periods
+ * [B][n_order] (0-padded), least-squares coefficients [B][2+2*n_order] of Tc on
+ * [1, n, sin(2 pi n/P_k), cos(2 pi n/P_k)...] (0-padded), softmax(ttv) = percentile(|ttv|,95)/2,
+ * avg_err = mean|harmonic model - ttv|.  tt/ttv/tt_offsets/n_tt are nbt_run's outputs;
+ * tt_cap_max = cfg.tt_cap_max.  Systems with < 3 transits get NaN. */
+int nbt_grid_post(const double* tt, const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt,
+                  int32_t n_systems, int32_t n_planets, int32_t tt_cap_max, double minfreq, double maxfreq,
+                  int32_t samples_per_peak, double peak_height, int32_t n_order, double* peak_periods,
+                  double* coeffs, int32_t* n_peaks, double* softmax, double* avg_err, int device,
+                  int device_ptrs, void* cuda_stream);
+
 /* Device time [ms] of the stages of this thread's last nbt_run / nbt_analyze issued with
  * NBT_F_TIMING, from CUDA events on the launch stream: ms4 = {front end (k_integrate or
  * k_scan_series), k_fit, k_ls_oc, RV stages}.  Synchronises on the last event. */
@@ -209,6 +222,10 @@ int nbt_timing(double* ms4);
  * 8 CTAs of 256 threads per SM) — the roofline denominator bench.py reports against, since
  * MEASURED_PEAKS.json carries no FP64 figure. */
 int nbt_fp64_peak(int device, int iters, double* tflops_out, double* ms_out);
+
+/* Diagnostic: dependent-issue latency [SM cycles] of a DFMA chain and of a MUFU.RSQ64H + DADD
+ * chain on `device` (one warp) — explains the latency-bound regime of small batches. */
+int nbt_fp64_latency(int device, double* dfma_cycles, double* rsqrt_dadd_cycles);
 
 #ifdef __cplusplus
 }

@@ -483,6 +483,177 @@ __global__ void __launch_bounds__(128) k_scan_series(const nbt_scan_args A) {
     if (status) atomicOr(&A.status[sys], status);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_grid_post: post-processing of one grid cell (simulations/simulation_grid.py:33-69), one block
+// per system, planet 1 only:
+//   exact periodogram of the O-C on astropy's autofrequency grid (spp, fmin, fmax from the caller)
+//   -> scipy.signal.find_peaks(power, height) -> sort by height, keep n_order
+//   -> least squares of Tc on [1, n, sin(2 pi n / P_k), cos(2 pi n / P_k) ...]   (np.linalg.lstsq)
+//   -> softmax(ttv) = 0.5 * percentile(|ttv|, 95), avg_err = mean |model - ttv|
+// Dynamic shared memory: max(n_freq, n_tt * (2 + 2 n_order)) doubles (power, then the basis).
+// ---------------------------------------------------------------------------------------------
+#define NBT_GRID_MAXORDER 8
+#define NBT_GRID_MAXCOL (2 + 2 * NBT_GRID_MAXORDER)
+
+struct nbt_grid_args {
+    const double* tt; const double* ttv; const int64_t* tt_offsets; const int32_t* n_tt;
+    double* peak_periods; double* coeffs; int32_t* n_peaks; double* softmax; double* avg_err;
+    int32_t B, Np, spp, n_order, smem_doubles;
+    double fmin, fmax, height;
+};
+
+__device__ double warp_percentile_abs(const double* x, int n, double q, int lane) {
+    const double pos = q * (double)(n - 1);
+    const int lo = (int)floor(pos);
+    const double frac = pos - (double)lo;
+    const double vlo = warp_kth_abs(x, n, lo, lane);
+    if (lo + 1 >= n) return vlo;
+    const double vhi = warp_kth_abs(x, n, lo + 1, lane);
+    return vlo + (vhi - vlo) * frac;
+}
+
+__global__ void __launch_bounds__(128) k_grid_post(const nbt_grid_args G) {
+    extern __shared__ double sm[];
+    __shared__ double s_red[4];
+    __shared__ double s_G[NBT_GRID_MAXCOL * NBT_GRID_MAXCOL], s_rhs[NBT_GRID_MAXCOL], s_c[NBT_GRID_MAXCOL];
+    __shared__ double s_pk_period[NBT_GRID_MAXORDER];
+    __shared__ int s_npk;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t off = G.tt_offsets[(size_t)b * G.Np];
+    const int cap = (int)(G.tt_offsets[(size_t)b * G.Np + 1] - off);
+    const int n = min(G.n_tt[(size_t)b * G.Np], cap);
+    const double* tt = G.tt + off;
+    const double* ttv = G.ttv + off;
+    const int m_max = 2 + 2 * G.n_order;
+    double* out_c = G.coeffs + (size_t)b * m_max;
+    double* out_p = G.peak_periods + (size_t)b * G.n_order;
+    if (n < 3) { // too few transits: the reference's lstsq/LombScargle would not run either
+        for (int i = tid; i < m_max; i += 128) out_c[i] = NAN;
+        for (int i = tid; i < G.n_order; i += 128) out_p[i] = NAN;
+        if (tid == 0) { G.n_peaks[b] = 0; G.softmax[b] = NAN; G.avg_err[b] = NAN; }
+        return;
+    }
+    // 1. periodogram into shared memory
+    const double T = (double)(n - 1);
+    long long nf = ls_nfreq(T, G.fmin, G.fmax, G.spp);
+    if (nf > G.smem_doubles) nf = G.smem_doubles;
+    const double df = ls_df(T, G.spp);
+    double ybar, YY;
+    warp_mean_var(ttv, n, lane, ybar, YY);   // every warp computes the same mean/variance
+    for (long long k = tid; k < nf; k += 128) sm[k] = ls_power_uniform(ttv, n, ybar, YY, G.fmin + (double)k * df);
+    __syncthreads();
+    // 2. find_peaks(height) + top n_order by height (scipy: strict rise, plateau midpoint, strict fall;
+    //    argsort(heights)[::-1] -> among equal heights the later peak first)
+    if (tid == 0) {
+        int idx[NBT_GRID_MAXORDER]; double hgt[NBT_GRID_MAXORDER];
+        int np = 0;
+        long long i = 1;
+        const long long imax = nf - 1;
+        while (i < imax) {
+            if (sm[i - 1] < sm[i]) {
+                long long ahead = i + 1;
+                while (ahead < imax && sm[ahead] == sm[i]) ahead++;
+                if (sm[ahead] < sm[i]) {
+                    const long long mid = (i + ahead - 1) / 2;
+                    const double hv = sm[mid];
+                    if (hv >= G.height) { // insert, keeping (height desc, index desc) order
+                        int pos = np < G.n_order ? np : G.n_order;
+                        while (pos > 0 && (hgt[pos - 1] < hv || hgt[pos - 1] == hv)) pos--;
+                        if (pos < G.n_order) {
+                            const int last = (np < G.n_order ? np : G.n_order - 1);
+                            for (int q = last; q > pos; q--) { idx[q] = idx[q - 1]; hgt[q] = hgt[q - 1]; }
+                            idx[pos] = (int)mid; hgt[pos] = hv;
+                            if (np < G.n_order) np++;
+                        }
+                    }
+                    i = ahead;
+                }
+            }
+            i++;
+        }
+        s_npk = np;
+        for (int q = 0; q < G.n_order; q++) {
+            const double per = (q < np) ? 1.0 / (G.fmin + (double)idx[q] * df) : NAN;
+            s_pk_period[q] = per;
+            out_p[q] = (q < np) ? per : 0.0;   // per_epoch_grid is zero-initialised in the reference
+        }
+        G.n_peaks[b] = np;
+    }
+    __syncthreads();
+    const int np = s_npk;
+    const int m = 2 + 2 * np;
+    // 3. basis in shared memory (column-major [m][n]); the epoch column is centred and scaled so that the
+    //    normal equations stay well conditioned
+    const double kbar = 0.5 * (double)(n - 1), ksc = 1.0 / fmax(kbar, 1.0);
+    if ((long long)n * m <= G.smem_doubles) {
+        for (int k = tid; k < n; k += 128) {
+            sm[k] = 1.0;
+            sm[n + k] = ((double)k - kbar) * ksc;
+            for (int q = 0; q < np; q++) {
+                double sn, cs;
+                sincospi(2.0 * (double)k / s_pk_period[q], &sn, &cs);
+                sm[(2 + 2 * q) * n + k] = sn;
+                sm[(3 + 2 * q) * n + k] = cs;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < m * m + m; e += 128) {
+            double acc = 0.0;
+            if (e < m * m) {
+                const int a = e / m, c = e % m;
+                if (c >= a) { for (int k = 0; k < n; k++) acc = fma(sm[a * n + k], sm[c * n + k], acc); s_G[a * m + c] = acc; }
+            } else {
+                const int a = e - m * m;
+                for (int k = 0; k < n; k++) acc = fma(sm[a * n + k], tt[k], acc);
+                s_rhs[a] = acc;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { // Cholesky of the (m x m) SPD normal matrix, upper triangle in s_G
+            bool ok = true;
+            for (int a = 0; a < m && ok; a++) {
+                for (int c = a; c < m; c++) {
+                    double v = s_G[a * m + c];
+                    for (int q = 0; q < a; q++) v -= s_G[q * m + a] * s_G[q * m + c];
+                    if (c == a) { if (!(v > 0.0)) { ok = false; break; } s_G[a * m + a] = sqrt(v); }
+                    else s_G[a * m + c] = v / s_G[a * m + a];
+                }
+            }
+            if (ok) {
+                for (int a = 0; a < m; a++) { double v = s_rhs[a]; for (int q = 0; q < a; q++) v -= s_G[q * m + a] * s_c[q]; s_c[a] = v / s_G[a * m + a]; }
+                for (int a = m - 1; a >= 0; a--) { double v = s_c[a]; for (int q = a + 1; q < m; q++) v -= s_G[a * m + q] * s_c[q]; s_c[a] = v / s_G[a * m + a]; }
+            } else for (int a = 0; a < m; a++) s_c[a] = NAN;
+        }
+        __syncthreads();
+        // 4. model - ttv; the harmonic part of the model is ypred - (c0 + c1 n)
+        double err = 0.0;
+        for (int k = tid; k < n; k += 128) {
+            double h = 0.0;
+            for (int a = 2; a < m; a++) h = fma(s_c[a], sm[a * n + k], h);
+            err += fabs(h - ttv[k]);
+        }
+        err = warp_sum(err);
+        if (lane == 0) s_red[wid] = err;
+        __syncthreads();
+        if (tid == 0) {
+            G.avg_err[b] = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) / (double)n;
+            // back to the unscaled epoch column: c1' (k - kbar) ksc + c0' = (c1' ksc) k + (c0' - c1' ksc kbar)
+            const double c1 = s_c[1] * ksc;
+            out_c[0] = s_c[0] - c1 * kbar;
+            out_c[1] = c1;
+            for (int a = 2; a < m_max; a++) out_c[a] = (a < m) ? s_c[a] : 0.0;
+        }
+    } else if (tid == 0) {
+        for (int a = 0; a < m_max; a++) out_c[a] = NAN;
+        G.avg_err[b] = NAN;
+    }
+    if (wid == 1) { // softmax = percentile(|ttv|, 95) / 2   (simulation_grid.py:17)
+        const double p95 = warp_percentile_abs(ttv, n, 0.95, lane);
+        if (lane == 0) G.softmax[b] = 0.5 * p95;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_chi2: nbody/nested.py:85-95, one thread per forward model
 // ---------------------------------------------------------------------------------------------
@@ -529,6 +700,21 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
     }
     const double r = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
     if (r == 12345.678) out[0] = r; // never true; keeps the chains alive
+}
+
+// one warp, one dependent DFMA / MUFU.RSQ64H chain: cycles per dependent instruction
+__global__ void k_fp64_latency(double* out, long long* cycles, int n, double a, double b) {
+    double v = threadIdx.x * 1e-9 + 1.0;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < n; i++) v = fma(v, a, b);
+    long long t1 = clock64();
+    double w = v;
+#pragma unroll 16
+    for (int i = 0; i < n; i++) { double y; asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w)); w = y + 1.5; }
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t1; }
+    out[threadIdx.x] = v + w;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1242,6 +1428,68 @@ int nbt_timing(double* ms4) {
         ms4[i] = (double)ms;
     }
     return 0;
+}
+
+
+int nbt_grid_post(const double* tt, const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt,
+                  int32_t n_systems, int32_t n_planets, int32_t tt_cap_max, double minfreq, double maxfreq,
+                  int32_t samples_per_peak, double peak_height, int32_t n_order, double* peak_periods,
+                  double* coeffs, int32_t* n_peaks, double* softmax, double* avg_err, int device,
+                  int device_ptrs, void* cuda_stream) {
+    if (!tt || !ttv || !tt_offsets || !n_tt || !peak_periods || !coeffs || !n_peaks || !softmax || !avg_err)
+        return nbt_fail(-10, "nbt_grid_post: NULL argument");
+    if (n_systems < 0 || n_planets < 1 || n_order < 0 || n_order > NBT_GRID_MAXORDER || samples_per_peak < 1 || tt_cap_max < 1)
+        return nbt_fail(-11, "nbt_grid_post: bad sizes (n_order <= %d)", NBT_GRID_MAXORDER);
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_grid_post: no CUDA device (there is no CPU fallback)");
+    if (n_systems == 0) return 0;
+    const int m = 2 + 2 * n_order;
+    const long long nf_cap = nbt_ls_nfreq((double)(tt_cap_max - 1 > 1 ? tt_cap_max - 1 : 1), minfreq, maxfreq, samples_per_peak);
+    long long need = std::max<long long>(nf_cap, (long long)tt_cap_max * m);
+    if (need * 8 > 200 * 1024) return nbt_fail(-12, "nbt_grid_post: %lld doubles of shared memory needed (max 25600)", need);
+    Stage S(device, device_ptrs, cuda_stream);
+    const int64_t nsp = (int64_t)n_systems * n_planets;
+    int64_t ntt = 0;
+    if (!device_ptrs) ntt = tt_offsets[nsp];
+    nbt_grid_args G;
+    G.tt = S.in(tt, (size_t)ntt); G.ttv = S.in(ttv, (size_t)ntt);
+    G.tt_offsets = S.in(tt_offsets, (size_t)nsp + 1); G.n_tt = S.in(n_tt, (size_t)nsp);
+    G.peak_periods = S.out(peak_periods, (size_t)n_systems * n_order); G.coeffs = S.out(coeffs, (size_t)n_systems * m);
+    G.n_peaks = S.out(n_peaks, (size_t)n_systems); G.softmax = S.out(softmax, (size_t)n_systems);
+    G.avg_err = S.out(avg_err, (size_t)n_systems);
+    G.B = n_systems; G.Np = n_planets; G.spp = samples_per_peak; G.n_order = n_order; G.smem_doubles = (int32_t)need;
+    G.fmin = minfreq; G.fmax = maxfreq; G.height = peak_height;
+    if (!S.rc) {
+        S.check(cudaFuncSetAttribute(k_grid_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(need * 8)), "cudaFuncSetAttribute");
+        if (!S.rc) k_grid_post<<<n_systems, 128, (size_t)need * 8, S.st>>>(G);
+    }
+    return S.finish();
+}
+
+int nbt_fp64_latency(int device, double* dfma_cycles, double* rsqrt_dadd_cycles) {
+    int rc = 0;
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_fp64_latency: no CUDA device");
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    double* d = nullptr; long long* c = nullptr;
+    const int n = 1 << 14;
+    NBT_CUDA(cudaSetDevice(device));
+    {
+        NBT_CUDA(cudaMalloc((void**)&d, 32 * 8));
+        NBT_CUDA(cudaMalloc((void**)&c, 16));
+        k_fp64_latency<<<1, 32>>>(d, c, n, 0.999999, 1e-7);
+        k_fp64_latency<<<1, 32>>>(d, c, n, 0.999999, 1e-7);
+        NBT_CUDA(cudaGetLastError());
+        long long h[2] = {0, 0};
+        NBT_CUDA(cudaMemcpy(h, c, 16, cudaMemcpyDeviceToHost));
+        if (dfma_cycles) *dfma_cycles = (double)h[0] / n;
+        if (rsqrt_dadd_cycles) *rsqrt_dadd_cycles = (double)h[1] / n;
+    }
+done:
+    if (d) cudaFree(d);
+    if (c) cudaFree(c);
+    if (rc != 0) cudaGetLastError();
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return rc;
 }
 
 int nbt_fp64_peak(int device, int iters, double* tflops_out, double* ms_out) {

@@ -334,3 +334,68 @@ def test_small_batch_and_single_system_use_lanes(gpu_lib):
     assert plan.cfg.lanes_systems == 0            # two planets: a lane's stage is no shorter than a thread's
     got, want = engine.run(plan), oracle_run(plan)
     compare_products(got, want, plan)
+
+
+def test_grid_cell_postprocessing(gpu_lib):
+    """simulations/simulation_grid.py:20-69: peaks / harmonic model / softmax / avg_err from the GPU vs
+    the reference's own calls (scipy.signal.find_peaks, np.linalg.lstsq, np.percentile) applied to the
+    same transit times, with the oracle's exact periodogram."""
+    from scipy.signal import find_peaks
+    from nbody_ai_b200 import grid
+    par, _ = workloads.c4_params(npts=5)
+    epochs, n_order = 120, 4
+    r = grid.generate_sim_batch(par, epochs=epochs, n_order=n_order)
+    buf = r["buffers"]
+    checked = 0
+    for b in range(len(par)):
+        Tc = buf.tt_of(b, 0)
+        n = len(Tc)
+        orbit = np.arange(n)
+        A = np.vstack([np.ones(n), orbit]).T
+        t0, per = np.linalg.lstsq(A, Tc, rcond=None)[0]
+        ttv = Tc - per * orbit - t0
+        assert np.abs(ttv - buf.ttv_of(b, 0)).max() < 1e-9
+        freq, power = oracle.lomb_scargle(orbit.astype(float), ttv, 1. / (1.5 * epochs), 1. / 2.1, 20)
+        peaks, amps = find_peaks(power, height=0.05)
+        peaks = peaks[np.argsort(amps['peak_heights'])[::-1]][:n_order]
+        peak_periods = 1. / freq[peaks]
+        assert r["n_peaks"][b] == len(peaks)
+        assert np.allclose(r["peak_periods"][b, :len(peaks)], peak_periods, rtol=1e-12)
+        assert np.all(r["peak_periods"][b, len(peaks):] == 0)
+        basis_list = [np.ones(n), orbit]
+        for k in range(len(peaks)):
+            basis_list.append(np.sin(2 * np.pi * orbit / peak_periods[k]))
+            basis_list.append(np.cos(2 * np.pi * orbit / peak_periods[k]))
+        basis = np.array(basis_list).T
+        coeffs = np.linalg.lstsq(basis, Tc, rcond=None)[0]
+        got = r["coeffs"][b, :len(coeffs)]
+        assert abs(got[0] - coeffs[0]) < 1e-8 and abs(got[1] - coeffs[1]) < 1e-10
+        scale = max(np.abs(coeffs[2:]).max(), 1e-7) if len(coeffs) > 2 else 1.0
+        assert np.abs(got[2:] - coeffs[2:]).max() < 1e-6 * scale + 1e-11
+        ttv_pred = basis @ coeffs - (coeffs[0] + coeffs[1] * orbit)
+        assert abs(r["avg_err"][b] - np.mean(np.abs(ttv_pred - ttv))) < 1e-9
+        assert abs(r["ttv_max"][b] - np.percentile(np.abs(ttv), 95) * 0.5) < 1e-12
+        checked += 1
+    assert checked == 25
+    # single-cell drop-in shapes
+    obj = [{'m': 1.12}, {'m': 0.000954, 'P': 1.42, 'inc': np.pi / 2}, {'m': 3e-4, 'P': 2.9, 'inc': np.pi / 2}]
+    pp, cf, sm, ae = grid.generate_sim(obj, epochs=60, n_order=4)
+    assert len(cf) == 2 + 2 * len(pp) and sm > 0 and ae >= 0
+
+
+def test_training_set_writer(gpu_lib, tmp_path):
+    """simulations/generate_simulations.py:41-110 format: [X, y] pickle, 1 + omegas rows per draw,
+    7-vector rows, `periods` transit times each, rejection rule honoured."""
+    import pickle
+    from nbody_ai_b200 import dataset
+    f = str(tmp_path / "ttv.pkl")
+    rng = np.random.default_rng(3)
+    X, y = dataset.generate_training_set(samples=4, omegas=2, periods=12, file=f, rng=rng)
+    assert len(X) == len(y) and len(X) % 3 == 0 and len(X) >= 4
+    Xl, yl = pickle.load(open(f, 'rb'))
+    assert len(Xl) == len(X)
+    for row, tc in zip(X, y):
+        assert len(row) == 7 and len(tc) == 12 and np.all(np.diff(tc) > 0)
+    for g in range(0, len(X), 3):      # variants share everything but omega_2
+        assert X[g][:5] == X[g + 1][:5] == X[g + 2][:5] and X[g][6] == X[g + 1][6]
+        assert X[g][5] != X[g + 1][5]
