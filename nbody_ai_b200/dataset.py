@@ -20,17 +20,14 @@ def _xn(objects):
 
 
 def _run(object_lists, periods, device):
-    """One nbt_run per distinct P1 is not possible in a single call (Ndays = P1 * periods differs per
-    system), so systems are integrated for the batch maximum and truncated at their own Ndays:
-    the output grid of the reference is np.linspace(0, P1*periods, round(P1*periods*24)) — 1-hour
-    cadence to within 1/(2 Noutputs) — which a common grid cannot reproduce exactly; each system is
-    therefore run on its own grid, grouped in one launch per call through B = 1 plans when grids
-    differ.  (The grids are identical for the omega variants of one draw.)"""
+    """Planet-1 transit products of each system on the reference's own output grid,
+    np.linspace(0, P1*periods, round(P1*periods*24)) (generate_simulations.py:47-50).  The grid
+    depends on P1, so systems are grouped by (Ndays, Noutputs) — the omega variants of one draw share
+    a grid and go out as one nbt_run — and returned as (tt, maxavg(ttv), n_tt) per system."""
     groups = {}
     for i, ob in enumerate(object_lists):
         P1 = ob[1]['P']
-        key = (P1 * periods, int(round(P1 * periods * 24)))
-        groups.setdefault(key, []).append(i)
+        groups.setdefault((P1 * periods, int(round(P1 * periods * 24))), []).append(i)
     results = [None] * len(object_lists)
     for (ndays, nout), idx in groups.items():
         par = np.stack([_abi.objects_to_params(object_lists[i]) for i in idx])
