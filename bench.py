@@ -88,6 +88,18 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def ncu_traffic(np_, b):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_integrate launch on this workload, from the
+    committed `ncu --set full` capture (profiles/r1_traffic.json); None if no capture matches."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if t.get("n_planets") == np_ and t.get("systems") == b:
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -162,6 +174,8 @@ def run_ours(args, rank, world, local_rank):
     tf, ms = C.c_double(0), C.c_double(0)
     _abi.check(lib.nbt_fp64_peak(local_rank, 1 << 16, C.byref(tf), C.byref(ms)), lib)
     fp64_peak = tf.value
+    _abi.check(lib.nbt_fp64_peak(local_rank, -(1 << 16), C.byref(tf), C.byref(ms)), lib)
+    fp64_peak_3reg = tf.value   # DFMA whose three operands are distinct registers (register-bandwidth bound)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -242,7 +256,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "fp64", "kernel": "k_integrate<%d>" % Np, "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None,
                          "peak_source": "nbt_fp64_peak DFMA-chain kernel measured in this run (nominal 37.2 at 1965 MHz)",
-                         "flops_per_launch": flops, "launch_ms": integ_launch_ms, "traffic": None},
+                         "peak_three_register_operands": fp64_peak_3reg,
+                         "flops_per_launch": flops, "launch_ms": integ_launch_ms, "traffic": ncu_traffic(Np, B)},
             "e2e": {"value": sims_all * args.steps / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": 3 * args.steps,

@@ -222,6 +222,8 @@ int nbt_timing(double* ms4);
  * 8 CTAs of 256 threads per SM) — the roofline denominator bench.py reports against, since
  * MEASURED_PEAKS.json carries no FP64 figure. */
 int nbt_fp64_peak(int device, int iters, double* tflops_out, double* ms_out);
+/* (iters < 0 runs |iters| iterations of the variant whose three DFMA operands are all distinct
+ * per-thread registers — the register-bandwidth-limited rate real code sees.) */
 
 /* Diagnostic: dependent-issue latency [SM cycles] of a DFMA chain and of a MUFU.RSQ64H + DADD
  * chain on `device` (one warp) — explains the latency-bound regime of small batches. */

@@ -702,6 +702,20 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
     if (r == 12345.678) out[0] = r; // never true; keeps the chains alive
 }
 
+// same, but all three DFMA operands are distinct per-thread registers (what real code looks like:
+// six 32-bit register reads per instruction instead of two)
+__global__ void __launch_bounds__(256) k_dfma_peak3(double* out, int iters, double a, double b) {
+    double v0 = threadIdx.x * 1e-9, v1 = v0 + 1e-3, v2 = v0 + 2e-3, v3 = v0 + 3e-3, v4 = v0 + 4e-3,
+           v5 = v0 + 5e-3, v6 = v0 + 6e-3, v7 = v0 + 7e-3;
+    double a0 = a + v0, a1 = a + v1, a2 = a - v2, a3 = a - v3, b0 = b + v4, b1 = b - v5, b2 = b + v6, b3 = b - v7;
+    for (int i = 0; i < iters; i++) {
+        v0 = fma(v0, a0, b0); v1 = fma(v1, a1, b1); v2 = fma(v2, a2, b2); v3 = fma(v3, a3, b3);
+        v4 = fma(v4, a1, b2); v5 = fma(v5, a2, b3); v6 = fma(v6, a3, b0); v7 = fma(v7, a0, b1);
+    }
+    const double r = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+    if (r == 12345.678) out[0] = r;
+}
+
 // one warp, one dependent DFMA / MUFU.RSQ64H chain: cycles per dependent instruction
 __global__ void k_fp64_latency(double* out, long long* cycles, int n, double a, double b) {
     double v = threadIdx.x * 1e-9 + 1.0;
@@ -1495,7 +1509,7 @@ done:
 int nbt_fp64_peak(int device, int iters, double* tflops_out, double* ms_out) {
     int rc = 0;
     if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_fp64_peak: no CUDA device");
-    if (iters <= 0) iters = 1 << 16;
+    if (iters == 0) iters = 1 << 16;
     int prev_dev = -1;
     cudaGetDevice(&prev_dev);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1508,10 +1522,14 @@ int nbt_fp64_peak(int device, int iters, double* tflops_out, double* ms_out) {
         NBT_CUDA(cudaMalloc((void**)&d, 8));
         NBT_CUDA(cudaEventCreate(&e0));
         NBT_CUDA(cudaEventCreate(&e1));
-        k_dfma_peak<<<blocks, threads>>>(d, iters / 8, 0.999999, 1e-7); // warm-up
+        const bool three = iters < 0;   // negative iters: the three-register-operand variant
+        if (three) iters = -iters;
+        if (three) k_dfma_peak3<<<blocks, threads>>>(d, iters / 8, 0.999999, 1e-7);
+        else k_dfma_peak<<<blocks, threads>>>(d, iters / 8, 0.999999, 1e-7); // warm-up
         NBT_CUDA(cudaGetLastError());
         NBT_CUDA(cudaEventRecord(e0));
-        k_dfma_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+        if (three) k_dfma_peak3<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+        else k_dfma_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
         NBT_CUDA(cudaEventRecord(e1));
         NBT_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;

@@ -432,7 +432,15 @@ NBT_HD nbt_orbit nbt_elements(double mu, double x, double y, double z, double vx
     o.e = (e2 > 0.0) ? e2 * nbt_rsqrt(e2) : 0.0;
     {
         const double ci = hz * ih;
-        o.inc = (ci > -1.0 && ci < 1.0) ? acos(ci) : ((ci <= -1.0) ? NBT_PI : 0.0);
+        if (fabs(ci) < 0.03) {
+            // near edge-on (every transiting system): acos(x) = pi/2 - asin(x), asin by its Maclaurin
+            // series; the first neglected term x^11 * 63/2816 is < 4e-19 for |x| < 0.03
+            const double c2 = ci * ci;
+            const double p = fma(c2, fma(c2, fma(c2, fma(c2, 35.0 / 1152.0, 15.0 / 336.0), 3.0 / 40.0), 1.0 / 6.0), 1.0);
+            o.inc = fma(-ci, p, 0.5 * NBT_PI);
+        } else {
+            o.inc = (ci > -1.0 && ci < 1.0) ? acos(ci) : ((ci <= -1.0) ? NBT_PI : 0.0);
+        }
         if (!(h2 > 0.0)) o.inc = NAN;
     }
     o.P = o.Omega = o.omega = o.M = 0.0;

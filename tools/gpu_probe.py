@@ -47,6 +47,8 @@ def main():
             tf, ms = C.c_double(), C.c_double()
             lib.nbt_fp64_peak(0, 1 << 16, C.byref(tf), C.byref(ms))
             print("  DFMA peak %.2f TFLOP/s (%.2f ms)" % (tf.value, ms.value))
+            lib.nbt_fp64_peak(0, -(1 << 16), C.byref(tf), C.byref(ms))
+            print("  DFMA with 3 distinct register operands %.2f TFLOP/s (%.2f ms)" % (tf.value, ms.value))
             l1, l2 = C.c_double(), C.c_double()
             lib.nbt_fp64_latency(0, C.byref(l1), C.byref(l2))
             print("  dependent DFMA latency %.1f cycles; MUFU.RSQ64H+DADD %.1f cycles" % (l1.value, l2.value))
