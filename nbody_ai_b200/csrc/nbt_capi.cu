@@ -114,17 +114,17 @@ __device__ double warp_maxavg(const double* x, int n, int lane) {
 #endif
 
 // launch-order slots [first, first + count) of the batch, one system per thread
-template <int NP>
+template <int NP, bool SERIES>
 __global__ void __launch_bounds__(NBT_BLOCK, NBT_MINBLOCKS) k_integrate(const nbt_run_args A, int first, int count) {
     const int g = blockIdx.x * NBT_BLOCK + threadIdx.x;
     if (g >= count) return;
     const int sys = (A.order != nullptr) ? A.order[first + g] : first + g;
-    nbt_simulate_system<NP>(A, sys);
+    nbt_simulate_system<NP, SERIES>(A, sys);
 }
 
 // launch-order slots [first, first + count), one planet per lane (32 / NP systems per warp)
 #define NBT_LBLOCK 64
-template <int NP>
+template <int NP, bool SERIES>
 __global__ void __launch_bounds__(NBT_LBLOCK) k_integrate_lanes(const nbt_run_args A, int first, int count) {
     constexpr int SPW = 32 / NP;
     const int warp = (int)((blockIdx.x * (unsigned)NBT_LBLOCK + threadIdx.x) >> 5), lane = threadIdx.x & 31;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NBT_LBLOCK) k_integrate_lanes(const nbt_run_ar
     const int sys = (A.order != nullptr) ? A.order[first + idx] : first + idx;
     const int base = g * NP;
     const unsigned gmask = ((NP == 32) ? 0xffffffffu : ((1u << NP) - 1u)) << base;
-    nbt_simulate_lane<NP>(A, sys, j, base, gmask, true);
+    nbt_simulate_lane<NP, SERIES>(A, sys, j, base, gmask, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -779,14 +779,17 @@ static int check_cfg(const nbt_config* cfg) {
 template <int NP>
 static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count, bool lanes, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
+    const bool series = (A.flags & NBT_F_SERIES) != 0 && A.series != nullptr;
     if (lanes) {
         constexpr int SPW = 32 / NP;
         const int warps = (count + SPW - 1) / SPW;
         const int grid = (warps * 32 + NBT_LBLOCK - 1) / NBT_LBLOCK;
-        k_integrate_lanes<NP><<<grid, NBT_LBLOCK, 0, st>>>(A, first, count);
+        if (series) k_integrate_lanes<NP, true><<<grid, NBT_LBLOCK, 0, st>>>(A, first, count);
+        else k_integrate_lanes<NP, false><<<grid, NBT_LBLOCK, 0, st>>>(A, first, count);
     } else {
         const int grid = (count + NBT_BLOCK - 1) / NBT_BLOCK;
-        k_integrate<NP><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
+        if (series) k_integrate<NP, true><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
+        else k_integrate<NP, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
     }
     return cudaGetLastError();
 }
@@ -807,7 +810,7 @@ static cudaError_t launch_integrate_np(int np, const nbt_run_args& A, int first,
 
 // side stream + fork/join events per device: the lanes kernel (long systems) runs concurrently
 // with the one-system-per-thread kernel (the bulk)
-struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+struct SideStream { cudaStream_t st = nullptr; };
 static std::mutex g_side_mu;
 static SideStream g_side[64];
 
@@ -818,8 +821,6 @@ static cudaError_t get_side(int dev, SideStream** out) {
     if (!s.st) {
         cudaError_t e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
         if (e != cudaSuccess) return e;
-        if ((e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-        if ((e = cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming)) != cudaSuccess) return e;
     }
     *out = &s;
     return cudaSuccess;
@@ -888,12 +889,18 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         if (nl > 0 && nl < B) {   // both kernels: fork the long systems onto the side stream
             SideStream* side = nullptr;
             if ((e = get_side(cfg->device, &side)) != cudaSuccess) return e;
-            if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(side->st, side->fork, 0)) != cudaSuccess) return e;
-            if ((e = launch_integrate_np(Np, A, 0, nl, true, side->st)) != cudaSuccess) return e;
-            if ((e = launch_integrate_np(Np, A, nl, B - nl, false, st)) != cudaSuccess) return e;
-            if ((e = cudaEventRecord(side->join, side->st)) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
+            // fork/join events are per call (concurrent callers on one device share only the side stream)
+            cudaEvent_t fork = nullptr, join = nullptr;
+            if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming)) != cudaSuccess) { cudaEventDestroy(fork); return e; }
+            e = cudaEventRecord(fork, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(side->st, fork, 0);
+            if (e == cudaSuccess) e = launch_integrate_np(Np, A, 0, nl, true, side->st);
+            if (e == cudaSuccess) e = launch_integrate_np(Np, A, nl, B - nl, false, st);
+            if (e == cudaSuccess) e = cudaEventRecord(join, side->st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
+            cudaEventDestroy(fork); cudaEventDestroy(join);   // destruction is deferred until the events complete
+            if (e != cudaSuccess) return e;
         } else {
             e = launch_integrate_np(Np, A, 0, B, nl == B, st);
             if (e != cudaSuccess) return e;

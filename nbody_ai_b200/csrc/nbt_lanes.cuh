@@ -85,7 +85,7 @@ __device__ __forceinline__ void nbt_accel_lane(unsigned gmask, int base, int j, 
 
 // One lane of one system: integrate + sample + detect transits (the lanes form of nbt_simulate_system).
 // `active` lanes own a real (system, planet); inactive ones shadow a valid system and write nothing.
-template <int NP>
+template <int NP, bool SERIES>
 __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int base, unsigned gmask, bool active) {
     const double* par = A.params + (size_t)sys * (NP + 1) * NBT_NPAR;
     double mr[NP], Gm[NP + 1];
@@ -130,7 +130,7 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
     const bool want_omega = (A.flags & NBT_F_MEAN_OMEGA) != 0;
     const bool want_rv = (A.flags & NBT_F_RV) != 0 && A.rv != nullptr;
     const bool want_orbit = (A.flags & NBT_F_ORBIT) != 0 && A.orbit_xz != nullptr;
-    const bool want_series = (A.flags & NBT_F_SERIES) != 0 && A.series != nullptr;
+    const bool want_series = SERIES;
     const bool tt_on = !((A.flags & NBT_F_PLANET1_ONLY) && j > 0);
     const double rv_scale = 1.496e11 * ((double)NO / (A.n_days * 24.0 * 60.0 * 60.0));
     const int W = 3 + 10 * NP;

@@ -9,7 +9,11 @@
 
 template <int NP>
 static void run_np(const nbt_run_args& A) {
-    for (int g = 0; g < A.B; g++) nbt_simulate_system<NP>(A, A.order ? A.order[g] : g);
+    const bool series = (A.flags & NBT_F_SERIES) != 0 && A.series != nullptr;
+    for (int g = 0; g < A.B; g++) {
+        if (series) nbt_simulate_system<NP, true>(A, A.order ? A.order[g] : g);
+        else nbt_simulate_system<NP, false>(A, A.order ? A.order[g] : g);
+    }
 }
 
 extern "C" int hostsim_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out) {
