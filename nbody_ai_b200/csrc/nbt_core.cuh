@@ -426,7 +426,7 @@ struct nbt_orbit { double P, a, e, inc, Omega, omega, M; };
 // Reciprocals / square roots go through the MUFU-seeded helpers (<= 1 ulp); the acos calls are
 // libdevice's.
 template <int MODE>
-NBT_HD nbt_orbit nbt_elements(double mu, double x, double y, double z, double vx, double vy, double vz) {
+NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, double vx, double vy, double vz) {
     nbt_orbit o;
     const double hx = y * vz - z * vy, hy = z * vx - x * vz, hz = x * vy - y * vx;
     const double h2 = fma(hx, hx, fma(hy, hy, hz * hz));
@@ -484,6 +484,28 @@ NBT_HD nbt_orbit nbt_elements(double mu, double x, double y, double z, double vx
     }
     (void)h;
     return o;
+}
+
+// Mid-transit time inside one output interval.  GRID_LINEAR: the reference's find_zero
+// (nbody/tools.py:61-65).  REFINED: Newton on the cubic Hermite interpolant of dx over the interval.
+// Out of line: it runs once per transit, and inlining it per planet bloats the sampling loop.
+NBT_HD_COLD double nbt_crossing_time(int tt_mode, double t_prev, double t, double dx_prev, double dx,
+                                     double dvx_prev, double dvx) {
+    if (tt_mode == NBT_TT_GRID_LINEAR) {
+        const double m = (dx - dx_prev) / (t - t_prev);
+        return -dx_prev / m + t_prev;
+    }
+    const double hh = t - t_prev;
+    const double p0 = dx_prev, p1 = dx, m0 = dvx_prev * hh, m1 = dvx * hh;
+    double u = p0 / (p0 - p1);
+    if (!(u >= 0.0 && u <= 1.0)) u = 0.5;
+    for (int it = 0; it < 6; it++) {
+        const double u2 = u * u, u3 = u2 * u;
+        const double f = (2 * u3 - 3 * u2 + 1) * p0 + (u3 - 2 * u2 + u) * m0 + (-2 * u3 + 3 * u2) * p1 + (u3 - u2) * m1;
+        const double fp = (6 * u2 - 6 * u) * p0 + (3 * u2 - 4 * u + 1) * m0 + (-6 * u2 + 6 * u) * p1 + (3 * u2 - 2 * u) * m1;
+        u -= f / fp;
+    }
+    return t_prev + u * hh;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -567,23 +589,7 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
 #pragma unroll
             for (int j = 0; j < NP; j++) {
                 if (j < n_tt_planets && dx_prev[j] >= 0.0 && dx[j] <= 0.0) { // simulation.py:168
-                    double t0;
-                    if (A.tt_mode == NBT_TT_GRID_LINEAR) {                   // tools.py:61-65
-                        const double m = (dx[j] - dx_prev[j]) / (t - t_prev);
-                        t0 = -dx_prev[j] / m + t_prev;
-                    } else { // Newton on the cubic Hermite interpolant of dx over the interval
-                        const double hh = t - t_prev;
-                        const double p0 = dx_prev[j], p1 = dx[j], m0 = dvx_prev[j] * hh, m1 = dvx[j] * hh;
-                        double u = p0 / (p0 - p1);
-                        if (!(u >= 0.0 && u <= 1.0)) u = 0.5;
-                        for (int it = 0; it < 6; it++) {
-                            const double u2 = u * u, u3 = u2 * u;
-                            const double f = (2 * u3 - 3 * u2 + 1) * p0 + (u3 - 2 * u2 + u) * m0 + (-2 * u3 + 3 * u2) * p1 + (u3 - u2) * m1;
-                            const double fp = (6 * u2 - 6 * u) * p0 + (3 * u2 - 4 * u + 1) * m0 + (-6 * u2 + 6 * u) * p1 + (3 * u2 - 2 * u) * m1;
-                            u -= f / fp;
-                        }
-                        t0 = t_prev + u * hh;
-                    }
+                    const double t0 = nbt_crossing_time(A.tt_mode, t_prev, t, dx_prev[j], dx[j], dvx_prev[j], dvx[j]);
                     const int64_t off = A.tt_offsets[(size_t)sys * NP + j];
                     const int64_t cap = A.tt_offsets[(size_t)sys * NP + j + 1] - off;
                     if (cnt[j] < cap) A.tt[off + cnt[j]] = t0; else status |= NBT_S_TT_OVERFLOW;

@@ -182,23 +182,7 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
         if (__any_sync(gmask, bad)) { status |= NBT_S_NONFINITE; break; } // whole group stops together
         if (o > 0) {
             if (tt_on && dx_prev >= 0.0 && dx <= 0.0) {                    // simulation.py:168
-                double t0;
-                if (A.tt_mode == NBT_TT_GRID_LINEAR) {                     // tools.py:61-65
-                    const double m = (dx - dx_prev) / (t - t_prev);
-                    t0 = -dx_prev / m + t_prev;
-                } else {
-                    const double hh = t - t_prev;
-                    const double p0 = dx_prev, p1 = dx, m0 = dvx_prev * hh, m1 = dvx * hh;
-                    double u = p0 / (p0 - p1);
-                    if (!(u >= 0.0 && u <= 1.0)) u = 0.5;
-                    for (int it = 0; it < 6; it++) {
-                        const double u2 = u * u, u3 = u2 * u;
-                        const double f = (2 * u3 - 3 * u2 + 1) * p0 + (u3 - 2 * u2 + u) * m0 + (-2 * u3 + 3 * u2) * p1 + (u3 - u2) * m1;
-                        const double fp = (6 * u2 - 6 * u) * p0 + (3 * u2 - 4 * u + 1) * m0 + (-6 * u2 + 6 * u) * p1 + (3 * u2 - 2 * u) * m1;
-                        u -= f / fp;
-                    }
-                    t0 = t_prev + u * hh;
-                }
+                const double t0 = nbt_crossing_time(A.tt_mode, t_prev, t, dx_prev, dx, dvx_prev, dvx);  // tools.py:61-65
                 if (active) { if (cnt < cap) A.tt[off + cnt] = t0; else status |= NBT_S_TT_OVERFLOW; }
                 cnt++;
             }
