@@ -18,8 +18,10 @@ def timed(params, nd, no, flags, reps=2, **kw):
     env = os.environ.get("NBT_PROBE_LANES")          # all | none | <int>; default: planner's choice
     if env:
         kw["lanes"] = len(params) if env == "all" else (0 if env == "none" else int(env))
+    if os.environ.get("NBT_PROBE_PARTITION"):          # "a,b" or "0,0"
+        kw["partition"] = tuple(int(v) for v in os.environ["NBT_PROBE_PARTITION"].split(","))
     plan = engine.Plan(params, nd, no, flags=flags, **kw)
-    print("  lanes_systems=%d" % plan.cfg.lanes_systems, end="")
+    print("  lanes=%d heavy=(%d,%d)" % (plan.cfg.lanes_systems, plan.cfg.heavy_a, plan.cfg.heavy_b), end="")
     d = engine.DeviceBuffers(plan)
     engine.run_device(plan, d)
     torch.cuda.synchronize()
@@ -71,6 +73,13 @@ def main():
             par = workloads.c2_params(10000, 6, 0)
             pl = engine.Plan(par, 365.0, 8760, flags=_abi.F_MEANS)
             timed(par, 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, reps=1, substeps=np.minimum(pl.substeps, cap))
+        elif c.startswith("c2heavy"):
+            par = workloads.c2_params(10000, 6, 0)
+            pl = engine.Plan(par, 365.0, 8760, flags=_abi.F_MEANS)
+            sel = par[pl.substeps == 3]
+            fl = {"c2heavy0": 0, "c2heavy1": _abi.F_MEANS, "c2heavy2": _abi.F_MEANS | _abi.F_MEAN_OMEGA,
+                  "c2heavy3": _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, "c2heavyp1": _abi.F_PLANET1_ONLY}[c]
+            timed(sel, 365.0, 8760, fl, reps=1, substeps=3)
         elif c == "c1big":
             timed(workloads.c1_params(227328), 30.0, 721, 0, substeps=1)
         elif c == "c1bigomega":
