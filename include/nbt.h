@@ -92,8 +92,6 @@ typedef struct nbt_config {
                             from host tt_offsets (required > 0 with NBT_F_DEVICE_PTRS) */
     int32_t lanes_systems; /* leading launch-order slots integrated by the one-planet-per-lane
                             kernel (nbt_plan_lanes); 0 = none, n_systems = all */
-    int32_t heavy_a;     /* leading launch-order slots run as heavy class A (2 CTAs per SM) and the next */
-    int32_t heavy_b;     /* heavy_b as class B (4 CTAs per SM); nbt_plan_partition; 0 = one launch */
     int32_t reserved;
 } nbt_config;
 
@@ -151,10 +149,6 @@ int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* s
 /* Number of leading launch-order slots for the one-planet-per-lane kernel (host helper); the
  * caller stores it in cfg.lanes_systems.  substeps / order may be NULL. */
 int nbt_plan_lanes(const nbt_config* cfg, const int32_t* substeps, const int32_t* order);
-/* Heavy classes of a heterogeneous batch (host helper): counts of leading launch-order slots for
- * cfg.heavy_a / cfg.heavy_b.  Requires `order` sorted by decreasing substeps (nbt_plan_order). */
-int nbt_plan_partition(const nbt_config* cfg, const int32_t* substeps, const int32_t* order, int32_t* heavy_a,
-                       int32_t* heavy_b);
 /* Fill ls_offsets[B*Np+1] from tt_offsets (capacity of the O-C periodogram). */
 int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets);
 

@@ -776,11 +776,8 @@ static int check_cfg(const nbt_config* cfg) {
     return 0;
 }
 
-// smem_bytes: dummy dynamic shared memory of the one-system-per-thread launch.  The kernel never touches
-// it; it only sets how many CTAs share an SM (SM partitioning, see enqueue_path).
 template <int NP>
-static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count, bool lanes, cudaStream_t st,
-                                    size_t smem_bytes = 0) {
+static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count, bool lanes, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     const bool series = (A.flags & NBT_F_SERIES) != 0 && A.series != nullptr;
     if (lanes) {
@@ -792,35 +789,28 @@ static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count,
     } else {
         const int grid = (count + NBT_BLOCK - 1) / NBT_BLOCK;
         if (series) k_integrate<NP, true><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
-        else {
-            if (smem_bytes > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(k_integrate<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-                if (e != cudaSuccess) return e;
-            }
-            k_integrate<NP, false><<<grid, NBT_BLOCK, smem_bytes, st>>>(A, first, count);
-        }
+        else k_integrate<NP, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
     }
     return cudaGetLastError();
 }
 
-static cudaError_t launch_integrate_np(int np, const nbt_run_args& A, int first, int count, bool lanes, cudaStream_t st,
-                                       size_t smem_bytes = 0) {
+static cudaError_t launch_integrate_np(int np, const nbt_run_args& A, int first, int count, bool lanes, cudaStream_t st) {
     switch (np) {
-    case 1: return launch_integrate<1>(A, first, count, false, st, smem_bytes);
-    case 2: return launch_integrate<2>(A, first, count, lanes, st, smem_bytes);
-    case 3: return launch_integrate<3>(A, first, count, lanes, st, smem_bytes);
-    case 4: return launch_integrate<4>(A, first, count, lanes, st, smem_bytes);
-    case 5: return launch_integrate<5>(A, first, count, lanes, st, smem_bytes);
-    case 6: return launch_integrate<6>(A, first, count, lanes, st, smem_bytes);
-    case 7: return launch_integrate<7>(A, first, count, lanes, st, smem_bytes);
-    case 8: return launch_integrate<8>(A, first, count, lanes, st, smem_bytes);
+    case 1: return launch_integrate<1>(A, first, count, false, st);
+    case 2: return launch_integrate<2>(A, first, count, lanes, st);
+    case 3: return launch_integrate<3>(A, first, count, lanes, st);
+    case 4: return launch_integrate<4>(A, first, count, lanes, st);
+    case 5: return launch_integrate<5>(A, first, count, lanes, st);
+    case 6: return launch_integrate<6>(A, first, count, lanes, st);
+    case 7: return launch_integrate<7>(A, first, count, lanes, st);
+    case 8: return launch_integrate<8>(A, first, count, lanes, st);
     default: return cudaErrorInvalidValue;
     }
 }
 
 // side stream + fork/join events per device: the lanes kernel (long systems) runs concurrently
 // with the one-system-per-thread kernel (the bulk)
-struct SideStream { cudaStream_t st = nullptr, st2 = nullptr; };
+struct SideStream { cudaStream_t st = nullptr; };
 static std::mutex g_side_mu;
 static SideStream g_side[64];
 
@@ -831,7 +821,6 @@ static cudaError_t get_side(int dev, SideStream** out) {
     if (!s.st) {
         cudaError_t e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
         if (e != cudaSuccess) return e;
-        if ((e = cudaStreamCreateWithFlags(&s.st2, cudaStreamNonBlocking)) != cudaSuccess) return e;
     }
     *out = &s;
     return cudaSuccess;
@@ -911,39 +900,6 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
             if (e == cudaSuccess) e = cudaEventRecord(join, side->st);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
             cudaEventDestroy(fork); cudaEventDestroy(join);   // destruction is deferred until the events complete
-            if (e != cudaSuccess) return e;
-        } else if (nl == 0 && (cfg->heavy_a > 0 || cfg->heavy_b > 0) && !(cfg->flags & NBT_F_SERIES)) {
-            // SM partitioning for heterogeneous batches.  A launch ends when its longest systems end, and a
-            // long warp that shares its SM sub-partition with two or three others runs at a fraction of the
-            // speed it has alone.  The launch order starts with the long systems; class A (the first
-            // heavy_a slots) and class B (the next heavy_b) go out first, on side streams, with a dummy
-            // shared-memory request that lets only 2 (A) or 4 (B) of their CTAs — and, because the bulk
-            // CTAs ask for 30 KB themselves, nothing else — share an SM.  The bulk fills the other SMs and
-            // takes over the heavy ones as they drain.
-            const int nA = std::min(cfg->heavy_a, B), nB = std::min(cfg->heavy_b, B - nA);
-            SideStream* side = nullptr;
-            if ((e = get_side(cfg->device, &side)) != cudaSuccess) return e;
-            cudaEvent_t fork = nullptr, joinA = nullptr, joinB = nullptr;
-            if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-            e = cudaEventCreateWithFlags(&joinA, cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&joinB, cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventRecord(fork, st);
-            if (e == cudaSuccess && nA > 0) {
-                e = cudaStreamWaitEvent(side->st, fork, 0);
-                if (e == cudaSuccess) e = launch_integrate_np(Np, A, 0, nA, false, side->st, 110 * 1024);
-                if (e == cudaSuccess) e = cudaEventRecord(joinA, side->st);
-            }
-            if (e == cudaSuccess && nB > 0) {
-                e = cudaStreamWaitEvent(side->st2, fork, 0);
-                if (e == cudaSuccess) e = launch_integrate_np(Np, A, nA, nB, false, side->st2, 55 * 1024);
-                if (e == cudaSuccess) e = cudaEventRecord(joinB, side->st2);
-            }
-            if (e == cudaSuccess) e = launch_integrate_np(Np, A, nA + nB, B - nA - nB, false, st, 30 * 1024);
-            if (e == cudaSuccess && nA > 0) e = cudaStreamWaitEvent(st, joinA, 0);
-            if (e == cudaSuccess && nB > 0) e = cudaStreamWaitEvent(st, joinB, 0);
-            if (fork) cudaEventDestroy(fork);
-            if (joinA) cudaEventDestroy(joinA);
-            if (joinB) cudaEventDestroy(joinB);
             if (e != cudaSuccess) return e;
         } else {
             e = launch_integrate_np(Np, A, 0, B, nl == B, st);
@@ -1091,31 +1047,6 @@ int nbt_plan_lanes(const nbt_config* cfg, const int32_t* substeps, const int32_t
     if (Np <= 1 || B == 0) return 0;
     if (Np >= 5) return B;
     if (Np >= 3 && B <= 4096) return B;
-    return 0;
-}
-
-/* Heavy classes of a heterogeneous batch (nbt_config.heavy_a / heavy_b, see enqueue_path): with the
- * launch order sorted by decreasing substeps, class A = systems with substeps >= 3 x the median,
- * class B = those with >= 2 x the median.  Only used when the batch is large enough to fill the GPU
- * and the heavy classes are a small minority (<= 15 %); otherwise both are 0. */
-int nbt_plan_partition(const nbt_config* cfg, const int32_t* substeps, const int32_t* order, int32_t* heavy_a,
-                       int32_t* heavy_b) {
-    int rc = check_cfg(cfg);
-    if (rc) return rc;
-    if (!heavy_a || !heavy_b) return nbt_fail(-10, "nbt_plan_partition: NULL argument");
-    *heavy_a = *heavy_b = 0;
-    const int B = cfg->n_systems;
-    if (!substeps || cfg->substeps > 0 || B < 148 * 256) return 0;
-    std::vector<int32_t> ks(substeps, substeps + B);
-    std::nth_element(ks.begin(), ks.begin() + B / 2, ks.end());
-    const int kmed = ks[B / 2];
-    int nA = 0, nAB = 0;
-    auto kof = [&](int slot) { return substeps[order ? order[slot] : slot]; };
-    while (nA < B && kof(nA) >= 3 * kmed) nA++;
-    nAB = nA;
-    while (nAB < B && kof(nAB) >= 2 * kmed) nAB++;
-    if (nAB == 0 || nAB > (int)(0.15 * B)) return 0;
-    *heavy_a = nA; *heavy_b = nAB - nA;
     return 0;
 }
 

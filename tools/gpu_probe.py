@@ -18,10 +18,8 @@ def timed(params, nd, no, flags, reps=2, **kw):
     env = os.environ.get("NBT_PROBE_LANES")          # all | none | <int>; default: planner's choice
     if env:
         kw["lanes"] = len(params) if env == "all" else (0 if env == "none" else int(env))
-    if os.environ.get("NBT_PROBE_PARTITION"):          # "a,b" or "0,0"
-        kw["partition"] = tuple(int(v) for v in os.environ["NBT_PROBE_PARTITION"].split(","))
     plan = engine.Plan(params, nd, no, flags=flags, **kw)
-    print("  lanes=%d heavy=(%d,%d)" % (plan.cfg.lanes_systems, plan.cfg.heavy_a, plan.cfg.heavy_b), end="")
+    print("  lanes=%d" % plan.cfg.lanes_systems, end="")
     d = engine.DeviceBuffers(plan)
     engine.run_device(plan, d)
     torch.cuda.synchronize()
