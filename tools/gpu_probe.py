@@ -38,6 +38,24 @@ def timed(params, nd, no, flags, reps=2, **kw):
     return ms
 
 
+def timed_big(params, nd, no, flags, **kw):
+    """One timed pass for a batch too large to copy back in full: status and counts only."""
+    t0 = time.time()
+    plan = engine.Plan(params, nd, no, flags=flags, **kw)
+    d = engine.DeviceBuffers(plan)
+    print("  planned in %.1f s: B=%d Np=%d steps=%.3g tt capacity %.3g doubles, k hist %s" % (
+        time.time() - t0, plan.B, plan.Np, plan.n_steps, float(plan.tt_offsets[-1]), np.bincount(plan.substeps).tolist()), flush=True)
+    engine.run_device(plan, d, timing=True)
+    torch.cuda.synchronize()
+    ms = engine.stage_timing()
+    st = d.status.cpu().numpy()
+    ntt = d.n_tt.cpu().numpy()
+    fl = plan.n_steps * f_step(plan.Np)
+    print("  integrate %.1f ms  fit %.1f ms  ls %.1f ms -> %.3g steps/s  %.2f TF  %.3g sims/s; transits %d; status %s" % (
+        ms[0], ms[1], ms[2], plan.n_steps / (ms[0] * 1e-3), fl / (ms[0] * 1e-3) * 1e-12, plan.B / (ms.sum() * 1e-3), int(ntt.sum()),
+        {int(s): int((st == s).sum()) for s in np.unique(st)}), flush=True)
+
+
 def main():
     cases = sys.argv[1:] or ["peak", "c1", "c1means", "c1omega", "c2k1", "c2"]
     lib = _abi.load()
@@ -78,6 +96,11 @@ def main():
             fl = {"c2heavy0": 0, "c2heavy1": _abi.F_MEANS, "c2heavy2": _abi.F_MEANS | _abi.F_MEAN_OMEGA,
                   "c2heavy3": _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, "c2heavyp1": _abi.F_PLANET1_ONLY}[c]
             timed(sel, 365.0, 8760, fl, reps=1, substeps=3)
+        elif c == "c5full":      # BASELINE config 5: 1M random 4-planet systems, 3-year integrations
+            timed_big(workloads.c5_params(1000000), 1095.0, 26280, _abi.F_MEANS)
+        elif c == "c4full":      # BASELINE config 4: 256 x 256 grid, 500 epochs of a 1.42 d planet at 30 min
+            par, meta = workloads.c4_params(256)
+            timed_big(par, meta["ndays"], meta["noutputs"], _abi.F_PLANET1_ONLY)
         elif c == "c1big":
             timed(workloads.c1_params(227328), 30.0, 721, 0, substeps=1)
         elif c == "c1bigomega":
