@@ -454,15 +454,15 @@ struct nbt_orbit { double P, a, e, inc, Omega, omega, M; };
 // MODE 0: a, e, inc (the analyze() means); 1: + omega; 2: the full set P, Omega, omega, M.
 // Reciprocals / square roots go through the MUFU-seeded helpers (<= 1 ulp); the acos calls are
 // libdevice's.
+// r, ir: |r| and 1/|r| of (x, y, z) — the caller has just refreshed them (nbt_radius).
 template <int MODE>
-NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, double vx, double vy, double vz) {
+NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, double vx, double vy, double vz,
+                                   double r, double ir) {
     nbt_orbit o;
     const double hx = y * vz - z * vy, hy = z * vx - x * vz, hz = x * vy - y * vx;
     const double h2 = fma(hx, hx, fma(hy, hy, hz * hz));
     const double v2 = fma(vx, vx, fma(vy, vy, vz * vz));
-    const double r2 = fma(x, x, fma(y, y, z * z));
-    const double ir = nbt_rsqrt(r2), r = r2 * ir;
-    const double ih = nbt_rsqrt(h2), h = h2 * ih;
+    const double ih = nbt_rsqrt(h2);
     const double vc2 = mu * ir;
     o.a = -mu * nbt_rcp(v2 - 2.0 * vc2);
     const double rv = fma(x, vx, fma(y, vy, z * vz));
@@ -487,13 +487,18 @@ NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, doub
     o.P = o.Omega = o.omega = o.M = 0.0;
     if (MODE >= 1) {
         const double nx = -hy, ny = hx, n2 = nx * nx + ny * ny;
-        const double nn = (n2 > 0.0) ? n2 * nbt_rsqrt(n2) : 0.0;
+        double nn = 0.0;
+        if (MODE >= 2 || o.inc < 1e-8 || o.inc > NBT_PI - 1e-8) nn = (n2 > 0.0) ? n2 * nbt_rsqrt(n2) : 0.0;
         if (o.inc < 1e-8 || o.inc > NBT_PI - 1e-8) {
             const double Omega = nbt_acos2(nx, nn, ny);
             const double pomega = nbt_acos2(ex, o.e, ey);
             o.omega = (o.inc < 0.5 * NBT_PI) ? pomega - Omega : Omega - pomega;
         } else {
-            o.omega = nbt_acos2(nx * ex + ny * ey, nn * o.e, ez);
+            // cos(omega) = n.e / (|n| |e|): one rsqrt of the product instead of a sqrt and a reciprocal
+            const double den2 = n2 * e2;
+            const double cth = (den2 > 0.0) ? (nx * ex + ny * ey) * nbt_rsqrt(den2) : 2.0;
+            const double val = (cth > -1.0 && cth < 1.0) ? acos(cth) : ((cth <= -1.0) ? NBT_PI : 0.0);
+            o.omega = (ez < 0.0) ? -val : val;
         }
         if (o.e <= 1e-8) o.omega = 0.0;
         if (MODE >= 2) {
@@ -511,7 +516,6 @@ NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, doub
             }
         }
     }
-    (void)h;
     return o;
 }
 
@@ -635,14 +639,14 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
             if (want_omega) {
 #pragma unroll
                 for (int j = 0; j < NP; j++) {
-                    const nbt_orbit ob = nbt_elements<1>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+                    const nbt_orbit ob = nbt_elements<1>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.r[j], s.ir[j]);
                     sum_a[j] += ob.a; sum_e[j] += ob.e; sum_i[j] += ob.inc; sum_o[j] += ob.omega;
                     if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < NP; j++) {
-                    const nbt_orbit ob = nbt_elements<0>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+                    const nbt_orbit ob = nbt_elements<0>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.r[j], s.ir[j]);
                     sum_a[j] += ob.a; sum_e[j] += ob.e; sum_i[j] += ob.inc;
                     if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
                 }
@@ -669,7 +673,7 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
                 row[0] = xs; row[1] = -Ty; row[2] = -Tz;
 #pragma unroll
                 for (int j = 0; j < NP; j++) {
-                    const nbt_orbit ob = nbt_elements<2>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j]);
+                    const nbt_orbit ob = nbt_elements<2>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.r[j], s.ir[j]);
                     double* p = row + 3 + 10 * j;
                     p[0] = dx[j] + xs; p[1] = qy[j] - Ty; p[2] = qz[j] - Tz;
                     p[3] = ob.P; p[4] = ob.a; p[5] = ob.e; p[6] = ob.inc; p[7] = ob.Omega; p[8] = ob.omega; p[9] = ob.M;

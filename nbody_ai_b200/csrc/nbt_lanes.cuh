@@ -191,7 +191,7 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
         dx_prev = dx; dvx_prev = dvx; xs_prev = xs; t_prev = t;
 
         if (want_series) {
-            const nbt_orbit ob = nbt_elements<2>(GMj, x, y, z, vx, vy, vz);
+            const nbt_orbit ob = nbt_elements<2>(GMj, x, y, z, vx, vy, vz, rj, irj);
             if (active) {
                 double* row = A.series + ((size_t)o * B + sys) * W;
                 if (j == 0) { row[0] = xs; row[1] = -Sy; row[2] = -Sz; }
@@ -203,11 +203,11 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
             if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
         } else if (want_means) {
             if (want_omega) {
-                const nbt_orbit ob = nbt_elements<1>(GMj, x, y, z, vx, vy, vz);
+                const nbt_orbit ob = nbt_elements<1>(GMj, x, y, z, vx, vy, vz, rj, irj);
                 sum_a += ob.a; sum_e += ob.e; sum_i += ob.inc; sum_o += ob.omega;
                 if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
             } else {
-                const nbt_orbit ob = nbt_elements<0>(GMj, x, y, z, vx, vy, vz);
+                const nbt_orbit ob = nbt_elements<0>(GMj, x, y, z, vx, vy, vz, rj, irj);
                 sum_a += ob.a; sum_e += ob.e; sum_i += ob.inc;
                 if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
             }

@@ -323,3 +323,76 @@ def stage_timing():
     ms = np.zeros(4)
     _abi.check(lib.nbt_timing(_abi.ptr(ms)), lib)
     return ms
+
+
+# -------------------------------------------------------------------------------------------
+# Single-process multi-GPU: one host thread per device (ctypes releases the GIL inside nbt_run),
+# each integrating its contiguous shard of the batch — the in-process form of SURVEY.md §8e.
+# -------------------------------------------------------------------------------------------
+class ShardedBuffers:
+    """Results of a batch that was split over several devices: routes the per-system views of
+    Buffers (tt_of, ttv_of, n_transits, ls_oc_of, ...) to the shard that owns the system."""
+
+    def __init__(self, shards, bounds):
+        self.shards, self.bounds = shards, bounds      # bounds[i] = (lo, hi) of shard i
+        self.B = bounds[-1][1]
+        self.Np = shards[0].plan.Np
+
+    def locate(self, b):
+        for sh, (lo, hi) in zip(self.shards, self.bounds):
+            if lo <= b < hi:
+                return sh, b - lo
+        raise IndexError(b)
+
+    def n_transits(self, b, j):
+        sh, q = self.locate(b)
+        return sh.n_transits(q, j)
+
+    def tt_of(self, b, j):
+        sh, q = self.locate(b)
+        return sh.tt_of(q, j)
+
+    def ttv_of(self, b, j):
+        sh, q = self.locate(b)
+        return sh.ttv_of(q, j)
+
+    def ls_oc_of(self, b, j):
+        sh, q = self.locate(b)
+        return sh.ls_oc_of(q, j)
+
+    def gathered(self, name):
+        """Per-(system, planet) or per-system array `name` (period, t0, ttv_max, mean_a, ..., status,
+        n_tt) concatenated over the shards in system order."""
+        return np.concatenate([getattr(sh, name) for sh in self.shards])
+
+
+def run_multi_gpu(params, n_days, n_outputs, devices=None, **plan_kw):
+    """Shard `params` by system index over `devices` (default: every visible GPU) and run the shards
+    concurrently, one host thread per device.  Returns ShardedBuffers."""
+    import threading
+    lib = _abi.load()
+    params = _as_params(params)
+    if devices is None:
+        devices = list(range(lib.nbt_device_count()))
+    if not devices:
+        raise RuntimeError("run_multi_gpu: no CUDA device (there is no CPU fallback)")
+    B = params.shape[0]
+    devices = devices[:max(1, min(len(devices), B))]
+    bounds = [shard_range(B, r, len(devices)) for r in range(len(devices))]
+    shards, errors = [None] * len(devices), []
+
+    def work(r):
+        try:
+            lo, hi = bounds[r]
+            shards[r] = run(Plan(params[lo:hi], n_days, n_outputs, device=devices[r], **plan_kw))
+        except Exception as exc:      # surfaced in the caller's thread below
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(len(devices))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return ShardedBuffers(shards, bounds)

@@ -399,3 +399,20 @@ def test_training_set_writer(gpu_lib, tmp_path):
     for g in range(0, len(X), 3):      # variants share everything but omega_2
         assert X[g][:5] == X[g + 1][:5] == X[g + 2][:5] and X[g][6] == X[g + 1][6]
         assert X[g][5] != X[g + 1][5]
+
+
+def test_in_process_multi_gpu_sharding(gpu_lib):
+    """engine.run_multi_gpu: shards over every visible device (one host thread each) reproduce the
+    single-device result bit for bit — systems are independent, there is no data-path collective."""
+    par = regular(workloads.random_systems(300, 2, seed=77))
+    one = engine.run(engine.Plan(par, 90.0, 2161, flags=FULL, lanes=0))
+    ndev = gpu_lib.nbt_device_count()
+    devs = list(range(ndev)) if ndev > 1 else [0, 0, 0]      # on one GPU: three shards on the same device
+    sh = engine.run_multi_gpu(par, 90.0, 2161, devices=devs, flags=FULL, lanes=0)
+    assert len(sh.shards) == len(devs) and sh.B == len(par)
+    for name in ("n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega", "status"):
+        assert np.array_equal(sh.gathered(name), getattr(one, name), equal_nan=True), name
+    for b in (0, 1, len(par) // 2, len(par) - 1):
+        for j in range(2):
+            assert np.array_equal(sh.tt_of(b, j), one.tt_of(b, j)) and np.array_equal(sh.ttv_of(b, j), one.ttv_of(b, j))
+            assert np.array_equal(sh.ls_oc_of(b, j)[1], one.ls_oc_of(b, j)[1])
