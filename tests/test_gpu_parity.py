@@ -416,3 +416,42 @@ def test_in_process_multi_gpu_sharding(gpu_lib):
         for j in range(2):
             assert np.array_equal(sh.tt_of(b, j), one.tt_of(b, j)) and np.array_equal(sh.ttv_of(b, j), one.ttv_of(b, j))
             assert np.array_equal(sh.ls_oc_of(b, j)[1], one.ls_oc_of(b, j)[1])
+
+
+def test_c5_full_length_four_planets(gpu_lib):
+    """BASELINE config 5 at full length (1095 d @ 1 h, 26 280 outputs, four planets, priors extended
+    outward): a 2048-system slice on the GPU, a stratified sample against the oracle, and batch
+    invariance of the sample (same bits whether run inside the slice or alone)."""
+    par = workloads.c5_params(2048, seed=2)
+    plan = engine.Plan(par, 1095.0, 26280, flags=_abi.F_MEANS, lanes=0)
+    got = engine.run(plan)
+    pick = np.arange(0, 2048, 64)
+    pick = np.array([b for b in pick if np.all(par[b, 2:, 1] / par[b, 1:-1, 1] > 1.8)])[:20]
+    sub_plan = engine.Plan(par[pick], 1095.0, 26280, substeps=plan.substeps[pick], flags=_abi.F_MEANS, lanes=0)
+    sub, want = engine.run(sub_plan), oracle_run(sub_plan)
+    ok = {q for q in range(len(pick)) if not (want.status[q] & (_abi.S_NONFINITE | _abi.S_UNBOUND))}
+    assert len(ok) >= 10
+    compare_products(sub, want, sub_plan, skip=set(range(len(pick))) - ok)
+    for q, b in enumerate(pick):
+        for j in range(4):
+            assert np.array_equal(sub.tt_of(q, j), got.tt_of(b, j))
+            assert sub.mean_a[q * 4 + j] == got.mean_a[b * 4 + j]
+
+
+def test_c4_grid_cells_full_length(gpu_lib):
+    """BASELINE config 4 at full length (500 epochs of the 1.42 d planet at 30 min = 34 080 outputs):
+    a 6 x 6 sub-grid; planet-1 transit times and O-C against the oracle."""
+    par, meta = workloads.c4_params(npts=6)
+    plan = engine.Plan(par, meta["ndays"], meta["noutputs"], flags=_abi.F_PLANET1_ONLY, lanes=0)
+    got = engine.run(plan)
+    pick = np.arange(0, 36, 5)
+    sub_plan = engine.Plan(par[pick], meta["ndays"], meta["noutputs"], substeps=plan.substeps[pick],
+                           flags=_abi.F_PLANET1_ONLY | _abi.F_MEANS, lanes=0)
+    sub, want = engine.run(sub_plan), oracle_run(sub_plan)
+    for q, b in enumerate(pick):
+        if par[b, 2, 1] / par[b, 1, 1] < 1.8 or (want.status[q] & (_abi.S_NONFINITE | _abi.S_UNBOUND)):
+            continue
+        assert sub.n_tt[q * 2] == want.n_tt[q * 2] and 495 <= sub.n_tt[q * 2] <= 505
+        assert np.abs(sub.tt_of(q, 0) - want.tt_of(q, 0)).max() * 86400 < TOL_TT_S
+        assert np.abs(sub.ttv_of(q, 0) - want.ttv_of(q, 0)).max() * 1440 < TOL_OC_MIN
+        assert np.array_equal(sub.tt_of(q, 0), got.tt_of(b, 0))
