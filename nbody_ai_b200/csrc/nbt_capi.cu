@@ -1065,7 +1065,7 @@ int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_of
     return 0;
 }
 
-/* Sub-step rule, calibrated against the oracle (tools/calibrate_substeps.py).
+/* Sub-step rule, calibrated against the oracle (tests/calibrate_substeps.py).
  * The binding tolerance is the orbit-averaged e to 1e-8 relative; the composition error scales
  * with (dt_sub / P_innermost)^order, so k = ceil(step * R(scheme) / P_min).  Hill-unstable pairs
  * (Delta < 2 sqrt 3) get no extra resolution: they are chaotic and no step size gives parity. */

@@ -100,3 +100,26 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "libnbt_oracle" not in txt, fn
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No libnbt.so -> the loader raises; nothing falls back to the CPU."""
+    monkeypatch.setattr(_abi, "_LIB", None)
+    monkeypatch.setattr(_abi, "_LIB_PATH", str(tmp_path / "libnbt.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _abi.load()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.Plan(workloads.c1_params(1), 10.0, 241)
+
+
+def test_oracle_is_only_used_by_test_infrastructure():
+    """oracle/ may be imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs only."""
+    allowed = {os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")}
+    for dirpath, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in (".git", "gpurun_out", "__pycache__", "oracle", "tests", ".pytest_cache")]
+        for fn in files:
+            if fn.endswith(".py"):
+                path = os.path.join(dirpath, fn)
+                txt = open(path).read()
+                if "import oracle" in txt or "from oracle" in txt:
+                    assert path in allowed, path

@@ -1,6 +1,6 @@
 """Pins the CPU oracle (test infrastructure) against every known answer the reference offers:
 G1 (figures/report_simulation.png table), G2 (sim_data.txt), the reference's own pure-numpy
-functions run on the oracle's series (tests/golden/ref_functions.npz, tools/make_golden.py),
+functions run on the oracle's series (tests/golden/ref_functions.npz, tests/golden/make_golden.py),
 an independent scipy DOP853 integration, scipy's Lomb-Scargle, numpy lstsq/percentile."""
 import json
 import os
