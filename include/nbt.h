@@ -200,6 +200,16 @@ int nbt_chi2(const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt, 
              const double* yerr, int32_t n_data, double* loglike, int device, int device_ptrs,
              void* cuda_stream);
 
+/* Likelihood of the UltraNest fitter, ttv_fit.py:47-94, for B forward models: for every planet j with
+ * has_data[j], Tc_sim = its transit times shifted so that planet 1's first transit is 0 and offset by
+ * the mean residual at the observed orbit numbers orbit[n_obs] (ttv_fit.py:40);
+ * loglike[b] = sum_j -0.5 sum_i ((tc[j][i] - Tc_sim[orbit[i]]) / tc_err[j][i])^2, and -1e6 for a planet
+ * whose simulation lacks an observed orbit number.  tc, tc_err: [n_planets][n_obs]. */
+int nbt_ttvfit_loglike(const double* tt, const int64_t* tt_offsets, const int32_t* n_tt, int32_t n_systems,
+                       int32_t n_planets, const int32_t* has_data, const double* tc, const double* tc_err,
+                       const int32_t* orbit, int32_t n_obs, double* loglike, int device, int device_ptrs,
+                       void* cuda_stream);
+
 /* Grid-cell post-processing of simulations/simulation_grid.py:33-69 for B systems (planet 1):
  * exact periodogram of the O-C on the autofrequency grid (minfreq, maxfreq, samples_per_peak),
  * scipy find_peaks(height=peak_height) sorted by height, top n_order (<= 8) peak periods

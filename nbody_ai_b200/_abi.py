@@ -146,6 +146,8 @@ def load():
     lib.nbt_maxavg.argtypes = [_dp, C.c_int64, C.c_int64, _dp, C.c_int, C.c_int, C.c_void_p]
     lib.nbt_fp64_peak.argtypes = [C.c_int, C.c_int, _dp, _dp]
     lib.nbt_timing.argtypes = [_dp]
+    lib.nbt_ttvfit_loglike.argtypes = [_dp, _lp, _ip, C.c_int32, C.c_int32, _ip, _dp, _dp, _ip, C.c_int32, _dp,
+                                       C.c_int, C.c_int, C.c_void_p]
     lib.nbt_grid_post.argtypes = [_dp, _dp, _lp, _ip, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32,
                                   C.c_double, C.c_int32, _dp, _dp, _ip, _dp, _dp, C.c_int, C.c_int, C.c_void_p]
     lib.nbt_fp64_latency.argtypes = [C.c_int, _dp, _dp]

@@ -688,6 +688,46 @@ __global__ void k_chi2(const double* __restrict__ ttv, const int64_t* __restrict
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_ttvfit: likelihood of ttv_fit.py:47-94 (UltraNest fitter), one thread per forward model.
+// For every planet with data: Tc_sim = its transit times; shifted so that planet 1's first
+// transit is 0; offset by the mean residual at the observed orbit numbers; chi2 accumulated.
+// A missing orbit number (IndexError in the reference) gives that planet's term -1e6.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_ttvfit(const double* __restrict__ tt, const int64_t* __restrict__ tt_offsets,
+                         const int32_t* __restrict__ n_tt, int B, int Np, const int32_t* __restrict__ has_data,
+                         const double* __restrict__ tc, const double* __restrict__ tc_err,
+                         const int32_t* __restrict__ orbit, int n_obs, double* __restrict__ loglike) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double chi2 = 0.0, sim_shift = 0.0;
+    for (int j = 0; j < Np; j++) {
+        if (!has_data[j]) continue;
+        const int64_t off = tt_offsets[(size_t)b * Np + j];
+        const int cap = (int)(tt_offsets[(size_t)b * Np + j + 1] - off);
+        const int n = min(n_tt[(size_t)b * Np + j], cap);
+        const double* ts = tt + off;
+        bool ok = n > 0;
+        if (ok && j == 0) sim_shift = ts[0];                 // Tc_sim.min(): transit times are increasing
+        for (int i = 0; i < n_obs && ok; i++) { const int k = orbit[i]; if (k >= n || k < -n) ok = false; }
+        if (!ok) { chi2 += -1e6; continue; }
+        const double* d = tc + (size_t)j * n_obs;
+        const double* e = tc_err + (size_t)j * n_obs;
+        double mean = 0.0;
+        for (int i = 0; i < n_obs; i++) { int k = orbit[i]; if (k < 0) k += n; mean += d[i] - (ts[k] - sim_shift); }
+        mean /= (double)n_obs;
+        double s2 = 0.0;
+        for (int i = 0; i < n_obs; i++) {
+            int k = orbit[i]; if (k < 0) k += n;
+            const double r = (d[i] - ((ts[k] - sim_shift) + mean)) / e[i];
+            s2 = fma(r, r, s2);
+        }
+        chi2 += -0.5 * s2;
+    }
+    loglike[b] = chi2;
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_dfma_peak: 8 independent DFMA chains per thread — the measured FP64 roofline denominator
 // ---------------------------------------------------------------------------------------------
@@ -1483,6 +1523,31 @@ int nbt_grid_post(const double* tt, const double* ttv, const int64_t* tt_offsets
         S.check(cudaFuncSetAttribute(k_grid_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(need * 8)), "cudaFuncSetAttribute");
         if (!S.rc) k_grid_post<<<n_systems, 128, (size_t)need * 8, S.st>>>(G);
     }
+    return S.finish();
+}
+
+
+int nbt_ttvfit_loglike(const double* tt, const int64_t* tt_offsets, const int32_t* n_tt, int32_t n_systems,
+                       int32_t n_planets, const int32_t* has_data, const double* tc, const double* tc_err,
+                       const int32_t* orbit, int32_t n_obs, double* loglike, int device, int device_ptrs,
+                       void* cuda_stream) {
+    if (!tt || !tt_offsets || !n_tt || !has_data || !tc || !tc_err || !orbit || !loglike)
+        return nbt_fail(-10, "nbt_ttvfit_loglike: NULL argument");
+    if (n_systems < 0 || n_planets < 1 || n_obs < 1) return nbt_fail(-11, "nbt_ttvfit_loglike: bad sizes");
+    if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_ttvfit_loglike: no CUDA device (there is no CPU fallback)");
+    if (n_systems == 0) return 0;
+    Stage S(device, device_ptrs, cuda_stream);
+    const int64_t nsp = (int64_t)n_systems * n_planets;
+    const int64_t ntt = device_ptrs ? 0 : tt_offsets[nsp];
+    const double* d_tt = S.in(tt, (size_t)ntt);
+    const int64_t* d_off = S.in(tt_offsets, (size_t)nsp + 1);
+    const int32_t* d_n = S.in(n_tt, (size_t)nsp);
+    const int32_t* d_has = S.in(has_data, (size_t)n_planets);
+    const double* d_tc = S.in(tc, (size_t)n_planets * n_obs);
+    const double* d_err = S.in(tc_err, (size_t)n_planets * n_obs);
+    const int32_t* d_orb = S.in(orbit, (size_t)n_obs);
+    double* d_ll = S.out(loglike, (size_t)n_systems);
+    if (!S.rc) k_ttvfit<<<(n_systems + 127) / 128, 128, 0, S.st>>>(d_tt, d_off, d_n, n_systems, n_planets, d_has, d_tc, d_err, d_orb, n_obs, d_ll);
     return S.finish();
 }
 

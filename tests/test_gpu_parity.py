@@ -455,3 +455,39 @@ def test_c4_grid_cells_full_length(gpu_lib):
         assert np.abs(sub.tt_of(q, 0) - want.tt_of(q, 0)).max() * 86400 < TOL_TT_S
         assert np.abs(sub.ttv_of(q, 0) - want.ttv_of(q, 0)).max() * 1440 < TOL_OC_MIN
         assert np.array_equal(sub.tt_of(q, 0), got.tt_of(b, 0))
+
+
+def test_ttv_fit_vectorised_likelihood(gpu_lib):
+    """ttv_fit.py:47-94 (UltraNest fitter): batched likelihood vs a direct numpy restatement applied to the
+    oracle's transit times."""
+    from nbody_ai_b200.ttv_fit import NbodyLikelihood
+    from nbody_ai_b200.tools import mearth, msun
+    truth = [{'m': 1.12}, {'m': 80 * mearth / msun, 'P': 3.2888, 'inc': np.pi / 2, 'e': 0, 'omega': 0},
+             {'m': 40 * mearth / msun, 'P': 7.0, 'inc': np.pi / 2, 'e': 0, 'omega': 0}]
+    t, ser, _, _ = oracle.integrate_series(_abi.objects_to_params(truth), 80, 80 * 24 + 1)
+    tc1 = oracle.transit_times(ser[:, 3], ser[:, 0], t)[2:20]
+    tc2 = oracle.transit_times(ser[:, 13], ser[:, 0], t)[:18]
+    rng = np.random.default_rng(9)
+    data = [{}, {'Tc': tc1 + rng.normal(0, 2e-4, 18), 'Tc_err': np.full(18, 2e-4)},
+            {'Tc': tc2 + rng.normal(0, 5e-4, 18), 'Tc_err': np.full(18, 5e-4)}]
+    bounds = [{}, {'P': [3.28, 3.30]}, {'P': [6.9, 7.1], 'm': [20 * mearth / msun, 60 * mearth / msun], 'omega': [-np.pi, np.pi]}]
+    L = NbodyLikelihood(data, truth, bounds)
+    thetas = np.array([L.prior_transform(u) for u in rng.uniform(size=(40, 4))])
+    got = L.loglike_batch(thetas)
+    par = L.params_for(thetas)
+    for b in (0, 7, 21, 39):
+        ts, sr, _, _ = oracle.integrate_series(par[b], L.sim_time, int(L.sim_time * 24))
+        chi2, shift = 0.0, 0.0
+        for i in (1, 2):
+            Tc_sim = oracle.transit_times(sr[:, 3 + 10 * (i - 1)], sr[:, 0], ts)
+            if i == 1:
+                shift = Tc_sim.min()
+            Tc_sim = Tc_sim - shift
+            res = data[i]['Tc'] - Tc_sim[L.orbit]
+            Tc_sim = Tc_sim + res.mean()
+            chi2 += -0.5 * np.sum(((data[i]['Tc'] - Tc_sim[L.orbit]) / data[i]['Tc_err']) ** 2)
+        assert abs(got[b] - chi2) <= 2e-3 * abs(chi2) + 1e-6, (b, got[b], chi2)
+    assert np.isfinite(got).all()
+    # an observed orbit number beyond the simulated span -> -1e6 for that planet (the reference's except branch)
+    L.orbit[-1] = 10 ** 6
+    assert (L.loglike_batch(thetas[:3]) <= -1e6).all()
