@@ -466,10 +466,10 @@ def test_ttv_fit_vectorised_likelihood(gpu_lib):
              {'m': 40 * mearth / msun, 'P': 7.0, 'inc': np.pi / 2, 'e': 0, 'omega': 0}]
     t, ser, _, _ = oracle.integrate_series(_abi.objects_to_params(truth), 80, 80 * 24 + 1)
     tc1 = oracle.transit_times(ser[:, 3], ser[:, 0], t)[2:20]
-    tc2 = oracle.transit_times(ser[:, 13], ser[:, 0], t)[:18]
     rng = np.random.default_rng(9)
-    data = [{}, {'Tc': tc1 + rng.normal(0, 2e-4, 18), 'Tc_err': np.full(18, 2e-4)},
-            {'Tc': tc2 + rng.normal(0, 5e-4, 18), 'Tc_err': np.full(18, 5e-4)}]
+    # the reference indexes every planet's Tc_sim with planet 1's orbit numbers (ttv_fit.py:37 "TODO extend
+    # for multiplanet systems"), so only planet 1 can carry data consistently
+    data = [{}, {'Tc': tc1 + rng.normal(0, 2e-4, 18), 'Tc_err': np.full(18, 2e-4)}, {}]
     bounds = [{}, {'P': [3.28, 3.30]}, {'P': [6.9, 7.1], 'm': [20 * mearth / msun, 60 * mearth / msun], 'omega': [-np.pi, np.pi]}]
     L = NbodyLikelihood(data, truth, bounds)
     thetas = np.array([L.prior_transform(u) for u in rng.uniform(size=(40, 4))])
@@ -478,7 +478,7 @@ def test_ttv_fit_vectorised_likelihood(gpu_lib):
     for b in (0, 7, 21, 39):
         ts, sr, _, _ = oracle.integrate_series(par[b], L.sim_time, int(L.sim_time * 24))
         chi2, shift = 0.0, 0.0
-        for i in (1, 2):
+        for i in (1,):
             Tc_sim = oracle.transit_times(sr[:, 3 + 10 * (i - 1)], sr[:, 0], ts)
             if i == 1:
                 shift = Tc_sim.min()
@@ -488,6 +488,11 @@ def test_ttv_fit_vectorised_likelihood(gpu_lib):
             chi2 += -0.5 * np.sum(((data[i]['Tc'] - Tc_sim[L.orbit]) / data[i]['Tc_err']) ** 2)
         assert abs(got[b] - chi2) <= 2e-3 * abs(chi2) + 1e-6, (b, got[b], chi2)
     assert np.isfinite(got).all()
-    # an observed orbit number beyond the simulated span -> -1e6 for that planet (the reference's except branch)
+    # planet-2 data indexed by planet-1 orbit numbers runs past planet 2's transits -> -1e6 for that planet
+    # (the reference's except branch); so does an orbit number beyond the simulated span
+    data2 = [data[0], data[1], {'Tc': np.arange(18) * 7.0, 'Tc_err': np.full(18, 1e-3)}]
+    L2 = NbodyLikelihood(data2, truth, bounds)
+    ll2 = L2.loglike_batch(thetas[:3])
+    assert np.all(ll2 <= -1e6) and np.allclose(ll2 + 1e6, got[:3], rtol=1e-9, atol=1e-6)
     L.orbit[-1] = 10 ** 6
     assert (L.loglike_batch(thetas[:3]) <= -1e6).all()
