@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NBT_LBLOCK) k_integrate_lanes(const nbt_run_ar
     const int sys = (A.order != nullptr) ? A.order[first + idx] : first + idx;
     const int base = g * NP;
     const unsigned gmask = ((NP == 32) ? 0xffffffffu : ((1u << NP) - 1u)) << base;
-    nbt_simulate_lane<NP, SERIES>(A, sys, j, base, gmask, true);
+    nbt_simulate_lane<NP, SERIES>(A, sys, j, base, gmask);
 }
 
 // ---------------------------------------------------------------------------------------------

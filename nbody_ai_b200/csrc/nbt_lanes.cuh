@@ -1,13 +1,12 @@
 // nbt_lanes.cuh — "one planet per lane" form of the integrator (device only).
 //
 // A system is spread over NP consecutive lanes of a warp (32/NP systems per warp): lane j holds
-// the Jacobi coordinate of planet j.  The Kepler drifts (the bulk of a stage) then run in
-// parallel across lanes and the interaction kick exchanges positions / pair accelerations with
-// warp shuffles across the bodies of a group.  Per lane a stage is ~40 % shorter than in the
-// one-system-per-thread kernel, which is what the latency/issue-bound cases need: the long
-// systems of a batch (most sub-steps: they set the kernel's critical path) and small batches that
-// cannot fill 148 SMs with one thread per system.  Total work is ~20 % higher (pairs and the
-// Jacobi recurrences are evaluated redundantly), so the throughput-bound bulk stays on k_integrate.
+// the Jacobi coordinate of planet j.  The Kepler drifts (the bulk of a stage) run in parallel across
+// lanes and the interaction kick exchanges positions / pair accelerations with warp shuffles
+// across the bodies of a group.  Total work is ~20 % higher than in k_integrate (pairs and the
+// Jacobi recurrences are evaluated redundantly) and a lane has a single dependency chain (ILP 1),
+// so this form pays only where one thread per system is issue-bound or spills (measured, see
+// nbt_plan_lanes): Np >= 5 always, Np >= 3 for small batches and single systems.
 //
 // Same arithmetic per body as nbt_core.cuh (nbt_kepler_drift, nbt_elements, nbt_rsqrt); sums over
 // bodies are taken in the same order, so results agree with k_integrate to round-off.
@@ -84,9 +83,8 @@ __device__ __forceinline__ void nbt_accel_lane(unsigned gmask, int base, int j, 
 }
 
 // One lane of one system: integrate + sample + detect transits (the lanes form of nbt_simulate_system).
-// `active` lanes own a real (system, planet); inactive ones shadow a valid system and write nothing.
 template <int NP, bool SERIES>
-__device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int base, unsigned gmask, bool active) {
+__device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int base, unsigned gmask) {
     const double* par = A.params + (size_t)sys * (NP + 1) * NBT_NPAR;
     double mr[NP], Gm[NP + 1];
     double GMj = 0.0;
@@ -183,16 +181,16 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
         if (o > 0) {
             if (tt_on && dx_prev >= 0.0 && dx <= 0.0) {                    // simulation.py:168
                 const double t0 = nbt_crossing_time(A.tt_mode, t_prev, t, dx_prev, dx, dvx_prev, dvx);  // tools.py:61-65
-                if (active) { if (cnt < cap) A.tt[off + cnt] = t0; else status |= NBT_S_TT_OVERFLOW; }
+                if (cnt < cap) A.tt[off + cnt] = t0; else status |= NBT_S_TT_OVERFLOW;
                 cnt++;
             }
-            if (want_rv && active && j == 0) A.rv[(size_t)(o - 1) * B + sys] = (xs - xs_prev) * rv_scale;
+            if (want_rv && j == 0) A.rv[(size_t)(o - 1) * B + sys] = (xs - xs_prev) * rv_scale;
         }
         dx_prev = dx; dvx_prev = dvx; xs_prev = xs; t_prev = t;
 
         if (want_series) {
             const nbt_orbit ob = nbt_elements<2>(GMj, x, y, z, vx, vy, vz, rj, irj);
-            if (active) {
+            {
                 double* row = A.series + ((size_t)o * B + sys) * W;
                 if (j == 0) { row[0] = xs; row[1] = -Sy; row[2] = -Sz; }
                 double* p = row + 3 + 10 * j;
@@ -212,7 +210,7 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
                 if (!(ob.a > 0.0)) status |= NBT_S_UNBOUND;
             }
         }
-        if (want_orbit && active && (o % A.orbit_stride) == 0) {            // simulation.py:227-228
+        if (want_orbit && (o % A.orbit_stride) == 0) {            // simulation.py:227-228
             double* dst = A.orbit_xz + (((size_t)(o / A.orbit_stride) * B + sys) * NP + j) * 2;
             dst[0] = dx + xs; dst[1] = hz - Sz;
         }
@@ -222,7 +220,7 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
     int gs = status;
 #pragma unroll
     for (int i = 0; i < NP; i++) gs |= __shfl_sync(gmask, status, base + i);
-    if (active) {
+    {
         const size_t sp = (size_t)sys * NP + j;
         A.n_tt[sp] = cnt;
         if (want_means || want_series) {
