@@ -1,0 +1,93 @@
+"""Host-side mirror of the reference interfaces: parameter mapping, planning and dict layouts that
+need no GPU (everything numeric on the path is CUDA and is covered by the -m gpu tests)."""
+import numpy as np
+import pytest
+
+from nbody_ai_b200 import _abi, engine, nested, simulation, tools, workloads
+from nbody_ai_b200.ttv_fit import NbodyLikelihood
+from conftest import golden
+
+
+def test_constants_and_scalar_helpers_match_reference():
+    """nbody/tools.py:11-59: constants, sa, hill_sphere against the reference's own outputs."""
+    ref = golden("ref_functions.npz")
+    assert tools.G == 0.00029591220828559104 and tools.msun == 1.989e30 and tools.mearth == 5.972e24
+    assert np.allclose([tools.sa(1.12, 3.2888), tools.sa(0.8, 20.0)], ref["sa"], rtol=1e-15)
+    objs = workloads.c1_objects()
+    hill = [tools.hill_sphere(objs, i=i) for i in (1, 2, 3)]
+    assert np.allclose(hill, ref["hill"], rtol=1e-10)
+    assert abs(tools.m2r_star(1.0) - 1.0) < 1e-15 and abs(tools.m2r_star(0.855) - 0.89) < 1e-12
+    with pytest.raises(ValueError):
+        tools.m2r_star(50.0)
+
+
+def test_vectorised_priors_agree_with_scalar_hill_sphere():
+    par = workloads.random_systems(40, 2, seed=4)
+    for b in range(40):
+        objs = [{'m': par[b, 0, 0]}, {'m': par[b, 1, 0], 'P': par[b, 1, 1]}, {'m': par[b, 2, 0], 'P': par[b, 2, 1]}]
+        a1, a2 = tools.sa(par[b, 0, 0], par[b, 1, 1]), tools.sa(par[b, 0, 0], par[b, 2, 1])
+        h1, h2 = tools.hill_sphere(objs, 1), tools.hill_sphere(objs, 2)
+        assert a1 + h1 <= a2 - h2                       # the reference's acceptance rule (simulation.py:87)
+        hb = workloads.hill_sphere_batch(par[b:b + 1, 0, 0], par[b:b + 1, 1, 0], par[b:b + 1, 1, 1])[0]
+        assert abs(hb / h1 - 1) < 1e-9
+    assert np.all((par[:, 1, 1] >= 0.8) & (par[:, 1, 1] <= 20) & (par[:, 0, 0] >= 0.75) & (par[:, 0, 0] <= 1.15))
+    ratio = par[:, 2, 0] / par[:, 1, 0]
+    assert np.all((ratio >= 0.1) & (ratio <= 10)) and np.all(par[:, 1:, 3] == np.pi / 2)
+
+
+def test_workload_shapes():
+    assert workloads.c1_params(3).shape == (3, 4, 7)
+    c2 = workloads.c2_params(5, 6, seed=0)
+    assert c2.shape == (35, 3, 7)
+    assert np.array_equal(c2[0:7, :, :5], np.repeat(c2[0:1, :, :5], 7, axis=0))      # variants differ in omega_2 only
+    assert len(set(c2[0:7, 2, 5])) == 7
+    c3, meta = workloads.c3_params(10)
+    assert c3.shape == (10, 3, 7) and meta["noutputs"] == meta["ndays"] * 48
+    c4, meta4 = workloads.c4_params(4)
+    assert c4.shape == (16, 3, 7) and meta4["noutputs"] == 34080 and np.all(c4[:, 1, 1] == 1.42)
+    assert workloads.c5_params(20).shape == (20, 5, 7)
+
+
+def test_plan_flags_and_views(nbt):
+    par = workloads.c1_params(2)
+    plan = engine.Plan(par, 365, 8760, flags=_abi.F_MEANS | _abi.F_LS_OC | _abi.F_RV | _abi.F_LS_RV | _abi.F_ORBIT)
+    buf = engine.Buffers(plan)
+    assert buf.rv.shape == (8759, 2) and buf.orbit_xz.shape == (2190, 2, 3, 2) and plan.rv_nfreq == 1816
+    assert buf.series is None and len(buf.tt) == plan.tt_offsets[-1]
+    assert plan.cfg.lanes_systems == 2                    # small 3-planet batch -> one planet per lane
+    assert np.array_equal(plan.times, np.linspace(0, 365, 8760))
+    f, p = buf.ls_rv_of(0)
+    assert len(f) == 1816 and abs(f[0] - 1 / 365) < 1e-18
+    p1 = engine.Plan(par, 60, 2881, flags=_abi.F_PLANET1_ONLY)
+    assert list(np.diff(p1.tt_offsets)) == [23, 1, 1, 23, 1, 1]
+    with pytest.raises(ValueError):
+        engine.Plan(par[:, :, :6], 10, 241)
+    with pytest.raises(ValueError):
+        engine.Plan(par, 10, 1)
+
+
+def test_sampler_parameter_mapping():
+    objects = [{'m': 1.22}, {'m': 0.01, 'P': 0.94145, 'inc': np.pi / 2}, {'m': 1e-4, 'P': 2.0, 'e': 0.0, 'omega': 0.0, 'inc': np.pi / 2}]
+    bounds = [[0.1, 0.2], {'P': [0.94, 0.95]}, {'P': [1.9, 2.4], 'm': [1e-5, 4e-4], 'omega': [-np.pi, np.pi]}]
+    out = nested.apply_params(objects, bounds, [0.15, 0.9412, 2.1, 2e-4, 1.0])
+    assert out[1]['P'] == 0.9412 and out[2]['P'] == 2.1 and out[2]['m'] == 2e-4 and out[2]['omega'] == 1.0
+    assert objects[2]['P'] == 2.0                          # the input list is not mutated
+    assert nested.nlfit_ndays(np.arange(56.0), objects) == int(np.round(1.5 * 56 * 0.94145))
+    data = [{}, {'Tc': 0.3 + 0.94145 * np.array([0, 1, 2, 5, 9.0]), 'Tc_err': np.full(5, 1e-3)}, {}]
+    L = NbodyLikelihood(data, objects, [{}, {'P': [0.94, 0.95]}, {'m': [1e-5, 4e-4]}])
+    assert list(L.orbit) == [0, 1, 2, 5, 9] and abs(L.sim_time - (9 * 0.94145 + 5 * 0.94145)) < 1e-12
+    th = L.prior_transform(np.array([0.5, 0.5]))
+    assert np.allclose(th, [0.945, 2.05e-4])
+    par = L.params_for(np.array([[0.941, 3e-4], [0.949, 1e-5]]))
+    assert par.shape == (2, 3, 7) and par[0, 1, 1] == 0.941 and par[1, 2, 0] == 1e-5 and par[0, 2, 1] == 2.0
+
+
+def test_randomize_draws_match_reference_rng():
+    """simulation.randomize() consumes np.random exactly like the reference (fixture from the reference's own
+    randomize() under np.random.seed(1234)); host-only, no GPU."""
+    ref = golden("ref_functions.npz")["randomize_seed1234"]
+    np.random.seed(1234)
+    for row in ref[:6]:
+        o = simulation.randomize()
+        got = [o[0]['m'], o[1]['m'], o[1]['P'], o[2]['m'], o[2]['P'], o[2]['e'], o[2]['omega'], o[1]['inc'], o[2]['inc']]
+        assert np.allclose(got, row, rtol=1e-12, atol=0)

@@ -33,8 +33,8 @@ def timed(params, nd, no, flags, reps=2, **kw):
     Np = plan.Np
     fl = plan.n_steps * f_step(Np)
     st = {int(s): int((h.status == s).sum()) for s in np.unique(h.status)}
-    print("  B=%d Np=%d steps=%.3g  integrate %.2f ms  fit %.3f ms  ls %.3f ms  -> %.3g steps/s  %.2f TF  status %s" % (
-        plan.B, Np, plan.n_steps, ms[0], ms[1], ms[2], plan.n_steps / (ms[0] * 1e-3), fl / (ms[0] * 1e-3) * 1e-12, st), flush=True)
+    print("  B=%d Np=%d steps=%.3g  integrate %.2f ms  fit %.3f ms  ls %.3f ms  rv %.3f ms -> %.3g steps/s  %.2f TF  status %s" % (
+        plan.B, Np, plan.n_steps, ms[0], ms[1], ms[2], ms[3], plan.n_steps / (ms[0] * 1e-3), fl / (ms[0] * 1e-3) * 1e-12, st), flush=True)
     return ms
 
 
@@ -101,6 +101,8 @@ def main():
         elif c == "c4full":      # BASELINE config 4: 256 x 256 grid, 500 epochs of a 1.42 d planet at 30 min
             par, meta = workloads.c4_params(256)
             timed_big(par, meta["ndays"], meta["noutputs"], _abi.F_PLANET1_ONLY)
+        elif c == "c1rv":      # full analyze() extras: RV series, its maxavg and its periodogram (8759 x 1816)
+            timed(workloads.c1_params(4096), 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC | _abi.F_RV | _abi.F_LS_RV, reps=1, lanes=0)
         elif c == "c1big":
             timed(workloads.c1_params(227328), 30.0, 721, 0, substeps=1)
         elif c == "c1bigomega":
