@@ -100,6 +100,16 @@ def ncu_traffic(np_, b):
     return None
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -141,7 +151,8 @@ def run_reference(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_systems_per_step": per_step, "n_days": N_DAYS, "n_outputs": N_OUTPUTS},
         "system_steps_per_s": sims * (N_OUTPUTS - 1),
-        "cpu_baseline": {"value": sims, "unit": "sims/s", "cores": nt, "kind": "port",
+        "cpu_baseline": {"value": sims, "unit": "sims/s", "cores": nt, "kind": "port", "cpu_model": cpu_model(),
+                         "host_cpus": os.cpu_count(),
                          "sample": "%d systems of the C2 batch per step, oracle (IAS15 + analyze) on %d host threads" % (per_step, nt)},
         "e2e": {"value": sims, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -266,7 +277,8 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             n_s = min(args.cpu_sample, B)
             dt, nt, _ = cpu_path(params[:n_s])
-            line["cpu_baseline"] = {"value": n_s / dt, "unit": "sims/s", "cores": nt, "kind": "port",
+            line["cpu_baseline"] = {"value": n_s / dt, "unit": "sims/s", "cores": nt, "kind": "port", "cpu_model": cpu_model(),
+                                    "host_cpus": os.cpu_count(),
                                     "sample": "first %d systems of the same batch, oracle (IAS15 + analyze) on %d host threads, %.1f s" % (n_s, nt, dt)}
         emit(line)
     if dist is not None:
