@@ -905,7 +905,8 @@ struct Arena {
 // (k_scan_series) instead of integrating (k_integrate).
 static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, const nbt_outputs* out,
                                 double* rv_sm_ws, cudaStream_t st, const double* scan_series = nullptr,
-                                const double* scan_times = nullptr, double scan_dt = 0.0) {
+                                const double* scan_times = nullptr, double scan_dt = 0.0,
+                                cudaEvent_t after_fit = nullptr) {
     const int B = cfg->n_systems, Np = cfg->n_bodies - 1, NO = cfg->n_outputs;
     if (B == 0) return cudaSuccess;
     cudaError_t e;
@@ -971,6 +972,9 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
     k_fit<<<fit_grid, 128, 0, st>>>(F);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     timing_mark(2, tim, st);
+    // everything but the periodograms and RV reductions is final here: the host path starts copying
+    // those products back on a second stream while k_ls_oc runs
+    if (after_fit && (e = cudaEventRecord(after_fit, st)) != cudaSuccess) return e;
 
     if ((cfg->flags & NBT_F_LS_OC) && out->ls_oc_power && in->ls_offsets) {
         nbt_lsoc_args L;
@@ -1161,6 +1165,7 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamPerThread;
     char* arena = nullptr;
     double* rv_ws = nullptr;
+    cudaEvent_t ev_fit = nullptr;
     NBT_CUDA(cudaSetDevice(cfg->device));
     ensure_pool(cfg->device);
     {
@@ -1240,15 +1245,25 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         dout.rv = (double*)dp(b_rv); dout.rv_max = (double*)dp(b_rvmax); dout.orbit_xz = (double*)dp(b_orb);
         dout.series = (double*)dp(b_ser); dout.ls_oc_power = (double*)dp(b_lsp); dout.ls_oc_nfreq = (int32_t*)dp(b_lsn);
         dout.ls_rv_power = (double*)dp(b_lsrv);
+        SideStream* side = nullptr;
+        NBT_CUDA(get_side(cfg->device, &side));
+        NBT_CUDA(cudaEventCreateWithFlags(&ev_fit, cudaEventDisableTiming));
         NBT_CUDA(enqueue_path(cfg, &din, &dout, (double*)dp(b_rvws), st, scan ? (const double*)dp(b_ser) : nullptr,
-                              (const double*)dp(b_times), scan_dt));
-        Buf* outs[] = {&b_tt, &b_ttv, &b_ntt, &b_per, &b_t0, &b_max, &b_ma, &b_me, &b_mi, &b_mo, &b_stat,
-                       &b_rv, &b_rvmax, &b_orb, &b_ser, &b_lsp, &b_lsn, &b_lsrv};
-        for (Buf* b : outs)
+                              (const double*)dp(b_times), scan_dt, ev_fit));
+        // products that are final after k_fit go back on the side stream, overlapping k_ls_oc / the RV stages
+        Buf* early[] = {&b_tt, &b_ttv, &b_ntt, &b_per, &b_t0, &b_max, &b_ma, &b_me, &b_mi, &b_mo, &b_stat, &b_orb, &b_ser};
+        Buf* late[] = {&b_rv, &b_rvmax, &b_lsp, &b_lsn, &b_lsrv};
+        NBT_CUDA(cudaStreamWaitEvent(side->st, ev_fit, 0));
+        for (Buf* b : early)
+            if (b->bytes && b->h_out) NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, side->st));
+        for (Buf* b : late)
             if (b->bytes && b->h_out) NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, st));
+        NBT_CUDA(cudaStreamSynchronize(side->st));
         NBT_CUDA(cudaStreamSynchronize(st));
     }
 done:
+    if (ev_fit) cudaEventDestroy(ev_fit);
+    if (rc != 0 && arena) cudaDeviceSynchronize();     // error path: nothing may still touch the arena
     if (arena) cudaFreeAsync(arena, st);
     if (rv_ws) cudaFreeAsync(rv_ws, st);
     if (rc != 0) cudaGetLastError();
