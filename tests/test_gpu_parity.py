@@ -496,3 +496,22 @@ def test_ttv_fit_vectorised_likelihood(gpu_lib):
     assert np.all(ll2 <= -1e6) and np.allclose(ll2 + 1e6, got[:3], rtol=1e-9, atol=1e-6)
     L.orbit[-1] = 10 ** 6
     assert (L.loglike_batch(thetas[:3]) <= -1e6).all()
+
+
+def test_single_planet_two_body(gpu_lib):
+    """n_bodies = 2: a pure Kepler orbit — strictly periodic transits (O-C at round-off), constant elements,
+    and agreement with the oracle; eccentric case included."""
+    par = np.zeros((3, 2, 7))
+    par[:, 0, 0] = [1.0, 0.8, 1.12]
+    par[:, 1, 0] = [1e-3, 3e-6, 2.7e-4]
+    par[:, 1, 1] = [3.3, 11.0, 0.9]
+    par[:, 1, 2] = [0.0, 0.3, 0.05]
+    par[:, 1, 3] = np.pi / 2
+    par[:, 1, 5] = [0.0, 1.0, 4.0]
+    plan = engine.Plan(par, 120.0, 2881, flags=FULL)
+    got, want = engine.run(plan), oracle_run(plan)
+    compare_products(got, want, plan)
+    for b in range(3):
+        assert np.abs(got.ttv_of(b, 0)).max() * 1440 < 0.1           # only the grid-linear interpolation error remains
+        assert abs(got.period[b] / par[b, 1, 1] - 1) < 1e-6
+        assert abs(got.mean_e[b] - par[b, 1, 2]) < 1e-9
