@@ -92,8 +92,7 @@ typedef struct nbt_config {
                             from host tt_offsets (required > 0 with NBT_F_DEVICE_PTRS) */
     int32_t lanes_systems; /* leading launch-order slots integrated by the one-planet-per-lane
                             kernel (nbt_plan_lanes); 0 = none, n_systems = all */
-    int32_t split_systems; /* leading launch-order slots (the long systems) integrated, fitted and
-                            analysed on a stream of their own (nbt_plan_split); 0 = one launch */
+    int32_t reserved;
 } nbt_config;
 
 typedef struct nbt_inputs {
@@ -150,8 +149,6 @@ int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* s
 /* Number of leading launch-order slots for the one-planet-per-lane kernel (host helper); the
  * caller stores it in cfg.lanes_systems.  substeps / order may be NULL. */
 int nbt_plan_lanes(const nbt_config* cfg, const int32_t* substeps, const int32_t* order);
-/* Size of the long-systems class for a split launch (host helper) -> cfg.split_systems. */
-int nbt_plan_split(const nbt_config* cfg, const int32_t* substeps, const int32_t* order);
 /* Fill ls_offsets[B*Np+1] from tt_offsets (capacity of the O-C periodogram). */
 int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets);
 
@@ -228,8 +225,7 @@ int nbt_grid_post(const double* tt, const double* ttv, const int64_t* tt_offsets
 
 /* Device time [ms] of the stages of this thread's last nbt_run / nbt_analyze issued with
  * NBT_F_TIMING, from CUDA events on the launch stream: ms4 = {front end (k_integrate or
- * k_scan_series), k_fit, k_ls_oc, RV stages}.  Synchronises on the last event.  For a split launch the
- * front-end time runs until both integrations are done; fit / ls_oc are the bulk's. */
+ * k_scan_series), k_fit, k_ls_oc, RV stages}.  Synchronises on the last event. */
 int nbt_timing(double* ms4);
 
 /* Diagnostic: measured FP64 DFMA throughput of `device` (8 independent chains per thread,

@@ -61,7 +61,7 @@ class nbt_config(C.Structure):
         ("ls_samples_per_peak", C.c_int32),
         ("tt_cap_max", C.c_int32),
         ("lanes_systems", C.c_int32),
-        ("split_systems", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -129,7 +129,6 @@ def load():
     lib.nbt_plan_order.argtypes = [C.POINTER(nbt_config), _dp, _ip, _ip]
     lib.nbt_plan_ls.argtypes = [C.POINTER(nbt_config), _lp, _lp]
     lib.nbt_plan_lanes.argtypes = [C.POINTER(nbt_config), _ip, _ip]
-    lib.nbt_plan_split.argtypes = [C.POINTER(nbt_config), _ip, _ip]
     lib.nbt_plan_substeps.argtypes = [C.POINTER(nbt_config), _dp, _ip]
     lib.nbt_count_steps.restype = C.c_int64
     lib.nbt_count_steps.argtypes = [C.POINTER(nbt_config), _ip]

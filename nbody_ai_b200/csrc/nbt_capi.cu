@@ -148,18 +148,14 @@ struct nbt_fit_args {
     const int32_t* n_tt;
     double* ttv; double* period; double* t0; double* ttv_max;
     int32_t* status;
-    const int32_t* order;        // launch order (or NULL); the kernel covers slots [first, first + count)
-    int32_t first, count;
     int32_t B, Np, flags;
 };
 
 __global__ void __launch_bounds__(128) k_fit(const nbt_fit_args F) {
-    const int wl = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (wl >= F.count * F.Np) return;
-    const int slot = F.first + wl / F.Np, j = wl % F.Np;
-    const int sys = F.order ? F.order[slot] : slot;
-    const int w = sys * F.Np + j;
+    if (w >= F.B * F.Np) return;
+    const int sys = w / F.Np, j = w % F.Np;
     const double Pj = F.params[((size_t)sys * (F.Np + 1) + j + 1) * NBT_NPAR + NBT_P_P];
     if ((F.flags & NBT_F_PLANET1_ONLY) && j > 0) {
         if (lane == 0) { F.period[w] = Pj; F.t0[w] = 0.0; F.ttv_max[w] = 0.0; }
@@ -282,18 +278,15 @@ struct nbt_lsoc_args {
     const int64_t* tt_offsets; const int64_t* ls_offsets;
     const double* ttv; const int32_t* n_tt;
     double* power; int32_t* nfreq;
-    const int32_t* order;        // launch order (or NULL); the kernel covers slots [first, first + count)
-    int32_t first, count;
     int32_t B, Np, flags, spp;
     double fmin, fmax;
 };
 
 __global__ void __launch_bounds__(128) k_ls_oc(const nbt_lsoc_args L) {
-    const int wl = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (wl >= L.count * L.Np) return;
-    const int slot = L.first + wl / L.Np, j = wl % L.Np;
-    const int w = (L.order ? L.order[slot] : slot) * L.Np + j;
+    if (w >= L.B * L.Np) return;
+    const int j = w % L.Np;
     const int64_t off = L.tt_offsets[w];
     const int cap = (int)(L.tt_offsets[w + 1] - off);
     const int n = min(L.n_tt[w], cap);
@@ -891,8 +884,7 @@ static void ensure_pool(int dev) {
 // stream around each stage of the last nbt_run of this thread; read back with nbt_timing().
 struct TimingState {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_side = nullptr;   // end of the long systems' integration on the side stream (split launches)
-    bool have = false, split = false; int device = -1;
+    bool have = false; int device = -1;
 };
 static thread_local TimingState g_timing;
 
@@ -919,16 +911,7 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
     if (B == 0) return cudaSuccess;
     cudaError_t e;
     const bool tim = (cfg->flags & NBT_F_TIMING) != 0;
-    // Split launch for heterogeneous batches: the first `ns` launch-order slots (the long systems,
-    // nbt_plan_split) are integrated, fitted and analysed on a side stream of their own.  A launch ends
-    // when its longest systems end; with one launch the GPU idles through that tail and only then runs
-    // k_fit / k_ls_oc for everybody.  Split, the bulk's fit and periodograms run inside the tail.
-    int ns = (scan_series == nullptr && cfg->lanes_systems <= 0) ? cfg->split_systems : 0;
-    if (ns < 0 || ns >= B) ns = 0;
-    const bool split = ns > 0;
-    cudaStream_t side_st = nullptr;
-    cudaEvent_t split_join = nullptr;
-    if (tim) { g_timing.have = true; g_timing.device = cfg->device; g_timing.split = split; }
+    if (tim) { g_timing.have = true; g_timing.device = cfg->device; }
     timing_mark(0, tim, st);
     if (scan_series == nullptr) {
         nbt_run_args A;
@@ -959,23 +942,6 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
             if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
             cudaEventDestroy(fork); cudaEventDestroy(join);   // destruction is deferred until the events complete
             if (e != cudaSuccess) return e;
-        } else if (split) {
-            SideStream* side = nullptr;
-            if ((e = get_side(cfg->device, &side)) != cudaSuccess) return e;
-            side_st = side->st;
-            cudaEvent_t fork = nullptr;
-            if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-            if ((e = cudaEventCreateWithFlags(&split_join, cudaEventDisableTiming)) != cudaSuccess) { cudaEventDestroy(fork); return e; }
-            e = cudaEventRecord(fork, st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(side_st, fork, 0);
-            if (e == cudaSuccess) e = launch_integrate_np(Np, A, 0, ns, false, side_st);      // long systems first
-            if (e == cudaSuccess && tim) {
-                if (!g_timing.ev_side) cudaEventCreate(&g_timing.ev_side);
-                e = cudaEventRecord(g_timing.ev_side, side_st);
-            }
-            if (e == cudaSuccess) e = launch_integrate_np(Np, A, ns, B - ns, false, st);
-            cudaEventDestroy(fork);
-            if (e != cudaSuccess) { cudaEventDestroy(split_join); return e; }
         } else {
             e = launch_integrate_np(Np, A, 0, B, nl == B, st);
             if (e != cudaSuccess) return e;
@@ -996,44 +962,27 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
 
-    // ephemeris fit + O-C periodogram of launch-order slots [first, first + count) on stream q
-    auto post = [&](int first, int count, cudaStream_t q, bool marks) -> cudaError_t {
-        if (count <= 0) return cudaSuccess;
-        const long long nw = (long long)count * Np;
-        const int grid = (int)((nw * 32 + 127) / 128);
-        nbt_fit_args F;
-        F.params = in->params; F.tt_offsets = in->tt_offsets; F.tt = out->tt; F.n_tt = out->n_tt;
-        F.ttv = out->ttv; F.period = out->period; F.t0 = out->t0; F.ttv_max = out->ttv_max; F.status = out->status;
-        F.order = (scan_series == nullptr) ? in->order : nullptr; F.first = first; F.count = count;
-        F.B = B; F.Np = Np; F.flags = cfg->flags;
-        k_fit<<<grid, 128, 0, q>>>(F);
-        cudaError_t ee = cudaGetLastError();
-        if (ee != cudaSuccess) return ee;
-        if (marks) {
-            timing_mark(2, tim, q);
-            // everything but the periodograms and RV reductions is final here: the host path starts
-            // copying those products back on a second stream while k_ls_oc runs
-            if (after_fit && !split && (ee = cudaEventRecord(after_fit, q)) != cudaSuccess) return ee;
-        }
-        if ((cfg->flags & NBT_F_LS_OC) && out->ls_oc_power && in->ls_offsets) {
-            nbt_lsoc_args L;
-            L.tt_offsets = in->tt_offsets; L.ls_offsets = in->ls_offsets; L.ttv = out->ttv; L.n_tt = out->n_tt;
-            L.power = out->ls_oc_power; L.nfreq = out->ls_oc_nfreq;
-            L.order = F.order; L.first = first; L.count = count; L.B = B; L.Np = Np; L.flags = cfg->flags;
-            L.spp = cfg->ls_samples_per_peak; L.fmin = cfg->ls_oc_minfreq; L.fmax = cfg->ls_oc_maxfreq;
-            k_ls_oc<<<grid, 128, 0, q>>>(L);
-            if ((ee = cudaGetLastError()) != cudaSuccess) return ee;
-        }
-        return cudaSuccess;
-    };
     timing_mark(1, tim, st);
-    if ((e = post(split ? ns : 0, split ? B - ns : B, st, true)) != cudaSuccess) return e;
-    if (split) {   // the long systems' own fit + periodogram follow their integration on the side stream
-        if ((e = post(0, ns, side_st, false)) != cudaSuccess) return e;
-        if ((e = cudaEventRecord(split_join, side_st)) != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(st, split_join, 0)) != cudaSuccess) return e;
-        cudaEventDestroy(split_join);   // deferred until the event completes
-        if (after_fit && (e = cudaEventRecord(after_fit, st)) != cudaSuccess) return e;
+    const long long nw = (long long)B * Np;
+    const int fit_grid = (int)((nw * 32 + 127) / 128);
+    nbt_fit_args F;
+    F.params = in->params; F.tt_offsets = in->tt_offsets; F.tt = out->tt; F.n_tt = out->n_tt;
+    F.ttv = out->ttv; F.period = out->period; F.t0 = out->t0; F.ttv_max = out->ttv_max; F.status = out->status;
+    F.B = B; F.Np = Np; F.flags = cfg->flags;
+    k_fit<<<fit_grid, 128, 0, st>>>(F);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    timing_mark(2, tim, st);
+    // everything but the periodograms and RV reductions is final here: the host path starts copying
+    // those products back on a second stream while k_ls_oc runs
+    if (after_fit && (e = cudaEventRecord(after_fit, st)) != cudaSuccess) return e;
+
+    if ((cfg->flags & NBT_F_LS_OC) && out->ls_oc_power && in->ls_offsets) {
+        nbt_lsoc_args L;
+        L.tt_offsets = in->tt_offsets; L.ls_offsets = in->ls_offsets; L.ttv = out->ttv; L.n_tt = out->n_tt;
+        L.power = out->ls_oc_power; L.nfreq = out->ls_oc_nfreq; L.B = B; L.Np = Np; L.flags = cfg->flags;
+        L.spp = cfg->ls_samples_per_peak; L.fmin = cfg->ls_oc_minfreq; L.fmax = cfg->ls_oc_maxfreq;
+        k_ls_oc<<<fit_grid, 128, 0, st>>>(L);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     timing_mark(3, tim, st);
     if ((cfg->flags & NBT_F_RV) && out->rv && rv_sm_ws && (out->rv_max || ((cfg->flags & NBT_F_LS_RV) && out->ls_rv_power))) {
@@ -1143,24 +1092,6 @@ int nbt_plan_lanes(const nbt_config* cfg, const int32_t* substeps, const int32_t
     if (Np >= 5) return B;
     if (Np >= 3 && B <= 4096) return B;
     return 0;
-}
-
-/* Number of leading launch-order slots that form the "long systems" class of a split launch
- * (nbt_config.split_systems): substeps >= 2 x the median, provided the batch fills the GPU
- * (B >= 148 x 256) and the class is a small minority (<= 15 %); otherwise 0 = one launch.
- * Needs `order` sorted by decreasing substeps (nbt_plan_order). */
-int nbt_plan_split(const nbt_config* cfg, const int32_t* substeps, const int32_t* order) {
-    int rc = check_cfg(cfg);
-    if (rc) return rc;
-    const int B = cfg->n_systems;
-    if (!substeps || cfg->substeps > 0 || B < 148 * 256) return 0;
-    std::vector<int32_t> ks(substeps, substeps + B);
-    std::nth_element(ks.begin(), ks.begin() + B / 2, ks.end());
-    const int kmed = ks[B / 2];
-    int n = 0;
-    while (n < B && substeps[order ? order[n] : n] >= 2 * kmed) n++;
-    if (n > (int)(0.15 * B)) return 0;
-    return n;
 }
 
 int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets) {
@@ -1571,13 +1502,6 @@ int nbt_timing(double* ms4) {
         if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_timing.ev[i], g_timing.ev[i + 1]);
         if (e != cudaSuccess) { cudaGetLastError(); return nbt_fail((int)e, "nbt_timing: %s", cudaGetErrorString(e)); }
         ms4[i] = (double)ms;
-    }
-    if (g_timing.split && g_timing.ev_side) { // front end = until BOTH integrations are done
-        float ms = 0.f;
-        cudaError_t e = cudaEventSynchronize(g_timing.ev_side);
-        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_timing.ev[0], g_timing.ev_side);
-        if (e != cudaSuccess) { cudaGetLastError(); return nbt_fail((int)e, "nbt_timing: %s", cudaGetErrorString(e)); }
-        if ((double)ms > ms4[0]) ms4[0] = (double)ms;
     }
     return 0;
 }

@@ -34,7 +34,7 @@ class Plan:
     """Configuration + CSR layout of one nbt_run call (host planning through libnbt's helpers)."""
 
     def __init__(self, params, n_days, n_outputs, substeps=None, scheme=SCHEME_M64,
-                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True, lanes=None, split=None):
+                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True, lanes=None):
         lib = _abi.load()
         self.params = _as_params(params)
         B, N, _ = self.params.shape
@@ -69,14 +69,6 @@ class Plan:
             if lanes < 0:
                 _abi.check(lanes, lib)
         self.cfg.lanes_systems = int(min(max(int(lanes), 0), B))
-        # long-systems class of a heterogeneous batch (split launch), see nbt_plan_split
-        if split is None:
-            split = 0
-            if self.cfg.lanes_systems == 0 and self.order is not None:
-                split = lib.nbt_plan_split(C.byref(self.cfg), _abi.ptr(self.substeps, C.c_int32), _abi.ptr(self.order, C.c_int32))
-                if split < 0:
-                    _abi.check(split, lib)
-        self.cfg.split_systems = int(split)
         # CSR capacities of the transit products
         self.tt_offsets = np.zeros(B * self.Np + 1, dtype=np.int64)
         cap = lib.nbt_plan_tt(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.tt_offsets, C.c_int64))

@@ -18,10 +18,8 @@ def timed(params, nd, no, flags, reps=2, **kw):
     env = os.environ.get("NBT_PROBE_LANES")          # all | none | <int>; default: planner's choice
     if env:
         kw["lanes"] = len(params) if env == "all" else (0 if env == "none" else int(env))
-    if os.environ.get("NBT_PROBE_SPLIT"):
-        kw["split"] = int(os.environ["NBT_PROBE_SPLIT"])
     plan = engine.Plan(params, nd, no, flags=flags, **kw)
-    print("  lanes=%d split=%d" % (plan.cfg.lanes_systems, plan.cfg.split_systems), end="")
+    print("  lanes=%d" % plan.cfg.lanes_systems, end="")
     d = engine.DeviceBuffers(plan)
     engine.run_device(plan, d)
     torch.cuda.synchronize()
