@@ -515,3 +515,31 @@ def test_single_planet_two_body(gpu_lib):
         assert np.abs(got.ttv_of(b, 0)).max() * 1440 < 0.1           # only the grid-linear interpolation error remains
         assert abs(got.period[b] / par[b, 1, 1] - 1) < 1e-6
         assert abs(got.mean_e[b] - par[b, 1, 2]) < 1e-9
+
+
+def test_inclined_three_dimensional_systems(gpu_lib):
+    """Mutually inclined 3-planet systems (inc 70-110 deg, random nodes / pericentres / anomalies) on both
+    integrator kernels against the oracle, full series included."""
+    rng = np.random.default_rng(21)
+    B = 40
+    par = np.zeros((B, 4, 7))
+    par[:, 0, 0] = rng.uniform(0.8, 1.2, B)
+    for j, per in enumerate((4.1, 9.7, 23.0)):
+        par[:, j + 1, 0] = rng.uniform(3e-6, 6e-4, B)
+        par[:, j + 1, 1] = per * rng.uniform(0.95, 1.05, B)
+        par[:, j + 1, 2] = rng.uniform(0.0, 0.08, B)
+        par[:, j + 1, 3] = np.radians(rng.uniform(70, 110, B))
+        par[:, j + 1, 4] = rng.uniform(0, 2 * np.pi, B)
+        par[:, j + 1, 5] = rng.uniform(0, 2 * np.pi, B)
+        par[:, j + 1, 6] = rng.uniform(0, 2 * np.pi, B)
+    for lanes in (0, B):
+        plan = engine.Plan(par, 150.0, 3601, flags=FULL | _abi.F_SERIES, lanes=lanes)
+        got, want = engine.run(plan), oracle_run(plan)
+        w = compare_products(got, want, plan)
+        assert w['inc'] < 1e-9 and np.abs(got.mean_omega - want.mean_omega).max() < 1e-6
+        d = np.abs(got.series - want.series)
+        for j in range(3):
+            c = 3 + 10 * j
+            assert d[:, :, c:c + 3].max() < 1e-9 and d[:, :, c + 6].max() < 1e-9          # x, y, z, inc
+            dO = np.abs(np.angle(np.exp(1j * (got.series[:, :, c + 7] - want.series[:, :, c + 7]))))
+            assert dO.max() < 1e-7                                                          # Omega

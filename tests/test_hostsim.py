@@ -129,3 +129,27 @@ def test_scheme_coefficients(built):
         assert abs(sum(bi * ci ** j for bi, ci in zip(b, c)) - 1 / ((j + 1) * 2 ** j)) < 1e-15
     e2 = sum(b[i] * b[j] * (tau[j] - tau[i]) for i in range(5) for j in range(i + 1, 5))
     assert abs(e2 - 1 / 6) < 1e-15
+
+
+def test_inclined_three_dimensional_systems(hostsim):
+    """Mutually inclined orbits with arbitrary nodes, arguments of pericentre and starting anomalies:
+    exercises the y/z components, the node-dependent element branches and the general acos path of the
+    inclination (|cos i| > 0.03)."""
+    rng = np.random.default_rng(21)
+    B = 10
+    par = np.zeros((B, 4, 7))
+    par[:, 0, 0] = rng.uniform(0.8, 1.2, B)
+    for j, per in enumerate((4.1, 9.7, 23.0)):
+        par[:, j + 1, 0] = rng.uniform(3e-6, 6e-4, B)
+        par[:, j + 1, 1] = per * rng.uniform(0.95, 1.05, B)
+        par[:, j + 1, 2] = rng.uniform(0.0, 0.08, B)
+        par[:, j + 1, 3] = np.radians(rng.uniform(70, 110, B))
+        par[:, j + 1, 4] = rng.uniform(0, 2 * np.pi, B)
+        par[:, j + 1, 5] = rng.uniform(0, 2 * np.pi, B)
+        par[:, j + 1, 6] = rng.uniform(0, 2 * np.pi, B)
+    plan = engine.Plan(par, 150.0, 3601, flags=_abi.F_MEANS | _abi.F_MEAN_OMEGA)
+    got, want = host_run(hostsim, plan), oracle_run(plan)
+    w = compare_products(got, want, plan)
+    assert w['inc'] < 1e-9
+    assert np.abs(got.mean_omega - want.mean_omega).max() < 1e-6
+    assert np.abs(np.degrees(got.mean_inc) - 90).max() > 5          # really inclined
