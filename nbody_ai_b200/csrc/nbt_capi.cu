@@ -114,12 +114,12 @@ __device__ double warp_maxavg(const double* x, int n, int lane) {
 #endif
 
 // launch-order slots [first, first + count) of the batch, one system per thread
-template <int NP, bool SERIES>
+template <int NP, bool SERIES, bool LAT>
 __global__ void __launch_bounds__(NBT_BLOCK, NBT_MINBLOCKS) k_integrate(const nbt_run_args A, int first, int count) {
     const int g = blockIdx.x * NBT_BLOCK + threadIdx.x;
     if (g >= count) return;
     const int sys = (A.order != nullptr) ? A.order[first + g] : first + g;
-    nbt_simulate_system<NP, SERIES>(A, sys);
+    nbt_simulate_system<NP, SERIES, LAT>(A, sys);
 }
 
 // launch-order slots [first, first + count), one planet per lane (32 / NP systems per warp)
@@ -828,8 +828,12 @@ static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count,
         else k_integrate_lanes<NP, false><<<grid, NBT_LBLOCK, 0, st>>>(A, first, count);
     } else {
         const int grid = (count + NBT_BLOCK - 1) / NBT_BLOCK;
-        if (series) k_integrate<NP, true><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
-        else k_integrate<NP, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
+        // Np <= 2 has a latency variant (branch-free drifts, more registers): it wins unless the launch is
+        // many waves of resident threads deep (148 SMs x 6 CTAs x 64 threads = 56 832 per wave)
+        const bool lat = NP <= 2 && count < 4 * 56832;
+        if (series) k_integrate<NP, true, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
+        else if (lat) k_integrate<NP, false, (NP <= 2)><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
+        else k_integrate<NP, false, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
     }
     return cudaGetLastError();
 }

@@ -257,6 +257,62 @@ NBT_HD void nbt_kepler_drift(double mu, double h, double& x, double& y, double& 
     r0io = r; ir0io = ir;
 }
 
+// Branch-free form of the one-shot solve: the same arithmetic as the fast path of nbt_kepler_drift,
+// committed through selects only when the convergence test holds; returns that test.  With no branch
+// inside, the drifts of all planets of a stage form ONE basic block, so the compiler interleaves
+// their dependency chains end to end (a lone warp is latency-bound: profiles/README.md); the caller
+// re-runs the rare failures through nbt_kepler_drift afterwards.
+NBT_HD bool nbt_kepler_drift_fast(double mu, double h, double& x, double& y, double& z, double& vx,
+                                  double& vy, double& vz, double& r0io, double& ir0io) {
+    const double ir0 = ir0io, r0 = r0io;
+    const double s = h * ir0, s2 = s * s;
+    const double kA = 0.5 * ir0, kB = (1.0 / 6.0) * ir0, kB5 = (5.0 / 6.0) * ir0, kC = (-1.0 / 24.0) * ir0;
+    const double mi0 = -mu * ir0;
+    const double v02 = fma(vx, vx, fma(vy, vy, vz * vz));
+    const double eta = fma(x, vx, fma(y, vy, z * vz));
+    const double beta = fma(2.0 * mu, ir0, -v02);
+    const double zeta = fma(-beta, r0, mu);
+    const double be = beta * eta;
+    const double A = eta * kA, AA = A * A;
+    const double Bc = zeta * kB, B5 = zeta * kB5, Cc = be * kC;
+    const double k3 = fma(2.0, AA, -Bc);
+    const double k4 = fma(A, fma(-5.0, AA, B5), -Cc);
+    const double X = fma(s2, fma(s, fma(s, k4, k3), -A), s);
+    const double X2 = X * X, X3 = X2 * X;
+    const double zz = beta * X2;
+    const double base = fma(r0, X, -h);
+    double c2, c3;
+    nbt_stumpff(zz, c2, c3);
+    const double G0 = fma(-zz, c2, 1.0);
+    const double G1 = X * fma(-zz, c3, 1.0), G2 = X2 * c2, G3 = X3 * c3;
+    const double F = fma(zeta, G3, fma(eta, G2, base));
+    const double r1 = fma(eta, G1, fma(zeta, G2, r0));
+    const double Fpp = fma(eta, G0, zeta * G1);
+    const double Fppp = fma(zeta, G0, -be * G1);
+    const double ir1 = nbt_rcp(r1);
+    const double u = -F * ir1;
+    const double a2 = (0.5 * ir1) * Fpp, a3 = ((1.0 / 6.0) * ir1) * Fppp;
+    const double d = u * fma(u, fma(u, fma(2.0 * a2, a2, -a3), -a2), 1.0);
+    const bool ok = fabs(d) <= 2e-4 * fabs(X) && zz < 0.5 && zz > -0.5;
+    const double nb6 = (-1.0 / 6.0) * beta;
+    const double hG0 = 0.5 * G0, hG1 = 0.5 * G1;
+    const double nG3 = fma(d, fma(d, fma(d, (1.0 / 6.0) * G0, hG1), G2), G3);
+    const double nG2 = fma(d, fma(d, fma(d, nb6 * G1, hG0), G1), G2);
+    const double nG1 = fma(d, fma(d, fma(d, nb6 * G0, -beta * hG1), G0), G1);
+    const double r = fma(d, fma(d, fma(d, nb6 * Fpp, 0.5 * Fppp), Fpp), r1);
+    const double ir = nbt_rcp_from(r, ir1);
+    const double fm1 = mi0 * nG2;
+    const double g = fma(-mu, nG3, h);
+    const double fd = (mi0 * nG1) * ir;
+    const double gdm1 = (-mu * nG2) * ir;
+    const double nx = fma(fm1, x, fma(g, vx, x)), ny = fma(fm1, y, fma(g, vy, y)), nz = fma(fm1, z, fma(g, vz, z));
+    const double nvx = fma(fd, x, fma(gdm1, vx, vx)), nvy = fma(fd, y, fma(gdm1, vy, vy)), nvz = fma(fd, z, fma(gdm1, vz, vz));
+    x = ok ? nx : x; y = ok ? ny : y; z = ok ? nz : z;
+    vx = ok ? nvx : vx; vy = ok ? nvy : vy; vz = ok ? nvz : vz;
+    r0io = ok ? r : r0; ir0io = ok ? ir : ir0;
+    return ok;
+}
+
 // |r| and 1/|r| from the coordinates (start of a run and at every output sample)
 NBT_HD void nbt_radius(double x, double y, double z, double& r, double& ir) {
     const double r2 = fma(x, x, fma(y, y, z * z));
@@ -413,7 +469,10 @@ NBT_HD void nbt_setup(const double* par, nbt_state<NP>& s, nbt_consts<NP>& c) {
 
 // one composition step of size dt; (ax,ay,az) holds the acceleration at the current positions
 // on entry and on exit (shared between the last kick of a step and the first of the next)
-template <int NP>
+// LAT: the latency variant (Np <= 2) — branch-free drifts fused into one basic block; ~20 % faster for a
+// lone warp (small batches, the long systems of a heterogeneous one) at ~40 more registers, i.e. 4
+// instead of 6 resident CTAs per SM and ~6 % less steady-state throughput (profiles/README.md)
+template <int NP, bool LAT>
 NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme& sc, double dt,
                      double (&ax)[NP], double (&ay)[NP], double (&az)[NP], int& status) {
     {
@@ -425,9 +484,23 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
     }
     for (int st = 0; st < sc.S; st++) {
         const double h = sc.a[st] * dt;
+        if (LAT && NP <= 2) {   // branch-free drifts in one basic block, rare failures redone afterwards
+            bool ok[NP], all_ok = true;
 #pragma unroll
-        for (int i = 0; i < NP; i++)
-            nbt_kepler_drift<(NP <= 2)>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
+            for (int i = 0; i < NP; i++) {
+                ok[i] = nbt_kepler_drift_fast(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i]);
+                all_ok = all_ok && ok[i];
+            }
+            if (!all_ok) {
+#pragma unroll
+                for (int i = 0; i < NP; i++)
+                    if (!ok[i]) nbt_kepler_drift<true>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NP; i++)
+                nbt_kepler_drift<(NP <= 2)>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
+        }
         nbt_accel<NP>(s, c, ax, ay, az);
         const double kb = sc.b[st + 1] * dt;
 #pragma unroll
@@ -564,7 +637,7 @@ struct nbt_run_args {
 
 // SERIES = the NBT_F_SERIES variant (full element set per sample, generate() compatibility); it is a
 // separate instantiation so that its large code stays out of the instruction caches of the batched path
-template <int NP, bool SERIES>
+template <int NP, bool SERIES, bool LAT = false>
 NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
     nbt_state<NP> s;
     nbt_consts<NP> c;
@@ -596,7 +669,7 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
 
     for (int o = 0; o < NO; o++) {
         if (o > 0) {
-            for (int sub = 0; sub < k; sub++) nbt_step<NP>(s, c, A.scheme, dt, ax, ay, az, status);
+            for (int sub = 0; sub < k; sub++) nbt_step<NP, LAT>(s, c, A.scheme, dt, ax, ay, az, status);
         }
         const double t = (o == NO - 1) ? A.n_days : (double)o * step;
         if (o > 0) { // refresh the carried radii from the coordinates (bounds their round-off drift)

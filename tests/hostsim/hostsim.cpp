@@ -11,8 +11,10 @@ template <int NP>
 static void run_np(const nbt_run_args& A) {
     const bool series = (A.flags & NBT_F_SERIES) != 0 && A.series != nullptr;
     for (int g = 0; g < A.B; g++) {
-        if (series) nbt_simulate_system<NP, true>(A, A.order ? A.order[g] : g);
-        else nbt_simulate_system<NP, false>(A, A.order ? A.order[g] : g);
+        // both drift variants are exercised: even launch slots run the latency (branch-free) one
+        if (series) nbt_simulate_system<NP, true, false>(A, A.order ? A.order[g] : g);
+        else if (g % 2 == 0) nbt_simulate_system<NP, false, true>(A, A.order ? A.order[g] : g);
+        else nbt_simulate_system<NP, false, false>(A, A.order ? A.order[g] : g);
     }
 }
 

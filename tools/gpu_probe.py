@@ -103,6 +103,18 @@ def main():
             timed_big(par, meta["ndays"], meta["noutputs"], _abi.F_PLANET1_ONLY)
         elif c == "c1rv":      # full analyze() extras: RV series, its maxavg and its periodogram (8759 x 1816)
             timed(workloads.c1_params(4096), 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC | _abi.F_RV | _abi.F_LS_RV, reps=1, lanes=0)
+        elif c in ("c2clean", "c2cleancap1", "c2dirty"):
+            # the C2 batch without / only its Hill-unstable systems (mutual separation < 4 R_Hill)
+            par = workloads.c2_params(10000, 6, 0)
+            a1, a2 = np.cbrt(par[:, 1, 1] ** 2), np.cbrt(par[:, 2, 1] ** 2)
+            rh = np.cbrt((par[:, 1, 0] + par[:, 2, 0]) / (3 * par[:, 0, 0])) * 0.5 * (a1 + a2)
+            clean = (a2 - a1) / rh >= 4.0
+            sel = par[~clean] if c == "c2dirty" else par[clean]
+            fl = _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC
+            if c == "c2cleancap1":
+                timed(sel, 365.0, 8760, fl, reps=1, substeps=1)
+            else:
+                timed(sel, 365.0, 8760, fl, reps=1)
         elif c == "c1big":
             timed(workloads.c1_params(227328), 30.0, 721, 0, substeps=1)
         elif c == "c1bigomega":
