@@ -511,13 +511,40 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
 }
 
 // ---------------------------------------------------------------------------------------------
+// acos without branches.  libdevice's acos takes different code paths for |x| < 0.5 and |x| >= 0.5;
+// arguments of pericentre are uniform on the circle, so the lanes of a warp always split and execute
+// both.  Here both ranges share one evaluation of the classic rational approximation
+//   asin(s) = s + s z p(z)/q(z),  z = s^2,  |s| <= 0.5   (coefficients of the FreeBSD msun e_asin.c)
+// with  z = x^2, s = x                     acos(x) = pi/2 - asin(x)             for |x| <  0.5
+//       z = (1-|x|)/2, s = sqrt(z)         acos(x) = 2 asin(s) | pi - 2 asin(s)  for |x| >= 0.5
+// selected per lane.  Max error vs libm over [-1, 1]: 3e-16 (tests/test_hostsim.py).
+// ---------------------------------------------------------------------------------------------
+NBT_HD double nbt_acos(double x) {
+    const double ax = fabs(x);
+    const bool big = ax >= 0.5;
+    const double zb = 0.5 * (1.0 - ax);
+    const double z = big ? zb : x * x;
+    const double sb = (zb > 0.0) ? zb * nbt_rsqrt(zb) : 0.0;         // sqrt(zb)
+    const double sv = big ? sb : x;
+    const double p = z * fma(z, fma(z, fma(z, fma(z, fma(z, 3.47933107596021167570e-05, 7.91534994289814532176e-04),
+                     -4.00555345006794114027e-02), 2.01212532134862925881e-01), -3.25565818622400915405e-01),
+                     1.66666666666666657415e-01);
+    const double q = fma(z, fma(z, fma(z, fma(z, 7.70381505559019352791e-02, -6.88283971605453293030e-01),
+                     2.02094576023350569471e+00), -2.40339491173441421878e+00), 1.0);
+    const double as = fma(sv, p * nbt_rcp(q), sv);                     // asin(sv)
+    const double small = 0.5 * NBT_PI - as;
+    const double large = (x > 0.0) ? 2.0 * as : NBT_PI - 2.0 * as;
+    return big ? large : small;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Jacobi osculating elements with REBOUND's conventions [3P] (primary = COM of lower-index
 // bodies, mu = G M_i): what ps[j].P/a/e/inc/Omega/omega/M return at nbody/simulation.py:150.
 // ---------------------------------------------------------------------------------------------
 NBT_HD double nbt_acos2(double num, double den, double disamb) {
     const double cth = num * nbt_rcp(den);
     double val;
-    if (cth > -1.0 && cth < 1.0) val = acos(cth);
+    if (cth > -1.0 && cth < 1.0) val = nbt_acos(cth);
     else val = (cth <= -1.0) ? NBT_PI : 0.0;
     return (disamb < 0.0) ? -val : val;
 }
@@ -553,7 +580,7 @@ NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, doub
             const double p = fma(c2, fma(c2, fma(c2, fma(c2, 35.0 / 1152.0, 15.0 / 336.0), 3.0 / 40.0), 1.0 / 6.0), 1.0);
             o.inc = fma(-ci, p, 0.5 * NBT_PI);
         } else {
-            o.inc = (ci > -1.0 && ci < 1.0) ? acos(ci) : ((ci <= -1.0) ? NBT_PI : 0.0);
+            o.inc = (ci > -1.0 && ci < 1.0) ? nbt_acos(ci) : ((ci <= -1.0) ? NBT_PI : 0.0);
         }
         if (!(h2 > 0.0)) o.inc = NAN;
     }
@@ -570,7 +597,7 @@ NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, doub
             // cos(omega) = n.e / (|n| |e|): one rsqrt of the product instead of a sqrt and a reciprocal
             const double den2 = n2 * e2;
             const double cth = (den2 > 0.0) ? (nx * ex + ny * ey) * nbt_rsqrt(den2) : 2.0;
-            const double val = (cth > -1.0 && cth < 1.0) ? acos(cth) : ((cth <= -1.0) ? NBT_PI : 0.0);
+            const double val = (cth > -1.0 && cth < 1.0) ? nbt_acos(cth) : ((cth <= -1.0) ? NBT_PI : 0.0);
             o.omega = (ez < 0.0) ? -val : val;
         }
         if (o.e <= 1e-8) o.omega = 0.0;

@@ -77,3 +77,8 @@ extern "C" int hostsim_kepler(double mu, double h, double* state6) {
     nbt_kepler_drift(mu, h, state6[0], state6[1], state6[2], state6[3], state6[4], state6[5], r, ir, status);
     return status;
 }
+
+// nbt_acos over an array, for the accuracy test
+extern "C" void hostsim_acos(const double* x, double* y, int n) {
+    for (int i = 0; i < n; i++) y[i] = nbt_acos(x[i]);
+}

@@ -153,3 +153,11 @@ def test_inclined_three_dimensional_systems(hostsim):
     assert w['inc'] < 1e-9
     assert np.abs(got.mean_omega - want.mean_omega).max() < 1e-6
     assert np.abs(np.degrees(got.mean_inc) - 90).max() > 5          # really inclined
+
+
+def test_branch_free_acos(hostsim):
+    """nbt_acos (one code path for both ranges) against libm over [-1, 1], including the ends."""
+    x = np.concatenate([np.linspace(-1, 1, 200001), [-1.0, -0.5, 0.5, 1.0, 1 - 1e-15, -1 + 1e-15, 0.0, 1e-300]])
+    y = np.zeros_like(x)
+    hostsim.hostsim_acos(x.ctypes.data_as(C.POINTER(C.c_double)), y.ctypes.data_as(C.POINTER(C.c_double)), len(x))
+    assert np.abs(y - np.arccos(x)).max() < 1e-15

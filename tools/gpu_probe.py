@@ -115,6 +115,9 @@ def main():
                 timed(sel, 365.0, 8760, fl, reps=1, substeps=1)
             else:
                 timed(sel, 365.0, 8760, fl, reps=1)
+        elif c in ("c2full_nomeans", "c2full_means"):   # the bench batch without / with part of the per-sample work
+            fl = {"c2full_nomeans": _abi.F_LS_OC, "c2full_means": _abi.F_MEANS | _abi.F_LS_OC}[c]
+            timed(workloads.c2_params(10000, 6, 0), 365.0, 8760, fl, reps=1)
         elif c == "c1big":
             timed(workloads.c1_params(227328), 30.0, 721, 0, substeps=1)
         elif c == "c1bigomega":
