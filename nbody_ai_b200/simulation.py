@@ -271,3 +271,11 @@ def generate_batch(systems, Ndays, Noutputs, integrator=None, full=True, rv=Fals
 def analyze_batch(result):
     """List of ttv_data dicts (analyze() layout) for every system of a BatchResult."""
     return [result.ttv_data(b) for b in range(len(result))]
+
+
+def report(data, savefile=None):
+    """simulation.py:235-334 is a matplotlib figure and is out of scope here.  `data` keeps every key it
+    reads (:249-299), so the reference's own report() renders the dict returned by analyze() unchanged:
+        from nbody.simulation import report; report(nbody_ai_b200.simulation.analyze(sim_data))"""
+    raise NotImplementedError("report() is plotting (out of scope); pass this ttv_data dict to the reference's "
+                              "nbody.simulation.report — the layout is identical")
