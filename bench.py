@@ -317,6 +317,14 @@ def emit(line):
         print(text, flush=True)
 
 
+def ensure_built():
+    """The in-tree libraries normally travel with the repo snapshot; compile them if they did not."""
+    from nbody_ai_b200 import _abi
+    if not os.path.exists(_abi.lib_path()):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def main():
     global OUT
     ap = argparse.ArgumentParser()
@@ -332,6 +340,7 @@ def main():
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     with StdoutToStderr() as OUT:
+        ensure_built()
         if args.impl == "reference":
             run_reference(args, rank, world)
         else:
