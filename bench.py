@@ -318,11 +318,19 @@ def emit(line):
 
 
 def ensure_built():
-    """The in-tree libraries normally travel with the repo snapshot; compile them if they did not."""
+    """The in-tree libraries normally travel with the repo snapshot; compile them if they did not
+    (local rank 0 builds, the other ranks of a torchrun job wait for the file)."""
     from nbody_ai_b200 import _abi
-    if not os.path.exists(_abi.lib_path()):
+    if os.path.exists(_abi.lib_path()):
+        return
+    if env_int("LOCAL_RANK", 0) == 0:
         import __graft_entry__
         __graft_entry__.build()
+    else:
+        t0 = time.time()
+        while not os.path.exists(_abi.lib_path()) and time.time() - t0 < 600:
+            time.sleep(1.0)
+        time.sleep(2.0)   # let the linker finish writing
 
 
 def main():
