@@ -110,6 +110,19 @@ def cpu_model():
     return "unknown"
 
 
+def hbm_side(traffic_bytes, launch_ms):
+    """The HBM view of the same launch (it is not the binding roof: the kernel is register-resident)."""
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "MEASURED_PEAKS.json"
+    except Exception:
+        peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    if traffic_bytes is None:
+        return None
+    ach = traffic_bytes / (launch_ms * 1e-3) * 1e-9
+    return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src}
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -268,7 +281,8 @@ def run_ours(args, rank, world, local_rank):
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None,
                          "peak_source": "nbt_fp64_peak DFMA-chain kernel measured in this run (nominal 37.2 at 1965 MHz)",
                          "peak_three_register_operands": fp64_peak_3reg,
-                         "flops_per_launch": flops, "launch_ms": integ_launch_ms, "traffic": ncu_traffic(Np, B)},
+                         "flops_per_launch": flops, "launch_ms": integ_launch_ms, "traffic": ncu_traffic(Np, B),
+                         "hbm": hbm_side(ncu_traffic(Np, B), integ_launch_ms)},
             "e2e": {"value": sims_all * args.steps / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": 3 * args.steps,
