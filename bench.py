@@ -37,9 +37,14 @@ WORKLOAD = ("C2: random 2-planet systems (randomize() priors, generate_simulatio
             "365 d @ 1 h, tt + ephemeris + O-C + maxavg + O-C periodogram + element means")
 
 
-def f_step(np_):
-    """Algorithmic FLOPs per system-step (FMA = 2, div/sqrt = 1)."""
-    return 272 * np_ + 12.5 * np_ * (np_ + 1) - 40
+def f_step(np_, stages=3, forces=4, grad_kicks=1):
+    """Algorithmic FLOPs per system-step = one Kepler-drift stage of one system (FMA = 2,
+    div/sqrt = 1): drift 230 Np + kick 6 Np + the force evaluation (Jacobi<->inertial 21 Np, pairs
+    12.5 Np (Np+1) - 25, indirect term 15 (Np-1)).  SURVEY's figure has one force evaluation per stage
+    (272 Np + 12.5 Np (Np+1) - 40); the default SBABC3 scheme has `forces` = 4 evaluations and one
+    displaced-position set-up (6 Np + 7 (Np-1)) per `stages` = 3 drift stages."""
+    force = 21 * np_ + 12.5 * np_ * (np_ + 1) - 25 + 15 * (np_ - 1)
+    return 236 * np_ + (forces * force + grad_kicks * (6 * np_ + 7 * (np_ - 1))) / stages
 
 
 F_OUT = 100  # per planet per output sample (Jacobi a, e, inc + crossing test)
@@ -269,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "systems_per_gpu": B, "draws": args.draws, "omega_variants": args.omegas,
-                       "n_planets": Np, "n_days": N_DAYS, "n_outputs": N_OUTPUTS, "scheme": "m64 (4-stage order (6,4) WH composition)",
+                       "n_planets": Np, "n_days": N_DAYS, "n_outputs": N_OUTPUTS, "scheme": "sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks)",
                        "substeps_hist": np.bincount(plan.substeps).tolist(), "parallelism": "shard-by-system x%d" % world,
                        "l2": "256 MiB device fill between steps, outside the per-step event pairs"},
             "system_steps_per_s": steps_per_s,

@@ -49,7 +49,10 @@ enum { NBT_SCHEME_WH2 = 0,   /* kick-drift-kick leapfrog */
        NBT_SCHEME_Y4 = 1,    /* Yoshida 4th-order triple jump */
        NBT_SCHEME_SABA4 = 2, /* Laskar-Robutel SBAB/SABA-class, 4 stages */
        NBT_SCHEME_M64 = 3,   /* order (6,4) 4-stage composition */
-       NBT_SCHEME_COUNT = 4 };
+       NBT_SCHEME_C4 = 4,    /* 2-stage force-gradient composition, O(eps dt^4 + eps^2 dt^4) */
+       NBT_SCHEME_SBABC3 = 5, /* 3-stage Lobatto composition + force-gradient end kicks, order (6,4):
+                                 the accuracy of M64 with three Kepler drifts per step (the default) */
+       NBT_SCHEME_COUNT = 6 };
 
 /* transit-time mode */
 enum { NBT_TT_GRID_LINEAR = 0, /* reference semantics: sign test + linear interpolation on the

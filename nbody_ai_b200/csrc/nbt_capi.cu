@@ -801,6 +801,8 @@ static int scheme_stages(int id) {
     case NBT_SCHEME_Y4: return 3;
     case NBT_SCHEME_SABA4: return 4;
     case NBT_SCHEME_M64: return 4;
+    case NBT_SCHEME_C4: return 2;
+    case NBT_SCHEME_SBABC3: return 3;
     default: return -1;
     }
 }
@@ -1123,7 +1125,7 @@ int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* subs
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (!params || !substeps) return nbt_fail(-10, "nbt_plan_substeps: NULL argument");
-    static const double R[NBT_SCHEME_COUNT] = {8000.0, 400.0, 800.0, 57.5}; /* P_min / dt_sub */
+    static const double R[NBT_SCHEME_COUNT] = {8000.0, 400.0, 800.0, 57.5, 200.0, 57.5}; /* P_min / dt_sub */
     const int B = cfg->n_systems, N = cfg->n_bodies;
     const double step = cfg->n_days / (double)(cfg->n_outputs - 1);
     for (int b = 0; b < B; b++) {

@@ -27,6 +27,7 @@
 
 #define NBT_PI 3.14159265358979323846264338327950288
 #define NBT_MAX_STAGES 8
+#define NBT_C4_GRAD (1.0 / 24.0)  /* displacement coefficient of the gradient kick of NBT_SCHEME_C4 */
 
 // ---------------------------------------------------------------------------------------------
 // reciprocal / reciprocal square root: MUFU seed (rsqrt.approx.f64 / rcp.approx.f64, ~2^-20) +
@@ -392,18 +393,59 @@ NBT_HD void nbt_accel(const nbt_state<NP>& s, const nbt_consts<NP>& c, double (&
     }
 }
 
-// composition coefficients: K(b[0]) D(a[0]) K(b[1]) ... D(a[S-1]) K(b[S])
+// acceleration of a (possibly force-gradient) kick: a'(q') for gd == 0, else a'(q' + gd a'(q'));
+// gd = g dt^2 is uniform over the launch
+template <int NP>
+NBT_HD void nbt_accel_grad(const nbt_state<NP>& s, const nbt_consts<NP>& c, double gd, double (&ax)[NP],
+                           double (&ay)[NP], double (&az)[NP]) {
+    nbt_accel<NP>(s, c, ax, ay, az);
+    if (gd != 0.0) {
+        nbt_state<NP> t;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            t.x[i] = fma(gd, ax[i], s.x[i]); t.y[i] = fma(gd, ay[i], s.y[i]); t.z[i] = fma(gd, az[i], s.z[i]);
+            if (i >= 1) nbt_radius(t.x[i], t.y[i], t.z[i], t.r[i], t.ir[i]);
+        }
+        nbt_accel<NP>(t, c, ax, ay, az);
+    }
+}
+
+// composition coefficients: K(b[0]) D(a[0]) K(b[1]) ... D(a[S-1]) K(b[S]).
+// g[i] != 0 makes kick i a force-gradient kick (g[0] == g[S]: the two end kicks of consecutive steps
+// share one evaluation, which is why (ax,ay,az) carries the kick acceleration): it is evaluated
+// at the Jacobi positions displaced by g[i] dt^2 a'(q'), which adds g[i] dt^2 (a'.grad) a' — the
+// commutator {B,{A,B}} = sum_i m'_i |a'_i|^2 of the interaction with the kinetic part of the Kepler
+// terms — without second derivatives (error of the displacement trick: O(dt^4 eps^3)).
 struct nbt_scheme {
     int S;
     double a[NBT_MAX_STAGES];
     double b[NBT_MAX_STAGES + 1];
+    double g[NBT_MAX_STAGES + 1];
 };
 
 NBT_HD nbt_scheme nbt_make_scheme(int id) {
     nbt_scheme s;
     for (int i = 0; i < NBT_MAX_STAGES; i++) s.a[i] = 0.0;
-    for (int i = 0; i <= NBT_MAX_STAGES; i++) s.b[i] = 0.0;
+    for (int i = 0; i <= NBT_MAX_STAGES; i++) s.b[i] = s.g[i] = 0.0;
     switch (id) {
+    case NBT_SCHEME_C4: { // Simpson kicks (1/6, 2/3, 1/6) around two half drifts, gradient term in the middle
+        // kick (Chin 1997, algorithm 4A, applied to the Wisdom-Holman splitting): both dt^2 terms cancel,
+        // O(eps dt^4 + eps^2 dt^4) with two Kepler drifts and three force evaluations per step
+        s.S = 2;
+        s.a[0] = 0.5; s.a[1] = 0.5;
+        s.b[0] = 1.0 / 6.0; s.b[1] = 2.0 / 3.0; s.b[2] = 1.0 / 6.0;
+        s.g[1] = NBT_C4_GRAD;
+    } break;
+    case NBT_SCHEME_SBABC3: { // Laskar & Robutel (2001) SBAB_3 = 4-point Lobatto, O(eps dt^6 + eps^2 dt^2), with
+        // their corrector c dt^3 {{A,B},B}, c = (13 - 5 sqrt 5)/288, folded into the end kicks as a
+        // force-gradient term g = c / b[0]: O(eps dt^6 + eps^2 dt^4) with three drifts and four force
+        // evaluations per step (the end kick's pair is shared by consecutive steps)
+        const double s5 = 2.2360679774997896964091737;
+        s.S = 3;
+        s.a[0] = 0.5 * (1.0 - 1.0 / s5); s.a[1] = 1.0 / s5; s.a[2] = s.a[0];
+        s.b[0] = 1.0 / 12.0; s.b[1] = 5.0 / 12.0; s.b[2] = 5.0 / 12.0; s.b[3] = 1.0 / 12.0;
+        s.g[0] = s.g[3] = (13.0 - 5.0 * s5) / 24.0;
+    } break;
     case NBT_SCHEME_Y4: { // Yoshida (1990) triple jump of kick-drift-kick
         const double w1 = 1.351207191959657634047688, w0 = -1.702414383919315268095376;
         s.S = 3;
@@ -501,7 +543,7 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
             for (int i = 0; i < NP; i++)
                 nbt_kepler_drift<(NP <= 2)>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
         }
-        nbt_accel<NP>(s, c, ax, ay, az);
+        nbt_accel_grad<NP>(s, c, sc.g[st + 1] * dt * dt, ax, ay, az);
         const double kb = sc.b[st + 1] * dt;
 #pragma unroll
         for (int i = 0; i < NP; i++) {
@@ -685,7 +727,7 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
     const int W = 3 + 10 * NP;
 
     double ax[NP], ay[NP], az[NP];
-    nbt_accel<NP>(s, c, ax, ay, az);
+    nbt_accel_grad<NP>(s, c, A.scheme.g[0] * dt * dt, ax, ay, az);
 
     double dx_prev[NP], dvx_prev[NP];
     double sum_a[NP], sum_e[NP], sum_i[NP], sum_o[NP];

@@ -82,6 +82,20 @@ __device__ __forceinline__ void nbt_accel_lane(unsigned gmask, int base, int j, 
     ax = jx; ay = jy; az = jz;
 }
 
+// acceleration of a (possibly force-gradient) kick, see nbt_accel_grad
+template <int NP>
+__device__ __forceinline__ void nbt_accel_lane_grad(unsigned gmask, int base, int j, double x, double y, double z,
+                                                    double irj, const double (&mr)[NP], const double (&Gm)[NP + 1],
+                                                    double GMj, double gd, double& ax, double& ay, double& az) {
+    nbt_accel_lane<NP>(gmask, base, j, x, y, z, irj, mr, Gm, GMj, ax, ay, az);
+    if (gd != 0.0) {
+        const double tx = fma(gd, ax, x), ty = fma(gd, ay, y), tz = fma(gd, az, z);
+        double tr, tir;
+        nbt_radius(tx, ty, tz, tr, tir);
+        nbt_accel_lane<NP>(gmask, base, j, tx, ty, tz, tir, mr, Gm, GMj, ax, ay, az);
+    }
+}
+
 // One lane of one system: integrate + sample + detect transits (the lanes form of nbt_simulate_system).
 template <int NP, bool SERIES>
 __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int base, unsigned gmask) {
@@ -137,7 +151,7 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
     double rj, irj;
     nbt_radius(x, y, z, rj, irj);
     double ax, ay, az;
-    nbt_accel_lane<NP>(gmask, base, j, x, y, z, irj, mr, Gm, GMj, ax, ay, az);
+    nbt_accel_lane_grad<NP>(gmask, base, j, x, y, z, irj, mr, Gm, GMj, sc.g[0] * dt * dt, ax, ay, az);
 
     double dx_prev = 0.0, dvx_prev = 0.0, xs_prev = 0.0, t_prev = 0.0;
     double sum_a = 0.0, sum_e = 0.0, sum_i = 0.0, sum_o = 0.0;
@@ -154,7 +168,7 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
                 }
                 for (int st = 0; st < sc.S; st++) {
                     nbt_kepler_drift(GMj, sc.a[st] * dt, x, y, z, vx, vy, vz, rj, irj, status);
-                    nbt_accel_lane<NP>(gmask, base, j, x, y, z, irj, mr, Gm, GMj, ax, ay, az);
+                    nbt_accel_lane_grad<NP>(gmask, base, j, x, y, z, irj, mr, Gm, GMj, sc.g[st + 1] * dt * dt, ax, ay, az);
                     const double kb = sc.b[st + 1] * dt;
                     vx = fma(kb, ax, vx); vy = fma(kb, ay, vy); vz = fma(kb, az, vz);
                 }

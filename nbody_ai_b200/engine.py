@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _abi
 from ._abi import (F_DEVICE_PTRS, F_LS_OC, F_LS_RV, F_MEAN_OMEGA, F_MEANS, F_ORBIT, F_PLANET1_ONLY,
-                   F_RV, F_SERIES, NBT_NPAR, SCHEME_M64, SCHEMES, TT_GRID_LINEAR, TT_REFINED)
+                   F_RV, F_SERIES, NBT_NPAR, SCHEME_SBABC3, SCHEMES, TT_GRID_LINEAR, TT_REFINED)
 
 
 def _as_params(params):
@@ -33,7 +33,7 @@ def _as_params(params):
 class Plan:
     """Configuration + CSR layout of one nbt_run call (host planning through libnbt's helpers)."""
 
-    def __init__(self, params, n_days, n_outputs, substeps=None, scheme=SCHEME_M64,
+    def __init__(self, params, n_days, n_outputs, substeps=None, scheme=SCHEME_SBABC3,
                  tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True, lanes=None):
         lib = _abi.load()
         self.params = _as_params(params)

@@ -45,7 +45,7 @@ extern "C" int hostsim_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outp
 
 // custom scheme (for calibration sweeps): a[S], b[S+1]
 extern "C" int hostsim_run_scheme(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, int S,
-                                  const double* a, const double* b) {
+                                  const double* a, const double* b, const double* g) {
     nbt_run_args A;
     std::memset(&A, 0, sizeof A);
     A.params = in->params; A.substeps = (cfg->substeps > 0) ? nullptr : in->substeps; A.order = in->order;
@@ -59,6 +59,7 @@ extern "C" int hostsim_run_scheme(const nbt_config* cfg, const nbt_inputs* in, n
     A.scheme.S = S;
     for (int i = 0; i < NBT_MAX_STAGES; i++) A.scheme.a[i] = i < S ? a[i] : 0.0;
     for (int i = 0; i <= NBT_MAX_STAGES; i++) A.scheme.b[i] = i <= S ? b[i] : 0.0;
+    for (int i = 0; i <= NBT_MAX_STAGES; i++) A.scheme.g[i] = (g && i <= S) ? g[i] : 0.0;
     switch (cfg->n_bodies - 1) {
     case 1: run_np<1>(A); break;
     case 2: run_np<2>(A); break;

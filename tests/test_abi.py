@@ -51,8 +51,8 @@ def test_plan_helpers(nbt):
     lcap = np.diff(plan.ls_offsets)
     for c, l in zip(cap[:20], lcap[:20]):
         assert l == (1 + int(np.round((0.5 - 1 / 180.) / (1.0 / (c - 1.0) / 10))) if c >= 3 else 0)
-    assert plan.n_steps == int(plan.substeps.sum()) * 8759 * 4
-    # sub-step rule: P_min / dt_sub >= 57.5 for the M64 scheme
+    assert plan.n_steps == int(plan.substeps.sum()) * 8759 * 3   # three drift stages per SBABC3 step
+    # sub-step rule: P_min / dt_sub >= 57.5 for the default SBABC3 scheme (and M64)
     step = 365.0 / 8759
     assert np.all(par[:, 1:, 1].min(1) / (step / plan.substeps) >= 57.5 - 1e-9)
 

@@ -61,14 +61,14 @@ def test_kepler_drift_two_body(hostsim):
         assert np.abs(s[3:] - want[3:]).max() < 2e-13 * a * n * 3
 
 
-@pytest.mark.parametrize("scheme,k", [("m64", 1), ("m64", 2), ("y4", 4), ("saba4", 8)])
+@pytest.mark.parametrize("scheme,k", [("sbabc3", 1), ("m64", 1), ("m64", 2), ("y4", 4), ("saba4", 8), ("c4", 3)])
 def test_readme_parity(hostsim, scheme, k):
     P = workloads.c1_params(1)
     plan = engine.Plan(P, 365, 8760, substeps=k, scheme=scheme, flags=_abi.F_MEANS | _abi.F_MEAN_OMEGA)
     got, want = host_run(hostsim, plan), oracle_run(plan)
     w = compare_products(got, want, plan)
     assert list(got.n_tt) == [111, 52, 31]
-    if scheme == "m64":
+    if scheme in ("m64", "sbabc3"):
         assert w['tt'] < 1e-3 and w['oc'] < 1e-6 and w['e'] < 1e-9
 
 
@@ -129,6 +129,27 @@ def test_scheme_coefficients(built):
         assert abs(sum(bi * ci ** j for bi, ci in zip(b, c)) - 1 / ((j + 1) * 2 ** j)) < 1e-15
     e2 = sum(b[i] * b[j] * (tau[j] - tau[i]) for i in range(5) for j in range(i + 1, 5))
     assert abs(e2 - 1 / 6) < 1e-15
+
+
+def test_gradient_scheme_coefficients(built):
+    """Force-gradient compositions: the kicks are a Lobatto quadrature (O(eps dt^2) and, for SBABC3,
+    O(eps dt^4) vanish) and the gradient kicks supply what the plain kicks lack of the O(eps^2 dt^2)
+    condition: sum_{i<j} b_i b_j (tau_j - tau_i) + sum_i b_i g_i = 1/6."""
+    s5 = 5 ** 0.5
+    schemes = {
+        "c4": ([0.5, 0.5], [1 / 6, 2 / 3, 1 / 6], [0, 1 / 24, 0], (2,)),
+        "sbabc3": ([(1 - 1 / s5) / 2, 1 / s5, (1 - 1 / s5) / 2], [1 / 12, 5 / 12, 5 / 12, 1 / 12],
+                   [(13 - 5 * s5) / 24, 0, 0, (13 - 5 * s5) / 24], (2, 4)),
+    }
+    for name, (a, b, g, moments) in schemes.items():
+        assert abs(sum(a) - 1) < 1e-15 and abs(sum(b) - 1) < 1e-15
+        tau = np.concatenate([[0], np.cumsum(a)])
+        c = tau - 0.5
+        for j in moments:
+            assert abs(sum(bi * ci ** j for bi, ci in zip(b, c)) - 1 / ((j + 1) * 2 ** j)) < 1e-15, name
+        n = len(b)
+        e2 = sum(b[i] * b[j] * (tau[j] - tau[i]) for i in range(n) for j in range(i + 1, n))
+        assert abs(e2 + sum(bi * gi for bi, gi in zip(b, g)) - 1 / 6) < 1e-15, name
 
 
 def test_inclined_three_dimensional_systems(hostsim):
