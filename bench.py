@@ -48,6 +48,23 @@ def f_step(np_, stages=3, forces=4, grad_kicks=1):
 
 
 F_OUT = 100  # per planet per output sample (Jacobi a, e, inc + crossing test)
+F_OMEGA = 75  # + argument of pericentre (eccentricity vector 20, node 7, acos 35, quadrant and sum 13), NBT_F_MEAN_OMEGA
+
+# (drift stages, force evaluations, displaced-position set-ups) per composition step of each NBT_SCHEME_*
+SCHEME_COST = {0: (1, 1, 0), 1: (3, 3, 0), 2: (4, 4, 0), 3: (4, 4, 0), 4: (2, 3, 1), 5: (3, 4, 1)}
+
+
+def plan_flops(plan):
+    """Algorithmic FLOPs of the integration stages of one launch of `plan` (sampling not included)."""
+    per, np_, sch = plan.cfg.n_outputs - 1, plan.Np, plan.cfg.scheme
+    if plan.substeps is None:
+        k_main, k_alt = plan.cfg.substeps * plan.B, 0
+    else:
+        k_main, k_alt = int(plan.substeps[plan.substeps > 0].sum()), -int(plan.substeps[plan.substeps < 0].sum())
+    s, f, g = SCHEME_COST[5 if sch == 6 else sch]
+    fl = k_main * per * s * f_step(np_, s, f, g)
+    s, f, g = SCHEME_COST[4]   # NBT_SCHEME_AUTO: negative counts are C4 steps
+    return fl + k_alt * per * s * f_step(np_, s, f, g)
 
 
 class ClockSampler(threading.Thread):
@@ -266,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
         sims_per_s = sims_all * args.steps / (dev_ms * 1e-3)
         steps_per_s = steps_all * args.steps / (dev_ms * 1e-3)
         # roofline of the dominant kernel (k_integrate), per launch on this rank
-        flops = plan.n_steps * f_step(Np) + B * N_OUTPUTS * F_OUT * Np
+        flops = plan_flops(plan) + B * N_OUTPUTS * (F_OUT + F_OMEGA) * Np   # the bench sets NBT_F_MEAN_OMEGA
         integ_launch_ms = stage_ms[0] / args.steps
         achieved = flops / (integ_launch_ms * 1e-3) * 1e-12
         line = {
@@ -274,8 +291,8 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "systems_per_gpu": B, "draws": args.draws, "omega_variants": args.omegas,
-                       "n_planets": Np, "n_days": N_DAYS, "n_outputs": N_OUTPUTS, "scheme": "sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks)",
-                       "substeps_hist": np.bincount(plan.substeps).tolist(), "parallelism": "shard-by-system x%d" % world,
+                       "n_planets": Np, "n_days": N_DAYS, "n_outputs": N_OUTPUTS, "scheme": "auto: sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks); c4 (2-stage force-gradient) where P_min >= 220 output steps",
+                       "substeps_hist": np.bincount(np.abs(plan.substeps)).tolist(), "c4_systems": int((plan.substeps < 0).sum()), "parallelism": "shard-by-system x%d" % world,
                        "l2": "256 MiB device fill between steps, outside the per-step event pairs"},
             "system_steps_per_s": steps_per_s,
             "system_steps_per_step": steps_all,
@@ -290,7 +307,7 @@ def run_ours(args, rank, world, local_rank):
                          "hbm": hbm_side(ncu_traffic(Np, B), integ_launch_ms)},
             "e2e": {"value": sims_all * args.steps / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": (3 + (1 if 0 < plan.cfg.alt_systems < B else 0)) * args.steps,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -52,7 +52,12 @@ enum { NBT_SCHEME_WH2 = 0,   /* kick-drift-kick leapfrog */
        NBT_SCHEME_C4 = 4,    /* 2-stage force-gradient composition, O(eps dt^4 + eps^2 dt^4) */
        NBT_SCHEME_SBABC3 = 5, /* 3-stage Lobatto composition + force-gradient end kicks, order (6,4):
                                  the accuracy of M64 with three Kepler drifts per step (the default) */
-       NBT_SCHEME_COUNT = 6 };
+       NBT_SCHEME_COUNT = 6,
+       NBT_SCHEME_AUTO = 6 }; /* SBABC3, except that systems resolved finely enough by the output grid itself
+                                 (P_min >= 220 output steps) take one cheaper C4 step per output:
+                                 nbt_plan_substeps marks them with negative counts in inputs.substeps,
+                                 nbt_plan_order sorts them last and counts them for cfg.alt_systems.  A
+                                 negative count outside those slots runs |count| SBABC3 steps. */
 
 /* transit-time mode */
 enum { NBT_TT_GRID_LINEAR = 0, /* reference semantics: sign test + linear interpolation on the
@@ -95,7 +100,8 @@ typedef struct nbt_config {
                             from host tt_offsets (required > 0 with NBT_F_DEVICE_PTRS) */
     int32_t lanes_systems; /* leading launch-order slots integrated by the one-planet-per-lane
                             kernel (nbt_plan_lanes); 0 = none, n_systems = all */
-    int32_t reserved;
+    int32_t alt_systems; /* NBT_SCHEME_AUTO: trailing launch-order slots that take C4 steps (nbt_plan_order
+                            returns it; every one must hold a negative count); 0 = all SBABC3 */
 } nbt_config;
 
 typedef struct nbt_inputs {
@@ -147,7 +153,8 @@ int64_t nbt_ls_nfreq(double baseline, double minfreq, double maxfreq, int sample
 int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets);
 /* Fill order[B]: permutation of 0..B-1 sorted by decreasing substeps, Hill-unstable systems
  * (mutual separation < 4 R_Hill, from params) first within equal substeps (host helper).
- * params or substeps may be NULL (that key is skipped). */
+ * params or substeps may be NULL (that key is skipped).  Negative counts (NBT_SCHEME_AUTO) sort last;
+ * returns how many there are (>= 0), which the caller stores in cfg.alt_systems, or < 0 on error. */
 int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* substeps, int32_t* order);
 /* Number of leading launch-order slots for the one-planet-per-lane kernel (host helper); the
  * caller stores it in cfg.lanes_systems.  substeps / order may be NULL. */

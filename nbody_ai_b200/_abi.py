@@ -15,9 +15,9 @@ NBT_MAX_BODIES = 9
 NBT_NPAR = 7
 P_M, P_P, P_E, P_INC, P_OMEGA_NODE, P_OMEGA_PERI, P_F = range(7)
 
-SCHEME_WH2, SCHEME_Y4, SCHEME_SABA4, SCHEME_M64, SCHEME_C4, SCHEME_SBABC3 = range(6)
+SCHEME_WH2, SCHEME_Y4, SCHEME_SABA4, SCHEME_M64, SCHEME_C4, SCHEME_SBABC3, SCHEME_AUTO = range(7)
 SCHEMES = {"wh2": SCHEME_WH2, "y4": SCHEME_Y4, "saba4": SCHEME_SABA4, "m64": SCHEME_M64,
-           "c4": SCHEME_C4, "sbabc3": SCHEME_SBABC3}
+           "c4": SCHEME_C4, "sbabc3": SCHEME_SBABC3, "auto": SCHEME_AUTO}
 TT_GRID_LINEAR, TT_REFINED = 0, 1
 
 F_MEANS = 1 << 0
@@ -62,7 +62,7 @@ class nbt_config(C.Structure):
         ("ls_samples_per_peak", C.c_int32),
         ("tt_cap_max", C.c_int32),
         ("lanes_systems", C.c_int32),
-        ("reserved", C.c_int32),
+        ("alt_systems", C.c_int32),
     ]
 
 
@@ -79,7 +79,7 @@ class nbt_outputs(C.Structure):
     ]
 
 
-def make_config(n_systems, n_bodies, n_days, n_outputs, substeps=0, scheme=SCHEME_SBABC3,
+def make_config(n_systems, n_bodies, n_days, n_outputs, substeps=0, scheme=SCHEME_AUTO,
                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0):
     cfg = nbt_config()
     cfg.struct_size = C.sizeof(nbt_config)

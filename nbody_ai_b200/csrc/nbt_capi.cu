@@ -113,13 +113,21 @@ __device__ double warp_maxavg(const double* x, int n, int lane) {
 #define NBT_MINBLOCKS 1
 #endif
 
-// launch-order slots [first, first + count) of the batch, one system per thread
+// launch-order slots [first, first + count) of the batch, one system per thread.  The first main_count
+// slots take A.scheme, the rest A.scheme_alt (NBT_SCHEME_AUTO), in separate blocks so that the scheme is
+// uniform over a block; one launch keeps the dispatch order heaviest-first (two concurrent launches
+// race for the SMs: the light one getting ahead cost 12 ms of the 72 ms bench launch).
+// (the throughput variant for two planets sits at 6 resident CTAs per SM, 168 registers: keep it there)
 template <int NP, bool SERIES, bool LAT>
-__global__ void __launch_bounds__(NBT_BLOCK, NBT_MINBLOCKS) k_integrate(const nbt_run_args A, int first, int count) {
-    const int g = blockIdx.x * NBT_BLOCK + threadIdx.x;
-    if (g >= count) return;
+__global__ void __launch_bounds__(NBT_BLOCK, (NP == 2 && !SERIES && !LAT) ? 6 : NBT_MINBLOCKS)
+k_integrate(const nbt_run_args A, int first, int count, int main_count) {
+    const int main_blocks = (main_count + NBT_BLOCK - 1) / NBT_BLOCK;
+    const bool alt = (int)blockIdx.x >= main_blocks;
+    const int g = alt ? main_count + ((int)blockIdx.x - main_blocks) * NBT_BLOCK + (int)threadIdx.x
+                      : (int)blockIdx.x * NBT_BLOCK + (int)threadIdx.x;
+    if (g >= (alt ? count : main_count)) return;
     const int sys = (A.order != nullptr) ? A.order[first + g] : first + g;
-    nbt_simulate_system<NP, SERIES, LAT>(A, sys);
+    nbt_simulate_system<NP, SERIES, LAT>(A, alt ? A.scheme_alt : A.scheme, sys);
 }
 
 // launch-order slots [first, first + count), one planet per lane (32 / NP systems per warp)
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(NBT_LBLOCK) k_integrate_lanes(const nbt_run_ar
     const int sys = (A.order != nullptr) ? A.order[first + idx] : first + idx;
     const int base = g * NP;
     const unsigned gmask = ((NP == 32) ? 0xffffffffu : ((1u << NP) - 1u)) << base;
-    nbt_simulate_lane<NP, SERIES>(A, sys, j, base, gmask);
+    nbt_simulate_lane<NP, SERIES>(A, A.scheme, sys, j, base, gmask);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -803,6 +811,7 @@ static int scheme_stages(int id) {
     case NBT_SCHEME_M64: return 4;
     case NBT_SCHEME_C4: return 2;
     case NBT_SCHEME_SBABC3: return 3;
+    case NBT_SCHEME_AUTO: return 3;   /* systems with substeps > 0; the marked ones (< 0) take C4's 2 */
     default: return -1;
     }
 }
@@ -821,7 +830,7 @@ static int check_cfg(const nbt_config* cfg) {
 }
 
 template <int NP>
-static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count, bool lanes, cudaStream_t st) {
+static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count, int main_count, bool lanes, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     const bool series = (A.flags & NBT_F_SERIES) != 0 && A.series != nullptr;
     if (lanes) {
@@ -831,34 +840,36 @@ static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count,
         if (series) k_integrate_lanes<NP, true><<<grid, NBT_LBLOCK, 0, st>>>(A, first, count);
         else k_integrate_lanes<NP, false><<<grid, NBT_LBLOCK, 0, st>>>(A, first, count);
     } else {
-        const int grid = (count + NBT_BLOCK - 1) / NBT_BLOCK;
+        if (main_count > count) main_count = count;
+        if (main_count < 0) main_count = 0;
+        const int grid = (main_count + NBT_BLOCK - 1) / NBT_BLOCK + (count - main_count + NBT_BLOCK - 1) / NBT_BLOCK;
         // Np <= 2 has a latency variant (branch-free drifts, more registers): it wins unless the launch is
         // many waves of resident threads deep (148 SMs x 6 CTAs x 64 threads = 56 832 per wave)
         const bool lat = NP <= 2 && count < 4 * 56832;
-        if (series) k_integrate<NP, true, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
-        else if (lat) k_integrate<NP, false, (NP <= 2)><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
-        else k_integrate<NP, false, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count);
+        if (series) k_integrate<NP, true, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count, main_count);
+        else if (lat) k_integrate<NP, false, (NP <= 2)><<<grid, NBT_BLOCK, 0, st>>>(A, first, count, main_count);
+        else k_integrate<NP, false, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count, main_count);
     }
     return cudaGetLastError();
 }
 
-static cudaError_t launch_integrate_np(int np, const nbt_run_args& A, int first, int count, bool lanes, cudaStream_t st) {
+static cudaError_t launch_integrate_np(int np, const nbt_run_args& A, int first, int count, int main_count, bool lanes, cudaStream_t st) {
     switch (np) {
-    case 1: return launch_integrate<1>(A, first, count, false, st);
-    case 2: return launch_integrate<2>(A, first, count, lanes, st);
-    case 3: return launch_integrate<3>(A, first, count, lanes, st);
-    case 4: return launch_integrate<4>(A, first, count, lanes, st);
-    case 5: return launch_integrate<5>(A, first, count, lanes, st);
-    case 6: return launch_integrate<6>(A, first, count, lanes, st);
-    case 7: return launch_integrate<7>(A, first, count, lanes, st);
-    case 8: return launch_integrate<8>(A, first, count, lanes, st);
+    case 1: return launch_integrate<1>(A, first, count, main_count, false, st);
+    case 2: return launch_integrate<2>(A, first, count, main_count, lanes, st);
+    case 3: return launch_integrate<3>(A, first, count, main_count, lanes, st);
+    case 4: return launch_integrate<4>(A, first, count, main_count, lanes, st);
+    case 5: return launch_integrate<5>(A, first, count, main_count, lanes, st);
+    case 6: return launch_integrate<6>(A, first, count, main_count, lanes, st);
+    case 7: return launch_integrate<7>(A, first, count, main_count, lanes, st);
+    case 8: return launch_integrate<8>(A, first, count, main_count, lanes, st);
     default: return cudaErrorInvalidValue;
     }
 }
 
-// side stream + fork/join events per device: the lanes kernel (long systems) runs concurrently
-// with the one-system-per-thread kernel (the bulk)
-struct SideStream { cudaStream_t st = nullptr; };
+// side streams per device: the lanes-kernel launches of a call (the long systems) run concurrently with
+// the one-thread-per-system launch; high priority, because the long systems should get their SMs first
+struct SideStream { cudaStream_t st[2] = {nullptr, nullptr}; };
 static std::mutex g_side_mu;
 static SideStream g_side[64];
 
@@ -866,10 +877,13 @@ static cudaError_t get_side(int dev, SideStream** out) {
     std::lock_guard<std::mutex> lk(g_side_mu);
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     SideStream& s = g_side[dev];
-    if (!s.st) {
-        cudaError_t e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
-        if (e != cudaSuccess) return e;
-    }
+    for (int i = 0; i < 2; i++)
+        if (!s.st[i]) {
+            int least = 0, greatest = 0;
+            cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s.st[i], cudaStreamNonBlocking, greatest);
+            if (e != cudaSuccess) return e;
+        }
     *out = &s;
     return cudaSuccess;
 }
@@ -931,29 +945,49 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         A.rv = out->rv; A.orbit_xz = out->orbit_xz; A.series = out->series;
         A.B = B; A.n_outputs = NO; A.substeps_all = cfg->substeps; A.tt_mode = cfg->tt_mode; A.flags = cfg->flags;
         A.orbit_stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
-        A.n_days = cfg->n_days; A.scheme = nbt_make_scheme(cfg->scheme);
+        A.n_days = cfg->n_days;
+        const bool automatic = cfg->scheme == NBT_SCHEME_AUTO;
+        A.scheme = nbt_make_scheme(automatic ? NBT_SCHEME_SBABC3 : cfg->scheme);
         int nl = cfg->lanes_systems < 0 ? 0 : cfg->lanes_systems;   // leading launch-order slots on the lanes kernel
         if (nl > B) nl = B;
         if (Np == 1) nl = 0;
-        if (nl > 0 && nl < B) {   // both kernels: fork the long systems onto the side stream
-            SideStream* side = nullptr;
+        int na = (automatic && cfg->alt_systems > 0) ? cfg->alt_systems : 0;   // trailing slots on the C4 scheme
+        if (na > B) na = B;
+        A.scheme_alt = automatic ? nbt_make_scheme(NBT_SCHEME_C4) : A.scheme;
+        // launch-order segments: [0, nl) on the lanes kernel (one launch per scheme: it takes A.scheme only),
+        // [nl, B) on the one-thread-per-system kernel (one launch, the C4 slots in its trailing blocks)
+        struct Seg { int first, count, main_count; bool lanes, alt; } seg[3];
+        int ns = 0;
+        const int la = nl < B - na ? nl : B - na;          // lanes slots on SBABC3
+        if (la > 0) seg[ns++] = {0, la, la, true, false};
+        if (nl > la) seg[ns++] = {la, nl - la, nl - la, true, true};
+        if (B > nl) seg[ns++] = {nl, B - nl, (B - na > nl ? B - na : nl) - nl, false, false};
+        // the last segment stays on `st`, the lanes launches fork to the side streams
+        const int main_seg = ns - 1;
+        SideStream* side = nullptr;
+        cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+        if (ns > 1) {
             if ((e = get_side(cfg->device, &side)) != cudaSuccess) return e;
-            // fork/join events are per call (concurrent callers on one device share only the side stream)
-            cudaEvent_t fork = nullptr, join = nullptr;
+            // fork/join events are per call (concurrent callers on one device share only the side streams)
             if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-            if ((e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming)) != cudaSuccess) { cudaEventDestroy(fork); return e; }
             e = cudaEventRecord(fork, st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(side->st, fork, 0);
-            if (e == cudaSuccess) e = launch_integrate_np(Np, A, 0, nl, true, side->st);
-            if (e == cudaSuccess) e = launch_integrate_np(Np, A, nl, B - nl, false, st);
-            if (e == cudaSuccess) e = cudaEventRecord(join, side->st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
-            cudaEventDestroy(fork); cudaEventDestroy(join);   // destruction is deferred until the events complete
-            if (e != cudaSuccess) return e;
-        } else {
-            e = launch_integrate_np(Np, A, 0, B, nl == B, st);
-            if (e != cudaSuccess) return e;
+        } else e = cudaSuccess;
+        int nside = 0;
+        for (int i = 0; i < ns && e == cudaSuccess; i++) {
+            nbt_run_args As = A;
+            if (seg[i].alt) As.scheme = A.scheme_alt;
+            if (i == main_seg) { e = launch_integrate_np(Np, As, seg[i].first, seg[i].count, seg[i].main_count, seg[i].lanes, st); continue; }
+            cudaStream_t ss = side->st[nside];
+            e = cudaStreamWaitEvent(ss, fork, 0);
+            if (e == cudaSuccess) e = launch_integrate_np(Np, As, seg[i].first, seg[i].count, seg[i].main_count, seg[i].lanes, ss);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join[nside], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(join[nside], ss);
+            nside++;
         }
+        for (int i = 0; i < nside && e == cudaSuccess; i++) e = cudaStreamWaitEvent(st, join[i], 0);   // after st's own launch
+        if (fork) cudaEventDestroy(fork);   // destruction is deferred until the events complete
+        for (int i = 0; i < 2; i++) if (join[i]) cudaEventDestroy(join[i]);
+        if (e != cudaSuccess) return e;
     } else {
         nbt_scan_args S;
         memset(&S, 0, sizeof S);
@@ -1077,13 +1111,18 @@ int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* s
     std::vector<uint8_t> unstable(params ? B : 0);
     if (params)
         for (int b = 0; b < B; b++) unstable[b] = hill_separation(params + (size_t)b * N * NBT_NPAR, N) < 4.0 ? 1 : 0;
+    // negative counts (NBT_SCHEME_AUTO: one C4 step per output) are the lightest systems: they sort last,
+    // which also keeps the two schemes in separate warps but for one
     std::stable_sort(order, order + B, [&](int32_t a, int32_t b) {
         const int ka = substeps ? substeps[a] : 1, kb = substeps ? substeps[b] : 1;
         if (ka != kb) return ka > kb;
         if (params && unstable[a] != unstable[b]) return unstable[a] > unstable[b];
         return false;
     });
-    return 0;
+    int nalt = 0;
+    if (substeps)
+        for (int b = 0; b < B; b++) nalt += substeps[b] < 0 ? 1 : 0;
+    return nalt;
 }
 
 /* How many leading launch-order slots go to the one-planet-per-lane kernel (nbt_config.lanes_systems).
@@ -1125,9 +1164,10 @@ int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* subs
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (!params || !substeps) return nbt_fail(-10, "nbt_plan_substeps: NULL argument");
-    static const double R[NBT_SCHEME_COUNT] = {8000.0, 400.0, 800.0, 57.5, 200.0, 57.5}; /* P_min / dt_sub */
+    static const double R[NBT_SCHEME_COUNT + 1] = {8000.0, 400.0, 800.0, 57.5, 220.0, 57.5, 57.5}; /* P_min / dt_sub */
     const int B = cfg->n_systems, N = cfg->n_bodies;
     const double step = cfg->n_days / (double)(cfg->n_outputs - 1);
+    const bool automatic = cfg->scheme == NBT_SCHEME_AUTO;
     for (int b = 0; b < B; b++) {
         const double* par = params + (size_t)b * N * NBT_NPAR;
         double pmin = INFINITY;
@@ -1138,6 +1178,11 @@ int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* subs
         double k = std::isfinite(pmin) ? ceil(step * R[cfg->scheme] / pmin) : 1.0;
         if (!(k >= 1.0)) k = 1.0;
         if (k > 65536.0) k = 65536.0;
+        /* AUTO: a C4 step costs ~0.7 of an SBABC3 step and needs 3.8x the resolution, so it only pays
+         * where a single step per output interval is already fine enough for it; Hill-unstable systems
+         * (which may break, and which nbt_plan_order groups by sub-step count) keep SBABC3 */
+        if (automatic && k == 1.0 && std::isfinite(pmin) && step * R[NBT_SCHEME_C4] <= pmin &&
+            hill_separation(par, N) >= 4.0) k = -1.0;
         substeps[b] = (int32_t)k;
     }
     return 0;
@@ -1147,9 +1192,10 @@ int64_t nbt_count_steps(const nbt_config* cfg, const int32_t* substeps) {
     if (check_cfg(cfg)) return -1;
     const int64_t S = scheme_stages(cfg->scheme), per = (int64_t)cfg->n_outputs - 1;
     if (cfg->substeps > 0 || !substeps) return (int64_t)cfg->n_systems * per * S * std::max(cfg->substeps, 1);
+    const int64_t S_alt = cfg->scheme == NBT_SCHEME_AUTO ? scheme_stages(NBT_SCHEME_C4) : S;
     int64_t tot = 0;
-    for (int b = 0; b < cfg->n_systems; b++) tot += (int64_t)substeps[b];
-    return tot * per * S;
+    for (int b = 0; b < cfg->n_systems; b++) tot += substeps[b] < 0 ? -(int64_t)substeps[b] * S_alt : (int64_t)substeps[b] * S;
+    return tot * per;
 }
 
 static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, void* cuda_stream,
@@ -1165,6 +1211,14 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
     if ((cfg->flags & NBT_F_MEANS) && (!out->mean_a || !out->mean_e || !out->mean_inc))
         return nbt_fail(-10, "nbt_run: NBT_F_MEANS needs mean_a, mean_e, mean_inc");
     if (!scan && cfg->substeps <= 0 && !in->substeps) return nbt_fail(-12, "nbt_run: cfg.substeps <= 0 needs inputs.substeps");
+    if (!scan && cfg->scheme == NBT_SCHEME_AUTO && cfg->alt_systems > 0) {
+        if (cfg->alt_systems > cfg->n_systems || cfg->substeps > 0 || !in->substeps)
+            return nbt_fail(-13, "nbt_run: cfg.alt_systems needs inputs.substeps and <= n_systems slots");
+        if (!(cfg->flags & NBT_F_DEVICE_PTRS))   // host arrays: every C4 slot must be one the planner marked
+            for (int g = cfg->n_systems - cfg->alt_systems; g < cfg->n_systems; g++)
+                if (in->substeps[in->order ? in->order[g] : g] >= 0)
+                    return nbt_fail(-13, "nbt_run: launch slot %d is inside cfg.alt_systems but its sub-step count is not negative", g);
+    }
     if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_run: no CUDA device (there is no CPU fallback)");
     const int B = cfg->n_systems, N = cfg->n_bodies, Np = N - 1, NO = cfg->n_outputs;
     if (B == 0) return 0;
@@ -1261,12 +1315,12 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         // products that are final after k_fit go back on the side stream, overlapping k_ls_oc / the RV stages
         Buf* early[] = {&b_tt, &b_ttv, &b_ntt, &b_per, &b_t0, &b_max, &b_ma, &b_me, &b_mi, &b_mo, &b_stat, &b_orb, &b_ser};
         Buf* late[] = {&b_rv, &b_rvmax, &b_lsp, &b_lsn, &b_lsrv};
-        NBT_CUDA(cudaStreamWaitEvent(side->st, ev_fit, 0));
+        NBT_CUDA(cudaStreamWaitEvent(side->st[0], ev_fit, 0));
         for (Buf* b : early)
-            if (b->bytes && b->h_out) NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, side->st));
+            if (b->bytes && b->h_out) NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, side->st[0]));
         for (Buf* b : late)
             if (b->bytes && b->h_out) NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, st));
-        NBT_CUDA(cudaStreamSynchronize(side->st));
+        NBT_CUDA(cudaStreamSynchronize(side->st[0]));
         NBT_CUDA(cudaStreamSynchronize(st));
     }
 done:

@@ -701,20 +701,22 @@ struct nbt_run_args {
     // config
     int32_t B, n_outputs, substeps_all, tt_mode, flags, orbit_stride;
     double n_days;
-    nbt_scheme scheme;
+    nbt_scheme scheme;      // composition of the systems with positive sub-step counts
+    nbt_scheme scheme_alt;  // NBT_SCHEME_AUTO: C4, for the trailing launch-order slots of a launch (whole blocks)
 };
 
 // SERIES = the NBT_F_SERIES variant (full element set per sample, generate() compatibility); it is a
 // separate instantiation so that its large code stays out of the instruction caches of the batched path
 template <int NP, bool SERIES, bool LAT = false>
-NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
+NBT_HD void nbt_simulate_system(const nbt_run_args& A, const nbt_scheme& sc, int sys) {
     nbt_state<NP> s;
     nbt_consts<NP> c;
     const double* par = A.params + (size_t)sys * (NP + 1) * NBT_NPAR;
     nbt_setup<NP>(par, s, c);
     int status = 0;
     const int NO = A.n_outputs, B = A.B;
-    const int k = (A.substeps != nullptr) ? A.substeps[sys] : A.substeps_all;
+    const int kraw = (A.substeps != nullptr) ? A.substeps[sys] : A.substeps_all;
+    const int k = kraw < 0 ? -kraw : kraw;
     const double step = A.n_days / (double)(NO - 1);
     const double dt = step / (double)k;
     const bool want_means = (A.flags & NBT_F_MEANS) != 0;
@@ -727,7 +729,7 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
     const int W = 3 + 10 * NP;
 
     double ax[NP], ay[NP], az[NP];
-    nbt_accel_grad<NP>(s, c, A.scheme.g[0] * dt * dt, ax, ay, az);
+    nbt_accel_grad<NP>(s, c, sc.g[0] * dt * dt, ax, ay, az);
 
     double dx_prev[NP], dvx_prev[NP];
     double sum_a[NP], sum_e[NP], sum_i[NP], sum_o[NP];
@@ -738,7 +740,7 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, int sys) {
 
     for (int o = 0; o < NO; o++) {
         if (o > 0) {
-            for (int sub = 0; sub < k; sub++) nbt_step<NP, LAT>(s, c, A.scheme, dt, ax, ay, az, status);
+            for (int sub = 0; sub < k; sub++) nbt_step<NP, LAT>(s, c, sc, dt, ax, ay, az, status);
         }
         const double t = (o == NO - 1) ? A.n_days : (double)o * step;
         if (o > 0) { // refresh the carried radii from the coordinates (bounds their round-off drift)

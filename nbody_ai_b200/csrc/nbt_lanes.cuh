@@ -98,7 +98,7 @@ __device__ __forceinline__ void nbt_accel_lane_grad(unsigned gmask, int base, in
 
 // One lane of one system: integrate + sample + detect transits (the lanes form of nbt_simulate_system).
 template <int NP, bool SERIES>
-__device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int base, unsigned gmask) {
+__device__ void nbt_simulate_lane(const nbt_run_args& A, const nbt_scheme& sc, int sys, int j, int base, unsigned gmask) {
     const double* par = A.params + (size_t)sys * (NP + 1) * NBT_NPAR;
     double mr[NP], Gm[NP + 1];
     double GMj = 0.0;
@@ -135,7 +135,8 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
     }
     int status = 0;
     const int NO = A.n_outputs, B = A.B;
-    const int k = (A.substeps != nullptr) ? A.substeps[sys] : A.substeps_all;
+    const int kraw = (A.substeps != nullptr) ? A.substeps[sys] : A.substeps_all;
+    const int k = kraw < 0 ? -kraw : kraw;
     const double step = A.n_days / (double)(NO - 1);
     const double dt = step / (double)k;
     const bool want_means = (A.flags & NBT_F_MEANS) != 0;
@@ -146,7 +147,6 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, int sys, int j, int bas
     const bool tt_on = !((A.flags & NBT_F_PLANET1_ONLY) && j > 0);
     const double rv_scale = 1.496e11 * ((double)NO / (A.n_days * 24.0 * 60.0 * 60.0));
     const int W = 3 + 10 * NP;
-    const nbt_scheme& sc = A.scheme;
 
     double rj, irj;
     nbt_radius(x, y, z, rj, irj);

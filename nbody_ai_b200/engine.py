@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _abi
 from ._abi import (F_DEVICE_PTRS, F_LS_OC, F_LS_RV, F_MEAN_OMEGA, F_MEANS, F_ORBIT, F_PLANET1_ONLY,
-                   F_RV, F_SERIES, NBT_NPAR, SCHEME_SBABC3, SCHEMES, TT_GRID_LINEAR, TT_REFINED)
+                   F_RV, F_SERIES, NBT_NPAR, SCHEME_AUTO, SCHEMES, TT_GRID_LINEAR, TT_REFINED)
 
 
 def _as_params(params):
@@ -33,7 +33,7 @@ def _as_params(params):
 class Plan:
     """Configuration + CSR layout of one nbt_run call (host planning through libnbt's helpers)."""
 
-    def __init__(self, params, n_days, n_outputs, substeps=None, scheme=SCHEME_SBABC3,
+    def __init__(self, params, n_days, n_outputs, substeps=None, scheme=SCHEME_AUTO,
                  tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True, lanes=None):
         lib = _abi.load()
         self.params = _as_params(params)
@@ -56,11 +56,21 @@ class Plan:
             self.substeps = np.ascontiguousarray(substeps, dtype=np.int32)
             assert self.substeps.shape == (B,)
         # launch order: heavy systems first, equal trip counts within a warp, unstable ones grouped
+        # (NBT_SCHEME_AUTO: the systems marked for C4 steps go last — sorted or not, the two schemes are two launches)
         self.order = None
-        if sort and B > 32:
+        marked = self.cfg.scheme == SCHEME_AUTO and self.substeps is not None and bool((self.substeps < 0).any())
+        if marked and not sort:
+            self.order = np.concatenate([np.flatnonzero(self.substeps >= 0), np.flatnonzero(self.substeps < 0)]).astype(np.int32)
+            self.cfg.alt_systems = int((self.substeps < 0).sum())
+            if np.array_equal(self.order, np.arange(B, dtype=np.int32)):
+                self.order = None
+        if sort and (B > 32 or marked):
             self.order = np.zeros(B, dtype=np.int32)
-            _abi.check(lib.nbt_plan_order(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.substeps, C.c_int32),
-                                          _abi.ptr(self.order, C.c_int32)), lib)
+            nalt = lib.nbt_plan_order(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.substeps, C.c_int32),
+                                      _abi.ptr(self.order, C.c_int32))
+            if nalt < 0:
+                _abi.check(nalt, lib)
+            self.cfg.alt_systems = int(nalt) if self.cfg.scheme == SCHEME_AUTO else 0
             if np.array_equal(self.order, np.arange(B, dtype=np.int32)):
                 self.order = None
         # which systems run one planet per lane (long ones / small batches), see nbt_plan_lanes

@@ -45,12 +45,12 @@ class Simulation:
 
 def _integrator_kw(integrator, Ndays, Noutputs):
     """integrator=None: REBOUND's default (IAS15) is matched within the parity tolerances by the
-    planned SBABC3 composition.  'whfast' (simulation.py:39-42): plain Wisdom-Holman leapfrog at
+    planned SBABC3 / C4 compositions (NBT_SCHEME_AUTO).  'whfast' (simulation.py:39-42): plain Wisdom-Holman leapfrog at
     REBOUND's default dt = 1e-3 d.  'tes' (:34-38) is a high-accuracy scheme: same as None."""
     if integrator == 'whfast':
         step = float(Ndays) / (int(Noutputs) - 1)
         return dict(scheme=_abi.SCHEME_WH2, substeps=max(1, int(np.ceil(step / 1e-3))))
-    return dict(scheme=_abi.SCHEME_SBABC3, substeps=None)
+    return dict(scheme=_abi.SCHEME_AUTO, substeps=None)
 
 
 def generate(objects, Ndays=None, Noutputs=None, integrator=None):

@@ -8,13 +8,13 @@
 #include "../../nbody_ai_b200/csrc/nbt_core.cuh"
 
 template <int NP>
-static void run_np(const nbt_run_args& A) {
+static void run_np(const nbt_run_args& A, int first, int count) {
     const bool series = (A.flags & NBT_F_SERIES) != 0 && A.series != nullptr;
-    for (int g = 0; g < A.B; g++) {
+    for (int g = first; g < first + count; g++) {
         // both drift variants are exercised: even launch slots run the latency (branch-free) one
-        if (series) nbt_simulate_system<NP, true, false>(A, A.order ? A.order[g] : g);
-        else if (g % 2 == 0) nbt_simulate_system<NP, false, true>(A, A.order ? A.order[g] : g);
-        else nbt_simulate_system<NP, false, false>(A, A.order ? A.order[g] : g);
+        if (series) nbt_simulate_system<NP, true, false>(A, A.scheme, A.order ? A.order[g] : g);
+        else if (g % 2 == 0) nbt_simulate_system<NP, false, true>(A, A.scheme, A.order ? A.order[g] : g);
+        else nbt_simulate_system<NP, false, false>(A, A.scheme, A.order ? A.order[g] : g);
     }
 }
 
@@ -28,17 +28,26 @@ extern "C" int hostsim_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outp
     A.rv = out->rv; A.orbit_xz = out->orbit_xz; A.series = out->series;
     A.B = cfg->n_systems; A.n_outputs = cfg->n_outputs; A.substeps_all = cfg->substeps;
     A.tt_mode = cfg->tt_mode; A.flags = cfg->flags; A.orbit_stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
-    A.n_days = cfg->n_days; A.scheme = nbt_make_scheme(cfg->scheme);
-    switch (cfg->n_bodies - 1) {
-    case 1: run_np<1>(A); break;
-    case 2: run_np<2>(A); break;
-    case 3: run_np<3>(A); break;
-    case 4: run_np<4>(A); break;
-    case 5: run_np<5>(A); break;
-    case 6: run_np<6>(A); break;
-    case 7: run_np<7>(A); break;
-    case 8: run_np<8>(A); break;
-    default: return -1;
+    A.n_days = cfg->n_days;
+    // NBT_SCHEME_AUTO as in enqueue_path: the trailing cfg.alt_systems launch slots take C4, the rest SBABC3
+    const bool automatic = cfg->scheme == NBT_SCHEME_AUTO;
+    int nalt = automatic ? cfg->alt_systems : 0;
+    if (nalt < 0) nalt = 0;
+    if (nalt > A.B) nalt = A.B;
+    for (int pass = 0; pass < 2; pass++) {
+        const int first = pass == 0 ? 0 : A.B - nalt, count = pass == 0 ? A.B - nalt : nalt;
+        A.scheme = nbt_make_scheme(automatic ? (pass == 0 ? NBT_SCHEME_SBABC3 : NBT_SCHEME_C4) : cfg->scheme);
+        switch (cfg->n_bodies - 1) {
+        case 1: run_np<1>(A, first, count); break;
+        case 2: run_np<2>(A, first, count); break;
+        case 3: run_np<3>(A, first, count); break;
+        case 4: run_np<4>(A, first, count); break;
+        case 5: run_np<5>(A, first, count); break;
+        case 6: run_np<6>(A, first, count); break;
+        case 7: run_np<7>(A, first, count); break;
+        case 8: run_np<8>(A, first, count); break;
+        default: return -1;
+        }
     }
     return 0;
 }
@@ -61,10 +70,10 @@ extern "C" int hostsim_run_scheme(const nbt_config* cfg, const nbt_inputs* in, n
     for (int i = 0; i <= NBT_MAX_STAGES; i++) A.scheme.b[i] = i <= S ? b[i] : 0.0;
     for (int i = 0; i <= NBT_MAX_STAGES; i++) A.scheme.g[i] = (g && i <= S) ? g[i] : 0.0;
     switch (cfg->n_bodies - 1) {
-    case 1: run_np<1>(A); break;
-    case 2: run_np<2>(A); break;
-    case 3: run_np<3>(A); break;
-    case 4: run_np<4>(A); break;
+    case 1: run_np<1>(A, 0, A.B); break;
+    case 2: run_np<2>(A, 0, A.B); break;
+    case 3: run_np<3>(A, 0, A.B); break;
+    case 4: run_np<4>(A, 0, A.B); break;
     default: return -1;
     }
     return 0;

@@ -51,10 +51,16 @@ def test_plan_helpers(nbt):
     lcap = np.diff(plan.ls_offsets)
     for c, l in zip(cap[:20], lcap[:20]):
         assert l == (1 + int(np.round((0.5 - 1 / 180.) / (1.0 / (c - 1.0) / 10))) if c >= 3 else 0)
-    assert plan.n_steps == int(plan.substeps.sum()) * 8759 * 3   # three drift stages per SBABC3 step
-    # sub-step rule: P_min / dt_sub >= 57.5 for the default SBABC3 scheme (and M64)
+    # default scheme (AUTO): three drift stages per SBABC3 step, two per C4 step (negative counts)
+    k = plan.substeps
+    assert plan.n_steps == (int(k[k > 0].sum()) * 3 - int(k[k < 0].sum()) * 2) * 8759
+    # sub-step rule: P_min / dt_sub >= 57.5 for SBABC3; C4 only at one step per output and P_min >= 220 steps
     step = 365.0 / 8759
-    assert np.all(par[:, 1:, 1].min(1) / (step / plan.substeps) >= 57.5 - 1e-9)
+    pmin = par[:, 1:, 1].min(1)
+    assert np.all(pmin[k > 0] / (step / k[k > 0]) >= 57.5 - 1e-9)
+    assert np.all(k[k < 0] == -1) and np.all(pmin[k < 0] >= 220 * step) and (k < 0).any()
+    sb = engine.Plan(par, 365.0, 8760, scheme="sbabc3")
+    assert np.array_equal(sb.substeps, np.abs(k)) and sb.n_steps == int(sb.substeps.sum()) * 8759 * 3
 
 
 def test_invalid_arguments(nbt):

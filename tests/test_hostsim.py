@@ -79,7 +79,11 @@ def test_planned_substeps_random_systems(hostsim):
     plan = engine.Plan(par, 200.0, 4801, flags=_abi.F_MEANS)
     got, want = host_run(hostsim, plan), oracle_run(plan)
     compare_products(got, want, plan)
-    assert plan.substeps.min() >= 1 and plan.order is None or sorted(plan.order) == list(range(plan.B))
+    assert plan.order is None or sorted(plan.order) == list(range(plan.B))
+    # default scheme (AUTO): the finely resolved systems took C4 steps, the others SBABC3
+    k = plan.substeps
+    assert (k < 0).any() and (k > 0).any() and plan.cfg.alt_systems == (k < 0).sum()
+    assert np.all(k[plan.order if plan.order is not None else np.arange(plan.B)][-plan.cfg.alt_systems:] < 0)
 
 
 def test_series_matches_oracle(hostsim):

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from nbody_ai_b200 import _abi, engine, workloads  # noqa: E402
-from bench import f_step  # noqa: E402
+from bench import plan_flops  # noqa: E402
 
 
 def timed(params, nd, no, flags, reps=2, **kw):
@@ -31,7 +31,7 @@ def timed(params, nd, no, flags, reps=2, **kw):
     ms /= reps
     h = d.to_host()
     Np = plan.Np
-    fl = plan.n_steps * f_step(Np)
+    fl = plan_flops(plan)
     st = {int(s): int((h.status == s).sum()) for s in np.unique(h.status)}
     print("  B=%d Np=%d steps=%.3g  integrate %.2f ms  fit %.3f ms  ls %.3f ms  rv %.3f ms -> %.3g steps/s  %.2f TF  status %s" % (
         plan.B, Np, plan.n_steps, ms[0], ms[1], ms[2], ms[3], plan.n_steps / (ms[0] * 1e-3), fl / (ms[0] * 1e-3) * 1e-12, st), flush=True)
@@ -44,13 +44,13 @@ def timed_big(params, nd, no, flags, **kw):
     plan = engine.Plan(params, nd, no, flags=flags, **kw)
     d = engine.DeviceBuffers(plan)
     print("  planned in %.1f s: B=%d Np=%d steps=%.3g tt capacity %.3g doubles, k hist %s" % (
-        time.time() - t0, plan.B, plan.Np, plan.n_steps, float(plan.tt_offsets[-1]), np.bincount(plan.substeps).tolist()), flush=True)
+        time.time() - t0, plan.B, plan.Np, plan.n_steps, float(plan.tt_offsets[-1]), np.bincount(np.abs(plan.substeps)).tolist()), flush=True)
     engine.run_device(plan, d, timing=True)
     torch.cuda.synchronize()
     ms = engine.stage_timing()
     st = d.status.cpu().numpy()
     ntt = d.n_tt.cpu().numpy()
-    fl = plan.n_steps * f_step(plan.Np)
+    fl = plan_flops(plan)
     print("  integrate %.1f ms  fit %.1f ms  ls %.1f ms -> %.3g steps/s  %.2f TF  %.3g sims/s; transits %d; status %s" % (
         ms[0], ms[1], ms[2], plan.n_steps / (ms[0] * 1e-3), fl / (ms[0] * 1e-3) * 1e-12, plan.B / (ms.sum() * 1e-3), int(ntt.sum()),
         {int(s): int((st == s).sum()) for s in np.unique(st)}), flush=True)
