@@ -9,7 +9,7 @@ through the C ABI of include/nbt.h; nothing here falls back to the CPU.
 Differences from the reference that a caller can observe:
   * generate() without Ndays/Noutputs returns a light `Simulation` handle (the reference returns
     a rebound.Simulation); integrate(sim, objects, Ndays, Noutputs) accepts it.
-  * the trajectory comes from a 4-stage order-(6,4) Wisdom-Holman composition whose step is
+  * the trajectory comes from order-(6,4) / order-4 force-gradient Wisdom-Holman compositions whose step is
     planned per system to sit inside the parity tolerances against REBOUND's IAS15
     (DESIGN.md §4), not from IAS15 itself.
   * report() (matplotlib) is out of scope.
