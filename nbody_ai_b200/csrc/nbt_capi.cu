@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -289,13 +290,14 @@ struct nbt_lsoc_args {
     const double* ttv; const int32_t* n_tt;
     double* power; int32_t* nfreq;
     int32_t B, Np, flags, spp;
+    int32_t w0, w1;   // (system, planet) series [w0, w1) of this launch
     double fmin, fmax;
 };
 
 __global__ void __launch_bounds__(128) k_ls_oc(const nbt_lsoc_args L) {
-    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int w = L.w0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (w >= L.B * L.Np) return;
+    if (w >= L.w1) return;
     const int j = w % L.Np;
     const int64_t off = L.tt_offsets[w];
     const int cap = (int)(L.tt_offsets[w + 1] - off);
@@ -845,7 +847,8 @@ static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count,
         const int grid = (main_count + NBT_BLOCK - 1) / NBT_BLOCK + (count - main_count + NBT_BLOCK - 1) / NBT_BLOCK;
         // Np <= 2 has a latency variant (branch-free drifts, more registers): it wins unless the launch is
         // many waves of resident threads deep (148 SMs x 6 CTAs x 64 threads = 56 832 per wave)
-        const bool lat = NP <= 2 && count < 4 * 56832;
+        bool lat = NP <= 2 && count < 4 * 56832;
+        if (const char* f = getenv("NBT_DEBUG_LAT")) lat = NP <= 2 && f[0] == '1';   // measurement hook
         if (series) k_integrate<NP, true, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count, main_count);
         else if (lat) k_integrate<NP, false, (NP <= 2)><<<grid, NBT_BLOCK, 0, st>>>(A, first, count, main_count);
         else k_integrate<NP, false, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count, main_count);
@@ -888,6 +891,8 @@ static cudaError_t get_side(int dev, SideStream** out) {
     return cudaSuccess;
 }
 
+#define NBT_LS_CHUNKS 4   // host path: ranges in which the O-C periodograms are computed and copied back
+
 static std::mutex g_pool_mu;
 static bool g_pool_ready[64] = {false};
 
@@ -928,7 +933,8 @@ struct Arena {
 static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, const nbt_outputs* out,
                                 double* rv_sm_ws, cudaStream_t st, const double* scan_series = nullptr,
                                 const double* scan_times = nullptr, double scan_dt = 0.0,
-                                cudaEvent_t after_fit = nullptr) {
+                                cudaEvent_t after_fit = nullptr, int n_ls_chunks = 0,
+                                const int32_t* ls_bounds = nullptr, cudaEvent_t* ls_events = nullptr) {
     const int B = cfg->n_systems, Np = cfg->n_bodies - 1, NO = cfg->n_outputs;
     if (B == 0) return cudaSuccess;
     cudaError_t e;
@@ -1023,8 +1029,30 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         L.tt_offsets = in->tt_offsets; L.ls_offsets = in->ls_offsets; L.ttv = out->ttv; L.n_tt = out->n_tt;
         L.power = out->ls_oc_power; L.nfreq = out->ls_oc_nfreq; L.B = B; L.Np = Np; L.flags = cfg->flags;
         L.spp = cfg->ls_samples_per_peak; L.fmin = cfg->ls_oc_minfreq; L.fmax = cfg->ls_oc_maxfreq;
-        k_ls_oc<<<fit_grid, 128, 0, st>>>(L);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        // host path: a few launches over ranges of series, an event after each, so that the periodograms of one
+        // range go back to the host while the next range is computed (ls_bounds[0..n_ls_chunks])
+        const int32_t whole[2] = {0, (int32_t)nw};
+        const int nc = (n_ls_chunks > 0 && ls_bounds && ls_events) ? n_ls_chunks : 1;
+        const int32_t* bounds = nc == n_ls_chunks && ls_bounds ? ls_bounds : whole;
+        // (odd ranges on a side stream: the ragged tail of one launch overlaps the next launch)
+        const bool piped = nc > 1 && after_fit != nullptr;
+        SideStream* side = nullptr;
+        if (piped) {
+            if ((e = get_side(cfg->device, &side)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(side->st[1], after_fit, 0)) != cudaSuccess) return e;
+        }
+        for (int c = 0; c < nc; c++) {
+            cudaStream_t ls = (piped && (c & 1)) ? side->st[1] : st;
+            L.w0 = bounds[c]; L.w1 = bounds[c + 1];
+            if (L.w1 > L.w0) {
+                k_ls_oc<<<(int)(((long long)(L.w1 - L.w0) * 32 + 127) / 128), 128, 0, ls>>>(L);
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            }
+            if (nc > 1 && (e = cudaEventRecord(ls_events[c], ls)) != cudaSuccess) return e;
+        }
+        if (piped)
+            for (int c = 1; c < nc; c += 2)
+                if ((e = cudaStreamWaitEvent(st, ls_events[c], 0)) != cudaSuccess) return e;
     }
     timing_mark(3, tim, st);
     if ((cfg->flags & NBT_F_RV) && out->rv && rv_sm_ws && (out->rv_max || ((cfg->flags & NBT_F_LS_RV) && out->ls_rv_power))) {
@@ -1228,6 +1256,7 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
     char* arena = nullptr;
     double* rv_ws = nullptr;
     cudaEvent_t ev_fit = nullptr;
+    cudaEvent_t ev_ls[NBT_LS_CHUNKS] = {};
     NBT_CUDA(cudaSetDevice(cfg->device));
     ensure_pool(cfg->device);
     {
@@ -1310,21 +1339,39 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         SideStream* side = nullptr;
         NBT_CUDA(get_side(cfg->device, &side));
         NBT_CUDA(cudaEventCreateWithFlags(&ev_fit, cudaEventDisableTiming));
+        // O-C periodograms (the largest product) in up to NBT_LS_CHUNKS ranges of equal capacity
+        int n_ls = 0;
+        int32_t ls_bounds[NBT_LS_CHUNKS + 1];
+        if (b_lsp.bytes && b_lsp.h_out && nls >= (int64_t)NBT_LS_CHUNKS * (1 << 20) && nsp < INT32_MAX) {
+            n_ls = NBT_LS_CHUNKS;
+            ls_bounds[0] = 0; ls_bounds[n_ls] = (int32_t)nsp;
+            for (int c = 1; c < n_ls; c++)
+                ls_bounds[c] = (int32_t)(std::lower_bound(in->ls_offsets, in->ls_offsets + nsp, nls * c / n_ls) - in->ls_offsets);
+            for (int c = 0; c < n_ls; c++) NBT_CUDA(cudaEventCreateWithFlags(&ev_ls[c], cudaEventDisableTiming));
+        }
         NBT_CUDA(enqueue_path(cfg, &din, &dout, (double*)dp(b_rvws), st, scan ? (const double*)dp(b_ser) : nullptr,
-                              (const double*)dp(b_times), scan_dt, ev_fit));
+                              (const double*)dp(b_times), scan_dt, ev_fit, n_ls, ls_bounds, ev_ls));
         // products that are final after k_fit go back on the side stream, overlapping k_ls_oc / the RV stages
         Buf* early[] = {&b_tt, &b_ttv, &b_ntt, &b_per, &b_t0, &b_max, &b_ma, &b_me, &b_mi, &b_mo, &b_stat, &b_orb, &b_ser};
         Buf* late[] = {&b_rv, &b_rvmax, &b_lsp, &b_lsn, &b_lsrv};
         NBT_CUDA(cudaStreamWaitEvent(side->st[0], ev_fit, 0));
         for (Buf* b : early)
             if (b->bytes && b->h_out) NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, side->st[0]));
+        for (int c = 0; c < n_ls; c++) {   // periodogram ranges follow their launches on the side stream
+            const int64_t lo = in->ls_offsets[ls_bounds[c]], hi = in->ls_offsets[ls_bounds[c + 1]];
+            NBT_CUDA(cudaStreamWaitEvent(side->st[0], ev_ls[c], 0));
+            if (hi > lo) NBT_CUDA(cudaMemcpyAsync((char*)b_lsp.h_out + lo * 8, (char*)dp(b_lsp) + lo * 8, (size_t)(hi - lo) * 8,
+                                                  cudaMemcpyDeviceToHost, side->st[0]));
+        }
         for (Buf* b : late)
-            if (b->bytes && b->h_out) NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, st));
+            if (b->bytes && b->h_out && !(n_ls > 0 && b == &b_lsp))
+                NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, st));
         NBT_CUDA(cudaStreamSynchronize(side->st[0]));
         NBT_CUDA(cudaStreamSynchronize(st));
     }
 done:
     if (ev_fit) cudaEventDestroy(ev_fit);
+    for (int c = 0; c < NBT_LS_CHUNKS; c++) if (ev_ls[c]) cudaEventDestroy(ev_ls[c]);
     if (rc != 0 && arena) cudaDeviceSynchronize();     // error path: nothing may still touch the arena
     if (arena) cudaFreeAsync(arena, st);
     if (rv_ws) cudaFreeAsync(rv_ws, st);
