@@ -68,6 +68,15 @@ def test_invalid_arguments(nbt):
     assert nbt.nbt_count_steps(C.byref(cfg), None) == -1          # n_bodies < 2
     cfg = _abi.make_config(1, 3, 10.0, 1, substeps=1)
     assert nbt.nbt_count_steps(C.byref(cfg), None) == -1          # n_outputs < 2
+    # NBT_SCHEME_AUTO: every launch slot inside cfg.alt_systems must hold a system the planner marked
+    par = workloads.c2_params(40, 0, seed=1)
+    plan = engine.Plan(par, 365.0, 8760)
+    assert 0 < plan.cfg.alt_systems < plan.B
+    buf = engine.Buffers(plan)
+    inp, out = buf.as_structs()
+    plan.cfg.alt_systems += 1
+    assert nbt.nbt_run(C.byref(plan.cfg), C.byref(inp), C.byref(out), None) == -13
+    assert b"alt_systems" in nbt.nbt_last_error()
     with pytest.raises(ValueError):
         _abi.objects_to_params([{'m': 1.0}, {'m': 1e-3}])          # planet without a period
     with pytest.raises(ValueError):

@@ -278,6 +278,29 @@ def test_full_size_invariants(gpu_lib):
     compare_products(got, want, p2, skip=set(range(p2.B)) - ok)
 
 
+def test_auto_scheme_agrees_with_sbabc3(gpu_lib):
+    """NBT_SCHEME_AUTO (C4 steps for the systems the output grid resolves finely) against SBABC3 for every
+    system: different compositions of the same flow, so not bit-equal, but far inside the parity tolerances;
+    the SBABC3 systems of the AUTO run are bit-equal to the SBABC3 run."""
+    par = regular(workloads.c2_params(300, 6, seed=4))
+    auto = engine.Plan(par, 365.0, 8760, flags=FULL)
+    sb = engine.Plan(par, 365.0, 8760, flags=FULL, scheme="sbabc3")
+    k = auto.substeps
+    assert (k < 0).sum() > 100 and (k > 0).sum() > 100 and np.array_equal(np.abs(k), sb.substeps)
+    a, b = engine.run(auto), engine.run(sb)
+    assert np.array_equal(a.n_tt, b.n_tt)
+    for sys_ in range(auto.B):
+        for j in range(2):
+            x, y = a.tt_of(sys_, j), b.tt_of(sys_, j)
+            if k[sys_] > 0:
+                assert np.array_equal(x, y) and a.mean_e[sys_ * 2 + j] == b.mean_e[sys_ * 2 + j]
+            elif len(x):
+                assert np.abs(x - y).max() * 86400 < 0.05 * TOL_TT_S
+                assert abs(a.mean_a[sys_ * 2 + j] / b.mean_a[sys_ * 2 + j] - 1) < 1e-9
+                assert abs(a.mean_e[sys_ * 2 + j] - b.mean_e[sys_ * 2 + j]) < 1e-8 * max(b.mean_e[sys_ * 2 + j], 1e-4)
+    assert any(not np.array_equal(a.tt_of(s_, 0), b.tt_of(s_, 0)) for s_ in np.flatnonzero(k < 0)[:20])
+
+
 @pytest.mark.parametrize("n_planets", [2, 3, 4])
 def test_lanes_kernel_matches_thread_kernel(gpu_lib, n_planets):
     """One-planet-per-lane kernel (warp shuffles across bodies) vs one-system-per-thread kernel:
@@ -289,6 +312,9 @@ def test_lanes_kernel_matches_thread_kernel(gpu_lib, n_planets):
     for lanes in (len(par), 7):
         plan = engine.Plan(par, 120.0, 2881, flags=flags, lanes=lanes)
         assert plan.cfg.lanes_systems == lanes
+        # default scheme: both compositions present, so the lanes kernel runs one launch per scheme and
+        # (lanes = 7) the thread kernel both in one launch
+        assert 0 < plan.cfg.alt_systems < len(par) and plan.cfg.alt_systems == (plan.substeps < 0).sum()
         got = engine.run(plan)
         assert np.array_equal(got.n_tt, ref.n_tt) and np.array_equal(got.status, ref.status)
         assert np.nanmax(np.abs(got.tt - ref.tt)) * 86400 < 1e-6
