@@ -128,6 +128,10 @@ def main():
             timed(par, 30.0, 721, _abi.F_MEANS | _abi.F_MEAN_OMEGA, substeps=1)
         elif c == "c5":
             timed(workloads.c5_params(65536), 30.0, 721, _abi.F_MEANS)
+        elif c == "c5lanes":     # the same on the one-planet-per-lane kernel
+            timed(workloads.c5_params(65536), 30.0, 721, _abi.F_MEANS, lanes=65536)
+        elif c == "c1biglanes":
+            timed(workloads.c1_params(227328), 30.0, 721, 0, substeps=1, lanes=227328)
         elif c == "c3":
             par, meta = workloads.c3_params(5000)
             timed(par, meta["ndays"], meta["noutputs"], _abi.F_PLANET1_ONLY, reps=3)
