@@ -195,12 +195,25 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """One process per GPU: run on the CPUs next to this rank's GPU, so that the pinned staging buffers
+    (first touch) and the 340 MB of D2H per step stay on the GPU's own socket.  Returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(gpu_index))
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from nbody_ai_b200 import _abi, engine, workloads
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -208,7 +221,15 @@ def run_ours(args, rank, world, local_rank):
     lib = _abi.load()
     dev = torch.device("cuda", local_rank)
 
-    params = workloads.c2_params(args.draws, args.omegas, seed=rank)
+    if world > 1:
+        # one global batch (a C2 draw per rank's worth of seeds), sharded by system with equal cost per rank:
+        # systems sorted by the planner's stage count are dealt to the ranks in snake order
+        everyone = np.concatenate([workloads.c2_params(args.draws, args.omegas, seed=r) for r in range(world)])
+        mine = engine.shard_balanced(engine.system_cost(everyone, N_DAYS, N_OUTPUTS), rank, world)
+        params = everyone[mine]
+        del everyone
+    else:
+        params = workloads.c2_params(args.draws, args.omegas, seed=0)
     B, Np = params.shape[0], params.shape[1] - 1
     flags = _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC
     plan = engine.Plan(params, N_DAYS, N_OUTPUTS, flags=flags, device=local_rank)
@@ -273,9 +294,16 @@ def run_ours(args, rank, world, local_rank):
 
     t = torch.tensor([dev_ms, e2e_ms, stage_ms[0]], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(B), float(plan.n_steps), float(n_tt_total)], dtype=torch.float64, device=dev)
+    # per-rank view (diagnosis of the max-over-ranks figure): step time, e2e time, SM clock, power-cap flag
+    mine = torch.tensor([dev_ms / args.steps, e2e_ms / args.steps, clocks["sm_mhz"] or 0.0,
+                         1.0 if "sw_power_cap" in clocks["reasons"] else 0.0], dtype=torch.float64, device=dev)
+    per_rank = [mine]
     if dist is not None:
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(per_rank, mine)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    per_rank = [[round(float(x), 3) for x in r.cpu()] for r in per_rank]
     dev_ms, e2e_ms, integ_ms = (float(x) for x in t.cpu())
     sims_all, steps_all, ntt_all = (float(x) for x in tot.cpu())
 
@@ -292,7 +320,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "systems_per_gpu": B, "draws": args.draws, "omega_variants": args.omegas,
                        "n_planets": Np, "n_days": N_DAYS, "n_outputs": N_OUTPUTS, "scheme": "auto: sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks); c4 (2-stage force-gradient) where P_min >= 220 output steps",
-                       "substeps_hist": np.bincount(np.abs(plan.substeps)).tolist(), "c4_systems": int((plan.substeps < 0).sum()), "parallelism": "shard-by-system x%d" % world,
+                       "substeps_hist": np.bincount(np.abs(plan.substeps)).tolist(), "c4_systems": int((plan.substeps < 0).sum()), "parallelism": "shard-by-system x%d%s" % (world, ", cost-balanced (engine.shard_balanced)" if world > 1 else ""), "cpu_affinity": affinity,
                        "l2": "256 MiB device fill between steps, outside the per-step event pairs"},
             "system_steps_per_s": steps_per_s,
             "system_steps_per_step": steps_all,
@@ -309,6 +337,7 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": 3 * args.steps,   # k_integrate, k_fit, k_ls_oc
             "clocks": clocks,
+            "ranks": {"columns": ["ms_per_step", "e2e_ms_per_step", "sm_mhz", "sw_power_cap"], "rows": per_rank},
         }
         if world == 1 and not args.no_cpu:
             n_s = min(args.cpu_sample, B)

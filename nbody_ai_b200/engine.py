@@ -230,17 +230,53 @@ def shard_range(n_systems, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_results(local, n_systems, group=None):
+def system_cost(params, n_days, n_outputs, scheme=SCHEME_AUTO):
+    """Relative integration cost of every system of a batch: Kepler-drift stages per output interval under
+    the planner's sub-step rule (3 per SBABC3 step, 2 per C4 step, ...) plus one for the per-sample work."""
+    lib = _abi.load()
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    B, N = params.shape[0], params.shape[1]
+    if isinstance(scheme, str):
+        scheme = SCHEMES[scheme]
+    cfg = _abi.make_config(B, N, n_days, n_outputs, substeps=0, scheme=scheme)
+    k = np.zeros(B, dtype=np.int32)
+    _abi.check(lib.nbt_plan_substeps(C.byref(cfg), _abi.ptr(params), _abi.ptr(k, C.c_int32)), lib)
+    stages = {0: 1, 1: 3, 2: 4, 3: 4, 4: 2, 5: 3, 6: 3}[int(scheme)]
+    return np.where(k < 0, -2.0 * k, float(stages) * k) + 1.0
+
+
+def shard_balanced(cost, rank, world_size):
+    """Cost-balanced shard of a batch: systems sorted by decreasing cost are dealt to the ranks in
+    snake order (0..W-1, W-1..0, ...), so that every rank gets the same count (+-1) and the same mix of
+    long and short systems.  Returns the sorted indices owned by `rank`; pass them to gather_results."""
+    cost = np.asarray(cost, dtype=np.float64)
+    order = np.argsort(-cost, kind="stable")
+    pos = np.arange(len(order))
+    lap, slot = np.divmod(pos, int(world_size))
+    owner = np.where(lap % 2 == 0, slot, int(world_size) - 1 - slot)
+    return np.sort(order[owner == int(rank)])
+
+
+def gather_results(local, n_systems, group=None, index=None):
     """Final host gather of per-rank result dicts (arrays whose first axis is the local system
-    index) onto every rank, via torch.distributed.all_gather_object (gloo or nccl groups)."""
+    index) onto every rank, via torch.distributed.all_gather_object (gloo or nccl groups).
+    index: the global indices of this rank's systems (shard_balanced); None = contiguous shards in
+    rank order (shard_range)."""
     import torch.distributed as dist
     ws = dist.get_world_size(group)
     parts = [None] * ws
-    dist.all_gather_object(parts, local, group=group)
+    dist.all_gather_object(parts, (local, None if index is None else np.asarray(index)), group=group)
     out = {}
     for k in local:
-        out[k] = np.concatenate([p[k] for p in parts], axis=0)
-        assert out[k].shape[0] == n_systems
+        cat = np.concatenate([p[0][k] for p in parts], axis=0)
+        assert cat.shape[0] == n_systems
+        if index is not None:
+            where = np.concatenate([p[1] for p in parts])
+            assert np.array_equal(np.sort(where), np.arange(n_systems))
+            full = np.empty_like(cat)
+            full[where] = cat
+            cat = full
+        out[k] = cat
     return out
 
 

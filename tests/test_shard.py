@@ -25,6 +25,25 @@ def test_shard_range_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_balanced_partition(built):
+    """Cost-balanced shards: a partition with equal counts (+-1) and near-equal cost, heavy systems spread."""
+    par = workloads.c2_params(400, 6, seed=5)
+    cost = engine.system_cost(par, 365.0, 8760)
+    assert cost.min() >= 3.0 and cost.max() >= 7.0          # C4 systems (2 + 1) ... several SBABC3 steps per hour
+    for ws in (1, 2, 3, 8):
+        parts = [engine.shard_balanced(cost, r, ws) for r in range(ws)]
+        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(len(par)))
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1 and all(np.all(np.diff(p) > 0) for p in parts)
+        tot = np.array([cost[p].sum() for p in parts])
+        assert tot.max() / tot.min() < 1.01
+        heavy = np.array([(cost[p] >= 7.0).sum() for p in parts])
+        assert heavy.max() - heavy.min() <= 1
+    # contiguous shards of the same batch are visibly less even
+    tot = np.array([cost[slice(*engine.shard_range(len(par), r, 8))].sum() for r in range(8)])
+    assert tot.max() / tot.min() > 1.01
+
+
 def _host_products(par):
     hs = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
     plan = engine.Plan(par, 40.0, 961, substeps=1, flags=_abi.F_MEANS)
@@ -45,8 +64,11 @@ def _worker(rank, world, port, q):
     lo, hi = engine.shard_range(len(par), rank, world)
     local = _host_products(par[lo:hi])
     full = engine.gather_results(local, len(par))
+    # the same with cost-balanced (non-contiguous) shards
+    mine = engine.shard_balanced(engine.system_cost(par, 40.0, 961), rank, world)
+    full_b = engine.gather_results(_host_products(par[mine]), len(par), index=mine)
     if rank == 0:
-        q.put({k: v for k, v in full.items()})
+        q.put(({k: v for k, v in full.items()}, {k: v for k, v in full_b.items()}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,10 +80,11 @@ def test_two_rank_shard_and_gather(built):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=180)
+    got, got_balanced = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     want = _host_products(workloads.c2_params(3, 2, seed=21))
     for k in want:
         assert np.array_equal(got[k], want[k], equal_nan=True), k
+        assert np.array_equal(got_balanced[k], want[k], equal_nan=True), k
