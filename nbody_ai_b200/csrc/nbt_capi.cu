@@ -1172,7 +1172,7 @@ int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* s
     std::iota(order, order + B, 0);
     // key 1: sub-steps, heaviest first (blocks are dispatched in index order, so the long
     // systems start first and a warp's lanes run equal trip counts);
-    // key 2: Hill-unstable systems first within a group, so that the lanes that may break or
+    // key 2: Hill-unstable systems first within a group, so that the lanes that may break (and stop) or
     // fall back to the slow Kepler path share warps instead of each stalling a healthy warp.
     std::vector<uint8_t> unstable(params ? B : 0);
     if (params)
@@ -1185,6 +1185,29 @@ int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* s
         if (params && unstable[a] != unstable[b]) return unstable[a] > unstable[b];
         return false;
     });
+    // The multi-step groups (k >= 2) are the critical path of a launch, and a warp's slow-path excursions
+    // add up over its lanes (measured: 32 unstable k = 3 systems in one warp run 73 ms, each alone 51 ms, a
+    // warp of stable ones 53 ms): there the unstable systems are spread evenly over the group's warps instead.
+    if (params && substeps) {
+        std::vector<int32_t> tmp;
+        for (int g0 = 0; g0 < B;) {
+            const int k = substeps[order[g0]];
+            int g1 = g0;
+            while (g1 < B && substeps[order[g1]] == k) g1++;
+            int u = 0;
+            while (g0 + u < g1 && unstable[order[g0 + u]]) u++;
+            const int n = g1 - g0, s = n - u;
+            if (k >= 2 && u > 0 && s > 0) {
+                tmp.assign(order + g0, order + g1);
+                int iu = 0, is = 0;
+                for (int p = 0; p < n; p++) {
+                    const bool take_u = (long long)(p + 1) * u / n > (long long)p * u / n;
+                    order[g0 + p] = take_u ? tmp[iu++] : tmp[u + is++];
+                }
+            }
+            g0 = g1;
+        }
+    }
     int nalt = 0;
     if (substeps)
         for (int b = 0; b < B; b++) nalt += substeps[b] < 0 ? 1 : 0;
