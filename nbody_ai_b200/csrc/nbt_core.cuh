@@ -526,7 +526,26 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
     }
     for (int st = 0; st < sc.S; st++) {
         const double h = sc.a[st] * dt;
-        if (LAT && NP <= 2) {   // branch-free drifts in one basic block, rare failures redone afterwards
+        if (NP >= 3) {   // branch-free drifts two planets at a time (one basic block per pair), failures redone
+#pragma unroll
+            for (int i0 = 0; i0 < NP; i0 += 2) {
+                bool ok[2] = {true, true};
+#pragma unroll
+                for (int q = 0; q < 2; q++)
+                    if (i0 + q < NP) {
+                        const int i = i0 + q;
+                        ok[q] = nbt_kepler_drift_fast(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i]);
+                    }
+                if (!(ok[0] && ok[1])) {
+#pragma unroll
+                    for (int q = 0; q < 2; q++)
+                        if (i0 + q < NP && !ok[q]) {
+                            const int i = i0 + q;
+                            nbt_kepler_drift<true>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
+                        }
+                }
+            }
+        } else if (LAT && NP <= 2) {   // branch-free drifts in one basic block, rare failures redone afterwards
             bool ok[NP], all_ok = true;
 #pragma unroll
             for (int i = 0; i < NP; i++) {
@@ -541,7 +560,7 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
         } else {
 #pragma unroll
             for (int i = 0; i < NP; i++)
-                nbt_kepler_drift<(NP <= 2)>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
+                nbt_kepler_drift<(NP <= 2 || NP >= 4)>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
         }
         nbt_accel_grad<NP>(s, c, sc.g[st + 1] * dt * dt, ax, ay, az);
         const double kb = sc.b[st + 1] * dt;
