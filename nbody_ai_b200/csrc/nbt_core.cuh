@@ -680,6 +680,42 @@ NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, doub
     return o;
 }
 
+// Branch-free a, e, inc (and omega) for the common case — a near edge-on, non-circular orbit — with the same
+// arithmetic as nbt_elements; returns whether that case holds (else the caller redoes the sample through
+// nbt_elements).  With no branch inside, the element chains of two planets interleave (the sampling work is
+// a quarter of the bench step and otherwise runs at ILP 1).
+template <bool OMEGA>
+NBT_HD bool nbt_elements_fast(double mu, double x, double y, double z, double vx, double vy, double vz,
+                              double ir, double& a, double& e, double& inc, double& omega) {
+    const double hx = y * vz - z * vy, hy = z * vx - x * vz, hz = x * vy - y * vx;
+    const double h2 = fma(hx, hx, fma(hy, hy, hz * hz));
+    const double v2 = fma(vx, vx, fma(vy, vy, vz * vz));
+    const double ih = nbt_rsqrt(h2);
+    const double vc2 = mu * ir;
+    a = -mu * nbt_rcp(v2 - 2.0 * vc2);
+    const double rv = fma(x, vx, fma(y, vy, z * vz));
+    const double vd2 = v2 - vc2;
+    const double imu = nbt_rcp(mu);
+    const double ex = imu * (vd2 * x - rv * vx), ey = imu * (vd2 * y - rv * vy), ez = imu * (vd2 * z - rv * vz);
+    const double e2 = fma(ex, ex, fma(ey, ey, ez * ez));
+    e = e2 * nbt_rsqrt(e2);
+    const double ci = hz * ih;
+    const double c2 = ci * ci;
+    const double p = fma(c2, fma(c2, fma(c2, fma(c2, 35.0 / 1152.0, 15.0 / 336.0), 3.0 / 40.0), 1.0 / 6.0), 1.0);
+    inc = fma(-ci, p, 0.5 * NBT_PI);
+    bool ok = fabs(ci) < 0.03 && h2 > 0.0 && e2 > 1e-16;
+    omega = 0.0;
+    if (OMEGA) {
+        const double nx = -hy, ny = hx, n2 = nx * nx + ny * ny;
+        const double den2 = n2 * e2;
+        const double cth = (nx * ex + ny * ey) * nbt_rsqrt(den2);
+        ok = ok && den2 > 0.0 && cth > -1.0 && cth < 1.0;
+        const double val = nbt_acos(cth);
+        omega = (ez < 0.0) ? -val : val;
+    }
+    return ok;
+}
+
 // Mid-transit time inside one output interval.  GRID_LINEAR: the reference's find_zero
 // (nbody/tools.py:61-65).  REFINED: Newton on the cubic Hermite interpolant of dx over the interval.
 // Out of line: it runs once per transit, and inlining it per planet bloats the sampling loop.
@@ -798,7 +834,38 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, const nbt_scheme& sc, int
         for (int j = 0; j < NP; j++) { dx_prev[j] = dx[j]; dvx_prev[j] = dvx[j]; }
         xs_prev = xs; t_prev = t;
 
-        if (want_means && !want_series) {
+        if (LAT && NP == 2 && want_means && !want_series) {
+            // both planets' element chains in one basic block (nbt_elements_fast), rare cases redone
+            double ea[NP], ee[NP], ei[NP], eo[NP];
+            bool ok[NP], all_ok = true;
+            if (want_omega) {
+#pragma unroll
+                for (int j = 0; j < NP; j++) {
+                    ok[j] = nbt_elements_fast<true>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.ir[j], ea[j], ee[j], ei[j], eo[j]);
+                    all_ok = all_ok && ok[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NP; j++) {
+                    ok[j] = nbt_elements_fast<false>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.ir[j], ea[j], ee[j], ei[j], eo[j]);
+                    all_ok = all_ok && ok[j];
+                }
+            }
+            if (!all_ok) {
+#pragma unroll
+                for (int j = 0; j < NP; j++)
+                    if (!ok[j]) {
+                        const nbt_orbit ob = want_omega ? nbt_elements<1>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.r[j], s.ir[j])
+                                                        : nbt_elements<0>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.r[j], s.ir[j]);
+                        ea[j] = ob.a; ee[j] = ob.e; ei[j] = ob.inc; eo[j] = ob.omega;
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                sum_a[j] += ea[j]; sum_e[j] += ee[j]; sum_i[j] += ei[j]; sum_o[j] += eo[j];
+                if (!(ea[j] > 0.0)) status |= NBT_S_UNBOUND;
+            }
+        } else if (want_means && !want_series) {
             if (want_omega) {
 #pragma unroll
                 for (int j = 0; j < NP; j++) {
