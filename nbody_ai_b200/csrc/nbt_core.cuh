@@ -27,6 +27,9 @@
 
 #define NBT_PI 3.14159265358979323846264338327950288
 #define NBT_MAX_STAGES 8
+#ifndef NBT_FAST_ELEMENTS
+#define NBT_FAST_ELEMENTS(NP, LAT) ((NP) >= 2)   /* which kernels sample the elements through nbt_elements_fast */
+#endif
 #define NBT_C4_GRAD (1.0 / 24.0)  /* displacement coefficient of the gradient kick of NBT_SCHEME_C4 */
 
 // ---------------------------------------------------------------------------------------------
@@ -834,36 +837,44 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, const nbt_scheme& sc, int
         for (int j = 0; j < NP; j++) { dx_prev[j] = dx[j]; dvx_prev[j] = dvx[j]; }
         xs_prev = xs; t_prev = t;
 
-        if (LAT && NP == 2 && want_means && !want_series) {
-            // both planets' element chains in one basic block (nbt_elements_fast), rare cases redone
-            double ea[NP], ee[NP], ei[NP], eo[NP];
-            bool ok[NP], all_ok = true;
-            if (want_omega) {
+        if (NBT_FAST_ELEMENTS(NP, LAT) && want_means && !want_series) {
+            // the element chains of two planets at a time in one basic block (nbt_elements_fast), rare cases redone
 #pragma unroll
-                for (int j = 0; j < NP; j++) {
-                    ok[j] = nbt_elements_fast<true>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.ir[j], ea[j], ee[j], ei[j], eo[j]);
-                    all_ok = all_ok && ok[j];
+            for (int j0 = 0; j0 < NP; j0 += 2) {
+                double ea[2], ee[2], ei[2], eo[2];
+                bool ok[2] = {true, true};
+                if (want_omega) {
+#pragma unroll
+                    for (int q = 0; q < 2; q++)
+                        if (j0 + q < NP) {
+                            const int j = j0 + q;
+                            ok[q] = nbt_elements_fast<true>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.ir[j], ea[q], ee[q], ei[q], eo[q]);
+                        }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 2; q++)
+                        if (j0 + q < NP) {
+                            const int j = j0 + q;
+                            ok[q] = nbt_elements_fast<false>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.ir[j], ea[q], ee[q], ei[q], eo[q]);
+                        }
                 }
-            } else {
+                if (!(ok[0] && ok[1])) {
 #pragma unroll
-                for (int j = 0; j < NP; j++) {
-                    ok[j] = nbt_elements_fast<false>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.ir[j], ea[j], ee[j], ei[j], eo[j]);
-                    all_ok = all_ok && ok[j];
+                    for (int q = 0; q < 2; q++)
+                        if (j0 + q < NP && !ok[q]) {
+                            const int j = j0 + q;
+                            const nbt_orbit ob = want_omega ? nbt_elements<1>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.r[j], s.ir[j])
+                                                            : nbt_elements<0>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.r[j], s.ir[j]);
+                            ea[q] = ob.a; ee[q] = ob.e; ei[q] = ob.inc; eo[q] = ob.omega;
+                        }
                 }
-            }
-            if (!all_ok) {
 #pragma unroll
-                for (int j = 0; j < NP; j++)
-                    if (!ok[j]) {
-                        const nbt_orbit ob = want_omega ? nbt_elements<1>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.r[j], s.ir[j])
-                                                        : nbt_elements<0>(c.GM[j], s.x[j], s.y[j], s.z[j], s.vx[j], s.vy[j], s.vz[j], s.r[j], s.ir[j]);
-                        ea[j] = ob.a; ee[j] = ob.e; ei[j] = ob.inc; eo[j] = ob.omega;
+                for (int q = 0; q < 2; q++)
+                    if (j0 + q < NP) {
+                        const int j = j0 + q;
+                        sum_a[j] += ea[q]; sum_e[j] += ee[q]; sum_i[j] += ei[q]; sum_o[j] += eo[q];
+                        if (!(ea[q] > 0.0)) status |= NBT_S_UNBOUND;
                     }
-            }
-#pragma unroll
-            for (int j = 0; j < NP; j++) {
-                sum_a[j] += ea[j]; sum_e[j] += ee[j]; sum_i[j] += ei[j]; sum_o[j] += eo[j];
-                if (!(ea[j] > 0.0)) status |= NBT_S_UNBOUND;
             }
         } else if (want_means && !want_series) {
             if (want_omega) {
