@@ -268,15 +268,16 @@ __device__ __noinline__ double ls_power_uniform_sum(const double* __restrict__ y
 // pair instead of 11.  Where a denominator is small (nu within 1.6e-4 of a multiple of 1/2: the exact
 // Nyquist frequency of integer epochs, whose sine term must cancel to round-off) the sums are summed.
 __device__ double ls_power_uniform(const double* __restrict__ y, int n, double ybar, double YY, double nu) {
-    double sd, cd, sh, ch;
-    sincospi(2.0 * nu, &sd, &cd);
-    sincospi(nu, &sh, &ch);
-    if (fabs(sd) < 1e-3 || fabs(sh) < 1e-3) return ls_power_uniform_sum(y, n, ybar, YY, nu);
+    // two sincospi calls; the double angles and the angles n w / 2, n w by the addition formulas
+    double sh, ch, sm, cm;
     const double dn = (double)n, dm = (double)(n - 1);
-    double sm, cm, sm2, cm2;
+    sincospi(nu, &sh, &ch);               // w / 2
     sincospi(dm * nu, &sm, &cm);          // phase (n-1) w / 2
-    sincospi(2.0 * dm * nu, &sm2, &cm2);  // the same for 2 w
-    const double D = sinpi(dn * nu) / sh, D2 = sinpi(2.0 * dn * nu) / sd;
+    const double sd = 2.0 * sh * ch, cd = fma(-2.0 * sh, sh, 1.0);        // w
+    if (fabs(sd) < 1e-3 || fabs(sh) < 1e-3) return ls_power_uniform_sum(y, n, ybar, YY, nu);
+    const double sm2 = 2.0 * sm * cm, cm2 = fma(-2.0 * sm, sm, 1.0);      // (n-1) w
+    const double sn = fma(sm, ch, cm * sh), cn_ = fma(cm, ch, -sm * sh);   // n w / 2
+    const double D = sn / sh, D2 = (2.0 * sn * cn_) / sd;
     const double C = cm * D, S = sm * D, C2 = cm2 * D2, S2 = 0.5 * (sm2 * D2);
     double YC = 0, YS = 0;
     for (int i0 = 0; i0 < n; i0 += NBT_LS_RESYNC) {
