@@ -330,11 +330,18 @@ struct nbt_lsoc_args {
     double* power; int32_t* nfreq;
     int32_t B, Np, flags, spp;
     int32_t w0, w1;   // (system, planet) series [w0, w1) of this launch
+    int32_t nchunk;   // warps per series: warp c takes the frequency chunks c, c + nchunk, ... (NBT_LS_FCHUNK each)
     double fmin, fmax;
 };
 
+// A series of n transits has ~4.9 n frequencies and costs ~n^2: one warp per series leaves the longest
+// series (456 transits, 2250 frequencies) as a tail of their own, so a series is cut into chunks of
+// NBT_LS_FCHUNK frequencies that separate warps take (nchunk of them per series; the surplus warps of a
+// short series exit at once).
+#define NBT_LS_FCHUNK 256
 __global__ void __launch_bounds__(128) k_ls_oc(const nbt_lsoc_args L) {
-    const int w = L.w0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const long long id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int w = L.w0 + (int)(id / L.nchunk), c0 = (int)(id % L.nchunk);
     const int lane = threadIdx.x & 31;
     if (w >= L.w1) return;
     const int j = w % L.Np;
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(128) k_ls_oc(const nbt_lsoc_args L) {
     const int cap = (int)(L.tt_offsets[w + 1] - off);
     const int n = min(L.n_tt[w], cap);
     if (n < 3 || ((L.flags & NBT_F_PLANET1_ONLY) && j > 0)) {
-        if (lane == 0) L.nfreq[w] = 0;
+        if (lane == 0 && c0 == 0) L.nfreq[w] = 0;
         return;
     }
     const int64_t loff = L.ls_offsets[w];
@@ -350,13 +357,17 @@ __global__ void __launch_bounds__(128) k_ls_oc(const nbt_lsoc_args L) {
     const double T = (double)(n - 1); // epochs = arange(n)
     long long nf = ls_nfreq(T, L.fmin, L.fmax, L.spp);
     if (nf > lcap) nf = lcap;
+    if (lane == 0 && c0 == 0) L.nfreq[w] = (int32_t)nf;
+    if ((long long)c0 * NBT_LS_FCHUNK >= nf) return;
     const double df = ls_df(T, L.spp);
     const double* y = L.ttv + off;
     double ybar, YY;
     warp_mean_var(y, n, lane, ybar, YY);
-    for (long long k = lane; k < nf; k += 32)
-        L.power[loff + k] = ls_power_uniform(y, n, ybar, YY, L.fmin + (double)k * df);
-    if (lane == 0) L.nfreq[w] = (int32_t)nf;
+    for (long long k0 = (long long)c0 * NBT_LS_FCHUNK; k0 < nf; k0 += (long long)L.nchunk * NBT_LS_FCHUNK) {
+        const long long k1 = min(nf, k0 + NBT_LS_FCHUNK);
+        for (long long k = k0 + lane; k < k1; k += 32)
+            L.power[loff + k] = ls_power_uniform(y, n, ybar, YY, L.fmin + (double)k * df);
+    }
 }
 
 // generic batched periodogram: one warp per (series, chunk of 32 frequencies)
@@ -1070,6 +1081,13 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         L.spp = cfg->ls_samples_per_peak; L.fmin = cfg->ls_oc_minfreq; L.fmax = cfg->ls_oc_maxfreq;
         // host path: a few launches over ranges of series, an event after each, so that the periodograms of one
         // range go back to the host while the next range is computed (ls_bounds[0..n_ls_chunks])
+        // warps per series from the largest transit capacity (cfg.tt_cap_max; unknown = 1, the warp loops)
+        {
+            const long long nf_max = cfg->tt_cap_max >= 3
+                ? nbt_ls_nfreq((double)(cfg->tt_cap_max - 1), cfg->ls_oc_minfreq, cfg->ls_oc_maxfreq, cfg->ls_samples_per_peak) : 0;
+            long long nch = (nf_max + NBT_LS_FCHUNK - 1) / NBT_LS_FCHUNK;
+            L.nchunk = (int32_t)std::min<long long>(std::max<long long>(nch, 1), 16);
+        }
         const int32_t whole[2] = {0, (int32_t)nw};
         const int nc = (n_ls_chunks > 0 && ls_bounds && ls_events) ? n_ls_chunks : 1;
         const int32_t* bounds = nc == n_ls_chunks && ls_bounds ? ls_bounds : whole;
@@ -1084,7 +1102,7 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
             cudaStream_t ls = (piped && (c & 1)) ? side->st[1] : st;
             L.w0 = bounds[c]; L.w1 = bounds[c + 1];
             if (L.w1 > L.w0) {
-                k_ls_oc<<<(int)(((long long)(L.w1 - L.w0) * 32 + 127) / 128), 128, 0, ls>>>(L);
+                k_ls_oc<<<(unsigned)(((long long)(L.w1 - L.w0) * L.nchunk * 32 + 127) / 128), 128, 0, ls>>>(L);
                 if ((e = cudaGetLastError()) != cudaSuccess) return e;
             }
             if (nc > 1 && (e = cudaEventRecord(ls_events[c], ls)) != cudaSuccess) return e;
@@ -1411,7 +1429,13 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
                 ls_bounds[c] = (int32_t)(std::lower_bound(in->ls_offsets, in->ls_offsets + nsp, nls * c / n_ls) - in->ls_offsets);
             for (int c = 0; c < n_ls; c++) NBT_CUDA(cudaEventCreateWithFlags(&ev_ls[c], cudaEventDisableTiming));
         }
-        NBT_CUDA(enqueue_path(cfg, &din, &dout, (double*)dp(b_rvws), st, scan ? (const double*)dp(b_ser) : nullptr,
+        nbt_config hcfg = *cfg;
+        if (hcfg.tt_cap_max <= 0) {   // derive the largest per-planet capacity from the host offsets
+            int64_t cm = 1;
+            for (int64_t i = 0; i < nsp; i++) cm = std::max(cm, in->tt_offsets[i + 1] - in->tt_offsets[i]);
+            hcfg.tt_cap_max = (int32_t)std::min<int64_t>(cm, INT32_MAX);
+        }
+        NBT_CUDA(enqueue_path(&hcfg, &din, &dout, (double*)dp(b_rvws), st, scan ? (const double*)dp(b_ser) : nullptr,
                               (const double*)dp(b_times), scan_dt, ev_fit, n_ls, ls_bounds, ev_ls));
         // products that are final after k_fit go back on the side stream, overlapping k_ls_oc / the RV stages
         Buf* early[] = {&b_tt, &b_ttv, &b_ntt, &b_per, &b_t0, &b_max, &b_ma, &b_me, &b_mi, &b_mo, &b_stat, &b_orb, &b_ser};
