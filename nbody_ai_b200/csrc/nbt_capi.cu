@@ -72,18 +72,36 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
-// k-th smallest (0-based) of |x[0..n)| by bisection on the IEEE bit pattern (monotone for
-// non-negative doubles): 63 warp-wide counting passes, no scratch memory, no sort.
-__device__ double warp_kth_abs(const double* x, int n, int k, int lane) {
+// k-th and (k+1)-th smallest (0-based) of |x[0..n)| by bisection on the IEEE bit pattern (monotone for
+// non-negative doubles): 63 warp-wide counting passes, no scratch memory, no sort.  The first 64 values
+// live in registers (a transit series is ~37 long) and a count is one ballot + popc per 32 values; the
+// (k+1)-th follows from the k-th in one more pass (a duplicate of it, or the smallest larger value).
+__device__ double warp_kth_abs(const double* x, int n, int k, int lane, double& next) {
+    const unsigned long long PAD = ~0ull;   // above every candidate
+    const unsigned long long a0 = (lane < n) ? (unsigned long long)__double_as_longlong(fabs(x[lane])) : PAD;
+    const unsigned long long a1 = (lane + 32 < n) ? (unsigned long long)__double_as_longlong(fabs(x[lane + 32])) : PAD;
     unsigned long long ans = 0ull;
     for (int bit = 62; bit >= 0; bit--) {
         const unsigned long long cand = ans | (1ull << bit);
-        int c = 0;
-        for (int i = lane; i < n; i += 32)
-            c += ((unsigned long long)__double_as_longlong(fabs(x[i])) < cand) ? 1 : 0;
-        c = warp_sum_i(c);
+        int c = __popc(__ballot_sync(0xffffffffu, a0 < cand)) + __popc(__ballot_sync(0xffffffffu, a1 < cand));
+        for (int i0 = 64; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            c += __popc(__ballot_sync(0xffffffffu, i < n && (unsigned long long)__double_as_longlong(fabs(x[i])) < cand));
+        }
         if (c <= k) ans = cand;
     }
+    // (k+1)-th: values <= ans number at least k + 1; one more of them means a duplicate
+    int le = __popc(__ballot_sync(0xffffffffu, a0 <= ans)) + __popc(__ballot_sync(0xffffffffu, a1 <= ans));
+    unsigned long long up = min(a0 > ans ? a0 : PAD, a1 > ans ? a1 : PAD);
+    for (int i0 = 64; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const unsigned long long v = (i < n) ? (unsigned long long)__double_as_longlong(fabs(x[i])) : PAD;
+        le += __popc(__ballot_sync(0xffffffffu, v <= ans));
+        up = min(up, v > ans ? v : PAD);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) up = min(up, __shfl_xor_sync(0xffffffffu, up, o));
+    next = __longlong_as_double((long long)((le >= k + 2) ? ans : up));
     return __longlong_as_double((long long)ans);
 }
 
@@ -95,12 +113,9 @@ __device__ double warp_maxavg(const double* x, int n, int lane) {
     const double pos = 0.75 * (double)(n - 1);
     const int lo = (int)floor(pos);
     const double frac = pos - (double)lo;
-    const double vlo = warp_kth_abs(x, n, lo, lane);
-    double p75 = vlo;
-    if (lo + 1 < n) {
-        const double vhi = warp_kth_abs(x, n, lo + 1, lane);
-        p75 = vlo + (vhi - vlo) * frac;
-    }
+    double vhi;
+    const double vlo = warp_kth_abs(x, n, lo, lane, vhi);
+    const double p75 = (lo + 1 < n) ? vlo + (vhi - vlo) * frac : vlo;
     return 0.5 * (p75 + mx);
 }
 
@@ -569,9 +584,9 @@ __device__ double warp_percentile_abs(const double* x, int n, double q, int lane
     const double pos = q * (double)(n - 1);
     const int lo = (int)floor(pos);
     const double frac = pos - (double)lo;
-    const double vlo = warp_kth_abs(x, n, lo, lane);
+    double vhi;
+    const double vlo = warp_kth_abs(x, n, lo, lane, vhi);
     if (lo + 1 >= n) return vlo;
-    const double vhi = warp_kth_abs(x, n, lo + 1, lane);
     return vlo + (vhi - vlo) * frac;
 }
 
