@@ -27,6 +27,9 @@
 
 #define NBT_PI 3.14159265358979323846264338327950288
 #define NBT_MAX_STAGES 8
+#ifndef NBT_DRIFT_GROUP
+#define NBT_DRIFT_GROUP(NP) ((NP) == 3 ? 3 : 2)   /* planets whose branch-free Kepler solves share a basic block */
+#endif
 #ifndef NBT_FAST_ELEMENTS
 #define NBT_FAST_ELEMENTS(NP, LAT) ((NP) >= 2)   /* which kernels sample the elements through nbt_elements_fast */
 #endif
@@ -529,19 +532,24 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
     }
     for (int st = 0; st < sc.S; st++) {
         const double h = sc.a[st] * dt;
-        if (NP >= 3) {   // branch-free drifts two planets at a time (one basic block per pair), failures redone
+        if (NP >= 3) {   // branch-free drifts NBT_DRIFT_GROUP planets at a time (one basic block each), failures redone
+            constexpr int GR = NBT_DRIFT_GROUP(NP);
 #pragma unroll
-            for (int i0 = 0; i0 < NP; i0 += 2) {
-                bool ok[2] = {true, true};
+            for (int i0 = 0; i0 < NP; i0 += GR) {
+                bool ok[GR];
+                bool all_ok = true;
 #pragma unroll
-                for (int q = 0; q < 2; q++)
+                for (int q = 0; q < GR; q++) {
+                    ok[q] = true;
                     if (i0 + q < NP) {
                         const int i = i0 + q;
                         ok[q] = nbt_kepler_drift_fast(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i]);
                     }
-                if (!(ok[0] && ok[1])) {
+                    all_ok = all_ok && ok[q];
+                }
+                if (!all_ok) {
 #pragma unroll
-                    for (int q = 0; q < 2; q++)
+                    for (int q = 0; q < GR; q++)
                         if (i0 + q < NP && !ok[q]) {
                             const int i = i0 + q;
                             nbt_kepler_drift<true>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
