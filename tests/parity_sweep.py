@@ -26,6 +26,22 @@ def hill_separation(par):
     return d
 
 
+def oracle_is_chaotic(par_b, n_days, n_outputs):
+    """The calibration's regularity test (tests/calibrate_substeps.py:is_regular): the oracle's own
+    answer must not move by more than 0.01 s in a transit time or 1e-9 in a mean eccentricity when P1 changes
+    by 1e-13 (relative).  A system that fails has no defined parity target."""
+    P = np.ascontiguousarray(par_b[None])
+    plan = engine.Plan(P, n_days, n_outputs, substeps=1, flags=_abi.F_MEANS)
+    a = engine.Buffers(plan); oracle.run(plan.cfg, P, a)
+    Q = P.copy(); Q[0, 1, 1] *= 1.0 + 1e-13
+    b = engine.Buffers(plan); oracle.run(plan.cfg, Q, b)
+    if not np.array_equal(a.n_tt, b.n_tt):
+        return True
+    dtt = max([np.abs(a.tt_of(0, j) - b.tt_of(0, j)).max() * 86400 for j in range(plan.Np) if a.n_transits(0, j)] + [0.0])
+    de = np.abs(a.mean_e - b.mean_e) / np.maximum(a.mean_e, 1e-4)
+    return bool(dtt > 1e-2 or de.max() > 1e-9)
+
+
 def sweep(par, n_days, n_outputs, label):
     flags = _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC
     plan = engine.Plan(par, n_days, n_outputs, flags=flags)
@@ -34,7 +50,7 @@ def sweep(par, n_days, n_outputs, label):
     t0 = time.time(); oracle.run(plan.cfg, plan.params, want); t_cpu = time.time() - t0
     delta = hill_separation(par)
     worst = dict(tt_s=0.0, oc_min=0.0, a_rel=0.0, e_rel=0.0, ls_power=0.0, ttv_max_min=0.0)
-    n_cmp = n_count_mismatch = 0
+    n_cmp = n_count_mismatch = n_chaotic = 0
     fails = []
     for b in range(plan.B):
         if delta[b] < 4.0 or (want.status[b] & (_abi.S_NONFINITE | _abi.S_UNBOUND | _abi.S_TT_OVERFLOW)):
@@ -56,13 +72,20 @@ def sweep(par, n_days, n_outputs, label):
                 w['ttv_max_min'] = max(w['ttv_max_min'], abs(got.ttv_max[sp] - want.ttv_max[sp]) * 1440)
             w['a_rel'] = max(w['a_rel'], abs(got.mean_a[sp] / want.mean_a[sp] - 1))
             w['e_rel'] = max(w['e_rel'], abs(got.mean_e[sp] - want.mean_e[sp]) / max(want.mean_e[sp], 1e-4))
+        # anything beyond a tenth of a tolerance is checked for regularity first: a chaotic system is excluded
+        if (w['tt_s'] > 0.1 or w['oc_min'] > 1e-4 or w['a_rel'] > 1e-9 or w['e_rel'] > 1e-9) and \
+                oracle_is_chaotic(par[b], n_days, n_outputs):
+            n_chaotic += 1
+            n_cmp -= 1
+            continue
         if w['tt_s'] > 1.0 or w['oc_min'] > 1e-3 or w['a_rel'] > 1e-8 or w['e_rel'] > 1e-8:
             fails.append(dict(system=int(b), hill_separation=float(delta[b]), P=par[b, 1:, 1].tolist(), **{k: float(v) for k, v in w.items()}))
         for k in worst:
             if np.isfinite(w[k]):
                 worst[k] = max(worst[k], w[k])
     return dict(label=label, n_systems=int(plan.B), n_planets=int(plan.Np), n_days=n_days, n_outputs=n_outputs,
-                compared=n_cmp, excluded_hill_unstable_or_broken=int(plan.B - n_cmp), transit_count_mismatches=n_count_mismatch,
+                compared=n_cmp, excluded_hill_unstable_or_broken=int(plan.B - n_cmp - n_chaotic),
+                excluded_chaotic_by_oracle_self_sensitivity=n_chaotic, transit_count_mismatches=n_count_mismatch,
                 outside_tolerance=len(fails), failures=fails[:10], worst={k: float(v) for k, v in worst.items()},
                 tolerances=dict(tt_s=1.0, oc_min=1e-3, a_rel=1e-8, e_rel=1e-8),
                 gpu_seconds_incl_copies=t_gpu, oracle_seconds=t_cpu, oracle_threads=oracle.max_threads())
