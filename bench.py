@@ -319,7 +319,7 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "systems_per_gpu": B, "draws": args.draws, "omega_variants": args.omegas,
-                       "n_planets": Np, "n_days": N_DAYS, "n_outputs": N_OUTPUTS, "scheme": "auto: sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks); c4 (2-stage force-gradient) where P_min >= 220 output steps",
+                       "n_planets": Np, "n_days": N_DAYS, "n_outputs": N_OUTPUTS, "scheme": "auto: sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks); c4 (2-stage force-gradient) where P_min >= 250 output steps",
                        "substeps_hist": np.bincount(np.abs(plan.substeps)).tolist(), "c4_systems": int((plan.substeps < 0).sum()), "parallelism": "shard-by-system x%d%s" % (world, ", cost-balanced (engine.shard_balanced)" if world > 1 else ""), "cpu_affinity": affinity,
                        "l2": "256 MiB device fill between steps, outside the per-step event pairs"},
             "system_steps_per_s": steps_per_s,

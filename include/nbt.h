@@ -54,7 +54,7 @@ enum { NBT_SCHEME_WH2 = 0,   /* kick-drift-kick leapfrog */
                                  the accuracy of M64 with three Kepler drifts per step (the default) */
        NBT_SCHEME_COUNT = 6,
        NBT_SCHEME_AUTO = 6 }; /* SBABC3, except that systems resolved finely enough by the output grid itself
-                                 (P_min >= 220 output steps) take one cheaper C4 step per output:
+                                 (P_min >= 250 output steps) take one cheaper C4 step per output:
                                  nbt_plan_substeps marks them with negative counts in inputs.substeps,
                                  nbt_plan_order sorts them last and counts them for cfg.alt_systems.  A
                                  negative count outside those slots runs |count| SBABC3 steps. */

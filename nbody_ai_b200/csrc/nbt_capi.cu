@@ -1287,7 +1287,7 @@ int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* subs
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (!params || !substeps) return nbt_fail(-10, "nbt_plan_substeps: NULL argument");
-    static const double R[NBT_SCHEME_COUNT + 1] = {8000.0, 400.0, 800.0, 57.5, 220.0, 57.5, 57.5}; /* P_min / dt_sub */
+    static const double R[NBT_SCHEME_COUNT + 1] = {8000.0, 400.0, 800.0, 57.5, 250.0, 57.5, 57.5}; /* P_min / dt_sub */
     const int B = cfg->n_systems, N = cfg->n_bodies;
     const double step = cfg->n_days / (double)(cfg->n_outputs - 1);
     const bool automatic = cfg->scheme == NBT_SCHEME_AUTO;

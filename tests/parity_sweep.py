@@ -51,7 +51,7 @@ def sweep(par, n_days, n_outputs, label):
     delta = hill_separation(par)
     worst = dict(tt_s=0.0, oc_min=0.0, a_rel=0.0, e_rel=0.0, ls_power=0.0, ttv_max_min=0.0)
     n_cmp = n_count_mismatch = n_chaotic = 0
-    fails = []
+    fails, top = [], []
     for b in range(plan.B):
         if delta[b] < 4.0 or (want.status[b] & (_abi.S_NONFINITE | _abi.S_UNBOUND | _abi.S_TT_OVERFLOW)):
             continue          # Hill-unstable / broken in the oracle itself: chaotic, no parity defined
@@ -83,10 +83,14 @@ def sweep(par, n_days, n_outputs, label):
         for k in worst:
             if np.isfinite(w[k]):
                 worst[k] = max(worst[k], w[k])
+        top.append((w['e_rel'], int(b)))
     return dict(label=label, n_systems=int(plan.B), n_planets=int(plan.Np), n_days=n_days, n_outputs=n_outputs,
                 compared=n_cmp, excluded_hill_unstable_or_broken=int(plan.B - n_cmp - n_chaotic),
                 excluded_chaotic_by_oracle_self_sensitivity=n_chaotic, transit_count_mismatches=n_count_mismatch,
-                outside_tolerance=len(fails), failures=fails[:10], worst={k: float(v) for k, v in worst.items()},
+                outside_tolerance=len(fails), failures=fails[:10],
+                largest_e_rel=[dict(system=b, e_rel=float(e), substeps=int(plan.substeps[b]), P=par[b, 1:, 1].tolist(),
+                                    mass_ratio=(par[b, 1:, 0] / par[b, 0, 0]).tolist(), hill_separation=float(delta[b]))
+                               for e, b in sorted(top, reverse=True)[:8]], worst={k: float(v) for k, v in worst.items()},
                 tolerances=dict(tt_s=1.0, oc_min=1e-3, a_rel=1e-8, e_rel=1e-8),
                 gpu_seconds_incl_copies=t_gpu, oracle_seconds=t_cpu, oracle_threads=oracle.max_threads())
 

@@ -54,11 +54,11 @@ def test_plan_helpers(nbt):
     # default scheme (AUTO): three drift stages per SBABC3 step, two per C4 step (negative counts)
     k = plan.substeps
     assert plan.n_steps == (int(k[k > 0].sum()) * 3 - int(k[k < 0].sum()) * 2) * 8759
-    # sub-step rule: P_min / dt_sub >= 57.5 for SBABC3; C4 only at one step per output and P_min >= 220 steps
+    # sub-step rule: P_min / dt_sub >= 57.5 for SBABC3; C4 only at one step per output and P_min >= 250 steps
     step = 365.0 / 8759
     pmin = par[:, 1:, 1].min(1)
     assert np.all(pmin[k > 0] / (step / k[k > 0]) >= 57.5 - 1e-9)
-    assert np.all(k[k < 0] == -1) and np.all(pmin[k < 0] >= 220 * step) and (k < 0).any()
+    assert np.all(k[k < 0] == -1) and np.all(pmin[k < 0] >= 250 * step) and (k < 0).any()
     sb = engine.Plan(par, 365.0, 8760, scheme="sbabc3")
     assert np.array_equal(sb.substeps, np.abs(k)) and sb.n_steps == int(sb.substeps.sum()) * 8759 * 3
 
