@@ -210,9 +210,12 @@ def test_standalone_functions_vs_reference_fixture(gpu_lib):
     fo, po = oracle.lomb_scargle(tr, y, 1. / 50, 0.5)
     assert np.array_equal(f, fo) and np.abs(p - po).max() < 1e-10
     # maxavg on ragged sizes vs numpy
-    for n in (1, 2, 3, 5, 33, 1000):
+    for n in (1, 2, 3, 5, 32, 33, 64, 65, 97, 1000):
         x = rng.normal(size=n)
         assert abs(tools.maxavg(x) - (np.percentile(np.abs(x), 75) + np.abs(x).max()) * 0.5) < 1e-15
+        # ties around the 75th percentile (the upper order statistic equals the lower one), zeros, one value
+        for y in (np.round(x, 1), np.zeros(n), np.full(n, -2.5), np.repeat(x[: max(n // 3, 1)], 3)[:n]):
+            assert abs(tools.maxavg(y) - (np.percentile(np.abs(y), 75) + np.abs(y).max()) * 0.5) < 1e-15
 
 
 def test_randomize_matches_reference_draws(gpu_lib):
