@@ -152,7 +152,8 @@ int64_t nbt_ls_nfreq(double baseline, double minfreq, double maxfreq, int sample
  * Returns the largest single capacity (>0), or <0 on error. */
 int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets);
 /* Fill order[B]: permutation of 0..B-1 sorted by decreasing substeps, Hill-unstable systems
- * (mutual separation < 4 R_Hill, from params) first within equal substeps (host helper).
+ * (mutual separation < 4 R_Hill, from params) first within equal substeps — spread evenly over the
+ * group instead where substeps >= 2 (host helper).
  * params or substeps may be NULL (that key is skipped).  Negative counts (NBT_SCHEME_AUTO) sort last;
  * returns how many there are (>= 0), which the caller stores in cfg.alt_systems, or < 0 on error. */
 int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* substeps, int32_t* order);
@@ -162,7 +163,9 @@ int nbt_plan_lanes(const nbt_config* cfg, const int32_t* substeps, const int32_t
 /* Fill ls_offsets[B*Np+1] from tt_offsets (capacity of the O-C periodogram). */
 int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets);
 
-/* Recommended composition steps per output interval for each system (host helper). */
+/* Recommended composition steps per output interval for each system: ceil(step * R / P_min) with the
+ * scheme's R (57.5 for SBABC3 / M64).  NBT_SCHEME_AUTO: -1 for the systems that take one C4 step
+ * per output instead (P_min >= 250 output steps, Hill separation >= 4).  Host helper. */
 int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* substeps);
 
 /* Number of system-steps (kick+drift stages) nbt_run will execute for this plan. */
