@@ -13,6 +13,11 @@
  *                         nbody/nested.py:44-47       get_ttv()    (ttvfast forward model)
  *   nbt_lomb_scargle   <- nbody/tools.py:97-104       lomb_scargle() -> astropy autopower
  *   nbt_chi2           <- nbody/nested.py:85-95       myloglike()  (chi^2 of the forward model)
+ *   nbt_ttvfit_loglike <- ttv_fit.py:58-94            nbody_fitter.loglike()
+ *   nbt_run + inputs.like (NBT_F_LOGLIKE): either likelihood fused behind the forward model on the launch
+ *                         stream — only loglike[B] and status[B] have to leave the device
+ *   inputs.n_days_sys / n_outputs_sys <- simulations/generate_simulations.py:45-50: every draw has its own grid
+ *                         (Ndays = P1 * periods, Noutputs = round(P1 * periods * 24)), one launch for all of them
  *   nbt_plan_*         <- no reference analogue (the reference grows Python lists); they size
  *                         the caller-owned CSR buffers the kernels write into.
  *
@@ -36,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NBT_ABI_VERSION 1
+#define NBT_ABI_VERSION 2
 #define NBT_G 0.00029591220828559104 /* day, AU, Msun — nbody/tools.py:18 */
 #define NBT_MAX_BODIES 9             /* star + 8 planets (solarsystem_nbody.py) */
 
@@ -53,11 +58,22 @@ enum { NBT_SCHEME_WH2 = 0,   /* kick-drift-kick leapfrog */
        NBT_SCHEME_SBABC3 = 5, /* 3-stage Lobatto composition + force-gradient end kicks, order (6,4):
                                  the accuracy of M64 with three Kepler drifts per step (the default) */
        NBT_SCHEME_COUNT = 6,
-       NBT_SCHEME_AUTO = 6 }; /* SBABC3, except that systems resolved finely enough by the output grid itself
+       NBT_SCHEME_AUTO = 6,  /* SBABC3, except that systems resolved finely enough by the output grid itself
                                  (P_min >= 250 output steps) take one cheaper C4 step per output:
                                  nbt_plan_substeps marks them with negative counts in inputs.substeps,
                                  nbt_plan_order sorts them last and counts them for cfg.alt_systems.  A
                                  negative count outside those slots runs |count| SBABC3 steps. */
+       NBT_SCHEME_IAS15 = 7, /* adaptive 15th-order Gauss-Radau (Rein & Spiegel 2015), one system per thread — what
+                                 the reference itself integrates with (REBOUND's default, nbody/simulation.py:31).
+                                 Far slower than the compositions and latency-bound; it is there for the few
+                                 systems no fixed step resolves (close encounters, error-amplifying pairs):
+                                 engine.run_verified routes them here.  substeps / order / alt_systems /
+                                 lanes_systems are ignored. */
+       NBT_SCHEME_WHFAST = 8 }; /* integrator='whfast' of nbody/simulation.py:39-42: REBOUND's WHFast (drift-kick-drift
+                                 in Jacobi coordinates) at its default dt = 1e-3 d with the 5th-order symplectic
+                                 corrector applied at the start and undone at the end of every sim.integrate(t)
+                                 (safe_mode = 0), last step of an interval shortened to land on the output
+                                 (exact_finish_time).  cfg.substeps = full steps per output interval is derived. */
 
 /* transit-time mode */
 enum { NBT_TT_GRID_LINEAR = 0, /* reference semantics: sign test + linear interpolation on the
@@ -74,19 +90,29 @@ enum { NBT_F_MEANS = 1 << 0,       /* time means of Jacobi a, e, inc (analyze :2
        NBT_F_LS_RV = 1 << 6,       /* RV periodogram per system (needs NBT_F_RV) */
        NBT_F_PLANET1_ONLY = 1 << 7,/* ttvfast: transit products for planet 1 only (analyze :181-184) */
        NBT_F_DEVICE_PTRS = 1 << 8, /* all buffers are device pointers; async on `stream` */
-       NBT_F_TIMING = 1 << 9       /* record CUDA events around each stage (read with nbt_timing) */
+       NBT_F_TIMING = 1 << 9,      /* record CUDA events around each stage (read with nbt_timing) */
+       NBT_F_LOGLIKE = 1 << 10,    /* evaluate inputs.like behind the forward model, on the same stream: outputs.loglike */
+       NBT_F_LS_PEAKS = 1 << 11    /* reduce each O-C periodogram (NBT_F_LS_OC) to its NBT_LS_NPEAKS highest local maxima
+                                      on the device: outputs.ls_oc_peaks; with ls_oc_power == NULL (host pointers) the
+                                      full power arrays never leave the device */
 };
+#define NBT_LS_NPEAKS 3
 
 /* per-system status bits (the reference signals these only indirectly) */
 enum { NBT_S_NONFINITE = 1 << 0, NBT_S_UNBOUND = 1 << 1, NBT_S_KEPLER = 1 << 2,
-       NBT_S_TT_OVERFLOW = 1 << 3, NBT_S_FEW_TRANSITS = 1 << 4 };
+       NBT_S_TT_OVERFLOW = 1 << 3, NBT_S_FEW_TRANSITS = 1 << 4,
+       NBT_S_UNCALIBRATED = 1 << 5, /* outside the envelope the sub-step rule was calibrated on (a planet pair closer
+                                       than 4 mutual Hill radii, e > 0.1, or m_planet / m_star > 0.013): the fixed-step
+                                       result may miss the parity tolerances; engine.run_verified checks such systems
+                                       by step doubling and re-integrates the ones that need it */
+       NBT_S_UNRESOLVED = 1 << 6 }; /* set by engine.run_verified: step doubling did not converge and no fallback ran */
 
 typedef struct nbt_config {
     int32_t struct_size; /* = sizeof(nbt_config), ABI guard */
     int32_t n_systems;   /* B */
     int32_t n_bodies;    /* star + planets, 2..NBT_MAX_BODIES */
-    int32_t n_outputs;   /* Noutputs of np.linspace(0, Ndays, Noutputs) */
-    double n_days;       /* Ndays */
+    int32_t n_outputs;   /* Noutputs of np.linspace(0, Ndays, Noutputs) (the largest, with inputs.n_outputs_sys) */
+    double n_days;       /* Ndays (the largest, with inputs.n_days_sys) */
     int32_t substeps;    /* composition steps per output interval; <=0: use inputs.substeps[] */
     int32_t scheme;      /* NBT_SCHEME_* */
     int32_t tt_mode;     /* NBT_TT_* */
@@ -104,6 +130,28 @@ typedef struct nbt_config {
                             returns it; every one must hold a negative count); 0 = all SBABC3 */
 } nbt_config;
 
+/* Likelihood evaluated behind the forward model (NBT_F_LOGLIKE).  All arrays follow the pointer convention of the
+ * call (host, or device with NBT_F_DEVICE_PTRS). */
+enum { NBT_LIKE_NESTED = 0,   /* nbody/nested.py:85-95 myloglike: planet-1 O-C against (x, y, yerr), linear term c1*x + c0 */
+       NBT_LIKE_TTVFIT = 1 }; /* ttv_fit.py:58-94: transit times of every planet with data, shifted and offset (see nbt_ttvfit_loglike) */
+enum { NBT_LOSS_LINEAR = 0,   /* z */
+       NBT_LOSS_SOFT_L1 = 1 };/* 2 (sqrt(1 + z) - 1)   (nbody/nested.py:79-82) */
+typedef struct nbt_like {
+    int32_t kind;            /* NBT_LIKE_* */
+    int32_t loss;            /* NBT_LOSS_* (NESTED only) */
+    int32_t n_data;          /* observed epochs (NESTED) / observed orbit numbers n_obs (TTVFIT) */
+    int32_t reserved;
+    const double* c0;        /* NESTED [B] intercept cube[0] */
+    const double* c1;        /* NESTED [B] slope cube[1] */
+    const double* x;         /* NESTED [n_data] epochs */
+    const double* y;         /* NESTED [n_data] mid-transit times */
+    const double* yerr;      /* NESTED [n_data] */
+    const int32_t* has_data; /* TTVFIT [Np] */
+    const double* tc;        /* TTVFIT [Np][n_data] */
+    const double* tc_err;    /* TTVFIT [Np][n_data] */
+    const int32_t* orbit;    /* TTVFIT [n_data] orbit numbers (ttv_fit.py:38-39) */
+} nbt_like;
+
 typedef struct nbt_inputs {
     const double* params;      /* [B][n_bodies][NBT_NPAR] */
     const int32_t* substeps;   /* [B] or NULL (then cfg.substeps applies to all) */
@@ -111,10 +159,17 @@ typedef struct nbt_inputs {
                                   counts within a warp, unstable systems grouped) or NULL */
     const int64_t* tt_offsets; /* [B*Np + 1] CSR capacity offsets into tt/ttv (nbt_plan_tt) */
     const int64_t* ls_offsets; /* [B*Np + 1] CSR capacity offsets into ls_oc_power, or NULL */
+    /* per-system output grids np.linspace(0, n_days_sys[b], n_outputs_sys[b]) — both or neither; NULL = the uniform
+     * grid of cfg.  Not combinable with the [n_outputs][B] products (NBT_F_RV, _ORBIT, _SERIES, _LS_RV). */
+    const double* n_days_sys;     /* [B] or NULL */
+    const int32_t* n_outputs_sys; /* [B] or NULL */
+    const nbt_like* like;         /* NBT_F_LOGLIKE: always a HOST pointer to the struct (its arrays follow the call's convention) */
 } nbt_inputs;
 
 typedef struct nbt_outputs {
-    /* transit products, CSR over (system, planet) */
+    /* transit products, CSR over (system, planet).  With host pointers any of tt, ttv, n_tt, period, t0, ttv_max may
+     * be NULL: it is still computed on the device (the fit, the periodogram and the likelihood read it) but not
+     * copied back. */
     double* tt;        /* mid-transit times [day] */
     double* ttv;       /* O-C [day] */
     int32_t* n_tt;     /* [B*Np] transits found (may exceed capacity -> NBT_S_TT_OVERFLOW) */
@@ -137,6 +192,8 @@ typedef struct nbt_outputs {
     double* ls_oc_power; /* CSR by ls_offsets     NBT_F_LS_OC */
     int32_t* ls_oc_nfreq;/* [B*Np] */
     double* ls_rv_power; /* [B][nbt_ls_nfreq(n_outputs-1 samples)]  NBT_F_LS_RV */
+    double* ls_oc_peaks; /* [B*Np][NBT_LS_NPEAKS][2] (frequency [1/epoch], power), highest first, NaN-padded   NBT_F_LS_PEAKS */
+    double* loglike;     /* [B]   NBT_F_LOGLIKE */
 } nbt_outputs;
 
 int nbt_abi_version(void);
@@ -148,28 +205,35 @@ const char* nbt_last_error(void);
  * (np.round is round-half-even), freq_k = fmin + k*df.  tools.py:104. */
 int64_t nbt_ls_nfreq(double baseline, double minfreq, double maxfreq, int samples_per_peak);
 
-/* Fill tt_offsets[B*Np+1] with CSR capacities ceil(1.05*Ndays/P)+3 per planet (host helper).
+/* Host planning helpers.  `in` supplies params (and, when set, n_days_sys / n_outputs_sys, substeps, order); the other
+ * fields of `in` are ignored.
+ *
+ * nbt_plan_tt: fill tt_offsets[B*Np+1] with CSR capacities min(ceil(1.05*Ndays/P)+3, Noutputs) per planet.
  * Returns the largest single capacity (>0), or <0 on error. */
-int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets);
-/* Fill order[B]: permutation of 0..B-1 sorted by decreasing substeps, Hill-unstable systems
- * (mutual separation < 4 R_Hill, from params) first within equal substeps — spread evenly over the
- * group instead where substeps >= 2 (host helper).
- * params or substeps may be NULL (that key is skipped).  Negative counts (NBT_SCHEME_AUTO) sort last;
+int nbt_plan_tt(const nbt_config* cfg, const nbt_inputs* in, int64_t* tt_offsets);
+/* Fill order[B]: permutation of 0..B-1 sorted by decreasing substeps (then decreasing n_outputs_sys), Hill-unstable
+ * systems (mutual separation < 4 R_Hill, from params) first within equal substeps — spread evenly over the
+ * group instead where substeps >= 2.
+ * in->params or in->substeps may be NULL (that key is skipped).  Negative counts (NBT_SCHEME_AUTO) sort last;
  * returns how many there are (>= 0), which the caller stores in cfg.alt_systems, or < 0 on error. */
-int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* substeps, int32_t* order);
-/* Number of leading launch-order slots for the one-planet-per-lane kernel (host helper); the
- * caller stores it in cfg.lanes_systems.  substeps / order may be NULL. */
-int nbt_plan_lanes(const nbt_config* cfg, const int32_t* substeps, const int32_t* order);
+int nbt_plan_order(const nbt_config* cfg, const nbt_inputs* in, int32_t* order);
+/* Number of leading launch-order slots for the one-planet-per-lane kernel; the caller stores it in
+ * cfg.lanes_systems. */
+int nbt_plan_lanes(const nbt_config* cfg, const nbt_inputs* in);
 /* Fill ls_offsets[B*Np+1] from tt_offsets (capacity of the O-C periodogram). */
 int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_offsets);
 
 /* Recommended composition steps per output interval for each system: ceil(step * R / P_min) with the
  * scheme's R (57.5 for SBABC3 / M64).  NBT_SCHEME_AUTO: -1 for the systems that take one C4 step
- * per output instead (P_min >= 250 output steps, Hill separation >= 4).  Host helper. */
-int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* substeps);
+ * per output instead (P_min >= 250 output steps, Hill separation >= 4). */
+int nbt_plan_substeps(const nbt_config* cfg, const nbt_inputs* in, int32_t* substeps);
 
-/* Number of system-steps (kick+drift stages) nbt_run will execute for this plan. */
-int64_t nbt_count_steps(const nbt_config* cfg, const int32_t* substeps);
+/* Number of system-steps (kick+drift stages) nbt_run will execute for this plan (in->substeps, grids). */
+int64_t nbt_count_steps(const nbt_config* cfg, const nbt_inputs* in);
+
+/* 1 if the system described by one parameter row block [n_bodies][NBT_NPAR] is outside the envelope the sub-step
+ * rule was calibrated on (what nbt_run reports as NBT_S_UNCALIBRATED), else 0. */
+int nbt_uncalibrated(const double* params_one, int n_bodies);
 
 /* The hot path: set up, integrate, detect transits, fit ephemerides, reduce. */
 int nbt_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, void* cuda_stream);
@@ -206,11 +270,11 @@ int nbt_lomb_scargle(const double* t, const double* y, int64_t n_series, int64_t
                      int device, int device_ptrs, void* cuda_stream);
 
 /* chi^2 of nested.py:85-95 for B forward models against one data vector:
- * loglike[b] = -0.5 * sum_i ((y_i - (c1[b]*x_i + c0[b]) - ttv[b][x_i]) / yerr_i)^2,
- * with the reference's penalty branch when epoch x_i is missing. */
+ * loglike[b] = -0.5 * sum_i loss(((y_i - (c1[b]*x_i + c0[b]) - ttv[b][x_i]) / yerr_i)^2), loss = NBT_LOSS_*
+ * (nested.py:79-82), with the reference's penalty branch when epoch x_i is missing. */
 int nbt_chi2(const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt, int32_t n_systems,
              int32_t n_planets, const double* c0, const double* c1, const double* x, const double* y,
-             const double* yerr, int32_t n_data, double* loglike, int device, int device_ptrs,
+             const double* yerr, int32_t n_data, int32_t loss, double* loglike, int device, int device_ptrs,
              void* cuda_stream);
 
 /* Likelihood of the UltraNest fitter, ttv_fit.py:47-94, for B forward models: for every planet j with

@@ -9,15 +9,15 @@ import os
 
 import numpy as np
 
-NBT_ABI_VERSION = 1
+NBT_ABI_VERSION = 2
 NBT_G = 0.00029591220828559104  # nbody/tools.py:18
 NBT_MAX_BODIES = 9
 NBT_NPAR = 7
 P_M, P_P, P_E, P_INC, P_OMEGA_NODE, P_OMEGA_PERI, P_F = range(7)
 
-SCHEME_WH2, SCHEME_Y4, SCHEME_SABA4, SCHEME_M64, SCHEME_C4, SCHEME_SBABC3, SCHEME_AUTO = range(7)
+SCHEME_WH2, SCHEME_Y4, SCHEME_SABA4, SCHEME_M64, SCHEME_C4, SCHEME_SBABC3, SCHEME_AUTO, SCHEME_IAS15, SCHEME_WHFAST = range(9)
 SCHEMES = {"wh2": SCHEME_WH2, "y4": SCHEME_Y4, "saba4": SCHEME_SABA4, "m64": SCHEME_M64,
-           "c4": SCHEME_C4, "sbabc3": SCHEME_SBABC3, "auto": SCHEME_AUTO}
+           "c4": SCHEME_C4, "sbabc3": SCHEME_SBABC3, "auto": SCHEME_AUTO, "ias15": SCHEME_IAS15, "whfast": SCHEME_WHFAST}
 TT_GRID_LINEAR, TT_REFINED = 0, 1
 
 F_MEANS = 1 << 0
@@ -30,12 +30,20 @@ F_LS_RV = 1 << 6
 F_PLANET1_ONLY = 1 << 7
 F_DEVICE_PTRS = 1 << 8
 F_TIMING = 1 << 9
+F_LOGLIKE = 1 << 10
+F_LS_PEAKS = 1 << 11
+LS_NPEAKS = 3
+LIKE_NESTED, LIKE_TTVFIT = 0, 1
+LOSS_LINEAR, LOSS_SOFT_L1 = 0, 1
+LOSSES = {"linear": LOSS_LINEAR, "soft_l1": LOSS_SOFT_L1}
 
 S_NONFINITE = 1 << 0
 S_UNBOUND = 1 << 1
 S_KEPLER = 1 << 2
 S_TT_OVERFLOW = 1 << 3
 S_FEW_TRANSITS = 1 << 4
+S_UNCALIBRATED = 1 << 5
+S_UNRESOLVED = 1 << 6
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -66,8 +74,15 @@ class nbt_config(C.Structure):
     ]
 
 
+class nbt_like(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("loss", C.c_int32), ("n_data", C.c_int32), ("reserved", C.c_int32),
+                ("c0", _dp), ("c1", _dp), ("x", _dp), ("y", _dp), ("yerr", _dp),
+                ("has_data", _ip), ("tc", _dp), ("tc_err", _dp), ("orbit", _ip)]
+
+
 class nbt_inputs(C.Structure):
-    _fields_ = [("params", _dp), ("substeps", _ip), ("order", _ip), ("tt_offsets", _lp), ("ls_offsets", _lp)]
+    _fields_ = [("params", _dp), ("substeps", _ip), ("order", _ip), ("tt_offsets", _lp), ("ls_offsets", _lp),
+                ("n_days_sys", _dp), ("n_outputs_sys", _ip), ("like", C.POINTER(nbt_like))]
 
 
 class nbt_outputs(C.Structure):
@@ -75,7 +90,7 @@ class nbt_outputs(C.Structure):
         ("tt", _dp), ("ttv", _dp), ("n_tt", _ip), ("period", _dp), ("t0", _dp), ("ttv_max", _dp),
         ("mean_a", _dp), ("mean_e", _dp), ("mean_inc", _dp), ("mean_omega", _dp), ("status", _ip),
         ("rv", _dp), ("rv_max", _dp), ("orbit_xz", _dp), ("series", _dp),
-        ("ls_oc_power", _dp), ("ls_oc_nfreq", _ip), ("ls_rv_power", _dp),
+        ("ls_oc_power", _dp), ("ls_oc_nfreq", _ip), ("ls_rv_power", _dp), ("ls_oc_peaks", _dp), ("loglike", _dp),
     ]
 
 
@@ -126,17 +141,18 @@ def load():
     lib.nbt_last_error.restype = C.c_char_p
     lib.nbt_ls_nfreq.restype = C.c_int64
     lib.nbt_ls_nfreq.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
-    lib.nbt_plan_tt.argtypes = [C.POINTER(nbt_config), _dp, _lp]
-    lib.nbt_plan_order.argtypes = [C.POINTER(nbt_config), _dp, _ip, _ip]
+    lib.nbt_plan_tt.argtypes = [C.POINTER(nbt_config), C.POINTER(nbt_inputs), _lp]
+    lib.nbt_plan_order.argtypes = [C.POINTER(nbt_config), C.POINTER(nbt_inputs), _ip]
     lib.nbt_plan_ls.argtypes = [C.POINTER(nbt_config), _lp, _lp]
-    lib.nbt_plan_lanes.argtypes = [C.POINTER(nbt_config), _ip, _ip]
-    lib.nbt_plan_substeps.argtypes = [C.POINTER(nbt_config), _dp, _ip]
+    lib.nbt_plan_lanes.argtypes = [C.POINTER(nbt_config), C.POINTER(nbt_inputs)]
+    lib.nbt_plan_substeps.argtypes = [C.POINTER(nbt_config), C.POINTER(nbt_inputs), _ip]
     lib.nbt_count_steps.restype = C.c_int64
-    lib.nbt_count_steps.argtypes = [C.POINTER(nbt_config), _ip]
+    lib.nbt_count_steps.argtypes = [C.POINTER(nbt_config), C.POINTER(nbt_inputs)]
+    lib.nbt_uncalibrated.argtypes = [_dp, C.c_int]
     lib.nbt_run.argtypes = [C.POINTER(nbt_config), C.POINTER(nbt_inputs), C.POINTER(nbt_outputs), C.c_void_p]
     lib.nbt_lomb_scargle.argtypes = [_dp, _dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int64,
                                      _dp, C.c_int, C.c_int, C.c_void_p]
-    lib.nbt_chi2.argtypes = [_dp, _lp, _ip, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.c_int32, _dp,
+    lib.nbt_chi2.argtypes = [_dp, _lp, _ip, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.c_int32, C.c_int32, _dp,
                              C.c_int, C.c_int, C.c_void_p]
     lib.nbt_analyze.argtypes = [C.POINTER(nbt_config), _dp, _dp, C.c_double, C.POINTER(nbt_inputs),
                                 C.POINTER(nbt_outputs), C.c_void_p]
@@ -168,16 +184,23 @@ def check(rc, lib=None):
 def objects_to_params(objects):
     """objects list-of-dicts (README.md:23-28) -> [n_bodies, NBT_NPAR] row block.
 
-    Keys are the ones the reference forwards to rebound.Simulation.add(**obj): m, P, e, inc,
-    Omega, omega, f; absent keys default to 0 like REBOUND's.
-    """
+    Keys are the ones the reference forwards to rebound.Simulation.add(**obj): m, P (or a), e, inc,
+    Omega, omega, f; absent keys default to 0 like REBOUND's.  A semi-major axis `a` is converted to
+    the period with the Jacobi mu = G (M_interior + m) that rebound.add uses."""
     out = np.zeros((len(objects), NBT_NPAR))
     keys = {"m": P_M, "P": P_P, "e": P_E, "inc": P_INC, "Omega": P_OMEGA_NODE, "omega": P_OMEGA_PERI, "f": P_F}
     for i, ob in enumerate(objects):
         for k, v in ob.items():
+            if k == "a":
+                continue
             if k not in keys:
-                raise ValueError("unsupported orbital key %r (supported: %s)" % (k, sorted(keys)))
+                raise ValueError("unsupported orbital key %r (supported: %s)" % (k, sorted(list(keys) + ["a"])))
             out[i, keys[k]] = float(v)
         if i > 0 and "P" not in ob:
-            raise ValueError("planet %d needs a period 'P'" % i)
+            if "a" not in ob:
+                raise ValueError("planet %d needs a period 'P' (or a semi-major axis 'a')" % i)
+            mu = NBT_G * out[:i + 1, P_M].sum()
+            out[i, P_P] = 2 * np.pi * np.sqrt(float(ob["a"]) ** 3 / mu)
+        elif i > 0 and "a" in ob:
+            raise ValueError("planet %d: give either 'P' or 'a', not both (rebound.add raises too)" % i)
     return out

@@ -10,6 +10,9 @@
 //                     (nbody/simulation.py:213 -> nbody/tools.py:97-104)           FP64-pipe bound
 //   k_transpose / k_rv_max / k_ls_series   RV products (nbody/simulation.py:186-188)
 //   k_chi2            nested-sampling log-likelihood (nbody/nested.py:85-95)
+//   k_integrate_ias15 the reference's own integrator (REBOUND's default IAS15) for the few systems no fixed step
+//                     resolves (engine.run_verified)                                latency-bound, rare
+//   k_ls_peaks        on-device reduction of the O-C periodograms to their highest peaks
 //   k_dfma_peak       DFMA-chain microbenchmark: the measured FP64 roofline denominator
 //
 // There is no CPU path in this library: without a CUDA device every compute entry fails.
@@ -26,6 +29,7 @@
 #include <vector>
 
 #include "nbt_core.cuh"
+#include "nbt_ias15.cuh"
 #include "nbt_lanes.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -127,6 +131,9 @@ __device__ double warp_maxavg(const double* x, int n, int lane) {
 #endif
 #ifndef NBT_MINBLOCKS
 #define NBT_MINBLOCKS 1
+#endif
+#ifndef NBT_LAT_MAX_SYSTEMS
+#define NBT_LAT_MAX_SYSTEMS (4 * 56832)   /* launches below this many systems take the latency variant (Np <= 2) */
 #endif
 
 // launch-order slots [first, first + count) of the batch, one system per thread.  The first main_count
@@ -382,6 +389,60 @@ __global__ void __launch_bounds__(128) k_ls_oc(const nbt_lsoc_args L) {
         const long long k1 = min(nf, k0 + NBT_LS_FCHUNK);
         for (long long k = k0 + lane; k < k1; k += 32)
             L.power[loff + k] = ls_power_uniform(y, n, ybar, YY, L.fmin + (double)k * df);
+    }
+}
+
+// NBT_F_LS_PEAKS: the NBT_LS_NPEAKS highest local maxima (p[k-1] < p[k] >= p[k+1], interior samples) of each O-C
+// periodogram, as (frequency, power) pairs, highest first, NaN-padded.  One warp per (system, planet) series.  Callers
+// that only read the peak of a periodogram (report()'s tables, simulation_grid) then need 48 bytes per series instead
+// of ~5 n_tt doubles — the power arrays were 234 of the 340 MB a bench step copied back.
+__global__ void __launch_bounds__(128) k_ls_peaks(const int64_t* __restrict__ tt_offsets, const int64_t* __restrict__ ls_offsets,
+                                                  const int32_t* __restrict__ n_tt, const int32_t* __restrict__ nfreq,
+                                                  const double* __restrict__ power, int nsp, int spp, double fmin,
+                                                  double* __restrict__ peaks) {
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= nsp) return;
+    double* out = peaks + (size_t)w * NBT_LS_NPEAKS * 2;
+    const int nf = nfreq[w];
+    const int cap = (int)(tt_offsets[w + 1] - tt_offsets[w]);
+    const int n = min(n_tt[w], cap);
+    if (nf < 3 || n < 3) {
+        if (lane < NBT_LS_NPEAKS * 2) out[lane] = NAN;
+        return;
+    }
+    const double* p = power + ls_offsets[w];
+    const double df = ls_df((double)(n - 1), spp);
+    // per-lane best NBT_LS_NPEAKS, then NBT_LS_NPEAKS rounds of warp arg-max
+    double bp[NBT_LS_NPEAKS]; int bk[NBT_LS_NPEAKS];
+#pragma unroll
+    for (int q = 0; q < NBT_LS_NPEAKS; q++) { bp[q] = -1.0; bk[q] = -1; }
+    for (int k = 1 + lane; k < nf - 1; k += 32) {
+        const double v = p[k];
+        if (p[k - 1] < v && v >= p[k + 1]) {
+            double cv = v; int ck = k;
+#pragma unroll
+            for (int q = 0; q < NBT_LS_NPEAKS; q++)
+                if (cv > bp[q]) { const double tv = bp[q]; const int tk = bk[q]; bp[q] = cv; bk[q] = ck; cv = tv; ck = tk; }
+        }
+    }
+    for (int r = 0; r < NBT_LS_NPEAKS; r++) {
+        double v = bp[0]; int k = bk[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, k, o);
+            if (ov > v || (ov == v && ok >= 0 && (k < 0 || ok < k))) { v = ov; k = ok; }
+        }
+        if (k >= 0 && bk[0] == k) {   // the winning lane pops its head
+#pragma unroll
+            for (int q = 0; q + 1 < NBT_LS_NPEAKS; q++) { bp[q] = bp[q + 1]; bk[q] = bk[q + 1]; }
+            bp[NBT_LS_NPEAKS - 1] = -1.0; bk[NBT_LS_NPEAKS - 1] = -1;
+        }
+        if (lane == 0) {
+            out[2 * r] = (k >= 0) ? fmin + (double)k * df : NAN;
+            out[2 * r + 1] = (k >= 0) ? v : NAN;
+        }
     }
 }
 
@@ -734,32 +795,36 @@ __global__ void __launch_bounds__(128) k_grid_post(const nbt_grid_args G) {
 // ---------------------------------------------------------------------------------------------
 // k_chi2: nbody/nested.py:85-95, one thread per forward model
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double nbt_loss(int loss, double z) {   // nested.py:79-82
+    return loss == NBT_LOSS_SOFT_L1 ? 2.0 * (sqrt(1.0 + z) - 1.0) : z;
+}
+
 __global__ void k_chi2(const double* __restrict__ ttv, const int64_t* __restrict__ tt_offsets,
                        const int32_t* __restrict__ n_tt, int B, int Np, const double* __restrict__ c0,
                        const double* __restrict__ c1, const double* __restrict__ x,
-                       const double* __restrict__ y, const double* __restrict__ yerr, int n_data,
+                       const double* __restrict__ y, const double* __restrict__ yerr, int n_data, int loss,
                        double* __restrict__ loglike) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int64_t off = tt_offsets[(size_t)b * Np];
     const int cap = (int)(tt_offsets[(size_t)b * Np + 1] - off);
-    const int n = min(n_tt[(size_t)b * Np], cap);
+    const int n0 = min(n_tt[(size_t)b * Np], cap);
     const double* tv = ttv + off;
     const double a0 = c0[b], a1 = c1[b];
     bool ok = true;
-    for (int i = 0; i < n_data; i++) { const int k = (int)x[i]; if (k >= n || k < -n) ok = false; }
+    for (int i = 0; i < n_data; i++) { const int k = (int)x[i]; if (k >= n0 || k < -n0) ok = false; }
     double s = 0.0;
     if (ok) {
         for (int i = 0; i < n_data; i++) {
-            int k = (int)x[i]; if (k < 0) k += n;
+            int k = (int)x[i]; if (k < 0) k += n0;
             const double r = (y[i] - (a1 * x[i] + a0) - tv[k]) / yerr[i];
-            s = fma(r, r, s);
+            s += nbt_loss(loss, r * r);
         }
         loglike[b] = -0.5 * s;
     } else { // IndexError branch: -10 * sum over the ttv that exist, paired index-for-index
-        for (int i = 0; i < n && i < n_data; i++) {
+        for (int i = 0; i < n0 && i < n_data; i++) {
             const double r = (y[i] - (a1 * x[i] + a0) - tv[i]) / yerr[i];
-            s = fma(r, r, s);
+            s += nbt_loss(loss, r * r);
         }
         loglike[b] = -10.0 * s;
     }
@@ -879,6 +944,8 @@ static int scheme_stages(int id) {
     case NBT_SCHEME_C4: return 2;
     case NBT_SCHEME_SBABC3: return 3;
     case NBT_SCHEME_AUTO: return 3;   /* systems with substeps > 0; the marked ones (< 0) take C4's 2 */
+    case NBT_SCHEME_IAS15: return 1;  /* adaptive: steps are not known in advance (counted as one per output) */
+    case NBT_SCHEME_WHFAST: return 1;
     default: return -1;
     }
 }
@@ -912,8 +979,7 @@ static cudaError_t launch_integrate(const nbt_run_args& A, int first, int count,
         const int grid = (main_count + NBT_BLOCK - 1) / NBT_BLOCK + (count - main_count + NBT_BLOCK - 1) / NBT_BLOCK;
         // Np <= 2 has a latency variant (branch-free drifts, more registers): it wins unless the launch is
         // many waves of resident threads deep (148 SMs x 6 CTAs x 64 threads = 56 832 per wave)
-        bool lat = NP <= 2 && count < 4 * 56832;
-        if (const char* f = getenv("NBT_DEBUG_LAT")) lat = NP <= 2 && f[0] == '1';   // measurement hook
+        const bool lat = NP <= 2 && count < NBT_LAT_MAX_SYSTEMS;
         if (series) k_integrate<NP, true, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count, main_count);
         else if (lat) k_integrate<NP, false, (NP <= 2)><<<grid, NBT_BLOCK, 0, st>>>(A, first, count, main_count);
         else k_integrate<NP, false, false><<<grid, NBT_BLOCK, 0, st>>>(A, first, count, main_count);
@@ -933,6 +999,39 @@ static cudaError_t launch_integrate_np(int np, const nbt_run_args& A, int first,
     case 8: return launch_integrate<8>(A, first, count, main_count, lanes, st);
     default: return cudaErrorInvalidValue;
     }
+}
+
+// NBT_SCHEME_IAS15: one system per thread, warp-sized blocks (a handful of systems: spread them over the SMs)
+template <int NP>
+__global__ void __launch_bounds__(32) k_integrate_ias15(const nbt_run_args A, const nbt_ias15_tables T) {
+    const int sys = (int)(blockIdx.x * 32u + threadIdx.x);
+    if (sys >= A.B) return;
+    nbt_simulate_system_ias15<NP>(A, T, sys);
+}
+
+static const nbt_ias15_tables& ias15_tables() {
+    static nbt_ias15_tables T;
+    static std::once_flag once;
+    std::call_once(once, [] { nbt_ias15_make_tables(T); });
+    return T;
+}
+
+static cudaError_t launch_special_np(int np, int scheme, const nbt_run_args& A, cudaStream_t st) {
+    if (scheme != NBT_SCHEME_IAS15) return cudaErrorNotSupported;
+    const int grid = (A.B + 31) / 32;
+    const nbt_ias15_tables& T = ias15_tables();
+    switch (np) {
+    case 1: k_integrate_ias15<1><<<grid, 32, 0, st>>>(A, T); break;
+    case 2: k_integrate_ias15<2><<<grid, 32, 0, st>>>(A, T); break;
+    case 3: k_integrate_ias15<3><<<grid, 32, 0, st>>>(A, T); break;
+    case 4: k_integrate_ias15<4><<<grid, 32, 0, st>>>(A, T); break;
+    case 5: k_integrate_ias15<5><<<grid, 32, 0, st>>>(A, T); break;
+    case 6: k_integrate_ias15<6><<<grid, 32, 0, st>>>(A, T); break;
+    case 7: k_integrate_ias15<7><<<grid, 32, 0, st>>>(A, T); break;
+    case 8: k_integrate_ias15<8><<<grid, 32, 0, st>>>(A, T); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
 }
 
 // side streams per device: the lanes-kernel launches of a call (the long systems) run concurrently with
@@ -1011,6 +1110,7 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         memset(&A, 0, sizeof A);
         A.params = in->params; A.substeps = (cfg->substeps > 0) ? nullptr : in->substeps; A.order = in->order;
         A.tt_offsets = in->tt_offsets;
+        A.n_days_sys = in->n_days_sys; A.n_outputs_sys = in->n_outputs_sys;
         A.tt = out->tt; A.n_tt = out->n_tt; A.mean_a = out->mean_a; A.mean_e = out->mean_e;
         A.mean_inc = out->mean_inc; A.mean_omega = out->mean_omega; A.status = out->status;
         A.rv = out->rv; A.orbit_xz = out->orbit_xz; A.series = out->series;
@@ -1018,6 +1118,11 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         A.orbit_stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
         A.n_days = cfg->n_days;
         const bool automatic = cfg->scheme == NBT_SCHEME_AUTO;
+        if (cfg->scheme == NBT_SCHEME_IAS15 || cfg->scheme == NBT_SCHEME_WHFAST) {
+            // the two integrators of the reference itself (REBOUND's default and its 'whfast' preset), one system
+            // per thread, no launch order / lanes / scheme mix
+            if ((e = launch_special_np(Np, cfg->scheme, A, st)) != cudaSuccess) return e;
+        } else {
         A.scheme = nbt_make_scheme(automatic ? NBT_SCHEME_SBABC3 : cfg->scheme);
         int nl = cfg->lanes_systems < 0 ? 0 : cfg->lanes_systems;   // leading launch-order slots on the lanes kernel
         if (nl > B) nl = B;
@@ -1059,6 +1164,7 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         if (fork) cudaEventDestroy(fork);   // destruction is deferred until the events complete
         for (int i = 0; i < 2; i++) if (join[i]) cudaEventDestroy(join[i]);
         if (e != cudaSuccess) return e;
+        }
     } else {
         nbt_scan_args S;
         memset(&S, 0, sizeof S);
@@ -1084,6 +1190,17 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
     F.B = B; F.Np = Np; F.flags = cfg->flags;
     k_fit<<<fit_grid, 128, 0, st>>>(F);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((cfg->flags & NBT_F_LOGLIKE) && in->like && out->loglike) {
+        // the sampler's likelihood behind the forward model, on the same stream: tt / ttv never leave the device
+        const nbt_like* L = in->like;
+        if (L->kind == NBT_LIKE_NESTED)
+            k_chi2<<<(B + 127) / 128, 128, 0, st>>>(out->ttv, in->tt_offsets, out->n_tt, B, Np, L->c0, L->c1, L->x, L->y, L->yerr,
+                                                     L->n_data, L->loss, out->loglike);
+        else
+            k_ttvfit<<<(B + 127) / 128, 128, 0, st>>>(out->tt, in->tt_offsets, out->n_tt, B, Np, L->has_data, L->tc, L->tc_err,
+                                                       L->orbit, L->n_data, out->loglike);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     timing_mark(2, tim, st);
     // everything but the periodograms and RV reductions is final here: the host path starts copying
     // those products back on a second stream while k_ls_oc runs
@@ -1125,6 +1242,12 @@ static cudaError_t enqueue_path(const nbt_config* cfg, const nbt_inputs* in, con
         if (piped)
             for (int c = 1; c < nc; c += 2)
                 if ((e = cudaStreamWaitEvent(st, ls_events[c], 0)) != cudaSuccess) return e;
+        if ((cfg->flags & NBT_F_LS_PEAKS) && out->ls_oc_peaks) {
+            k_ls_peaks<<<(unsigned)((nw * 32 + 127) / 128), 128, 0, st>>>(in->tt_offsets, in->ls_offsets, out->n_tt, out->ls_oc_nfreq,
+                                                                           out->ls_oc_power, (int)nw, cfg->ls_samples_per_peak,
+                                                                           cfg->ls_oc_minfreq, out->ls_oc_peaks);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
     }
     timing_mark(3, tim, st);
     if ((cfg->flags & NBT_F_RV) && out->rv && rv_sm_ws && (out->rv_max || ((cfg->flags & NBT_F_LS_RV) && out->ls_rv_power))) {
@@ -1173,41 +1296,67 @@ int64_t nbt_ls_nfreq(double baseline, double minfreq, double maxfreq, int spp) {
     return 1 + (int64_t)rint((maxfreq - minfreq) / df);
 }
 
-int nbt_plan_tt(const nbt_config* cfg, const double* params, int64_t* tt_offsets) {
+// per-system output grid (inputs.n_days_sys / n_outputs_sys) or the uniform one of cfg
+static inline double grid_days(const nbt_config* cfg, const nbt_inputs* in, int b) {
+    return (in && in->n_days_sys) ? in->n_days_sys[b] : cfg->n_days;
+}
+static inline int grid_outputs(const nbt_config* cfg, const nbt_inputs* in, int b) {
+    return (in && in->n_outputs_sys) ? in->n_outputs_sys[b] : cfg->n_outputs;
+}
+static int check_grids(const nbt_config* cfg, const nbt_inputs* in) {
+    if (!in) return 0;
+    if ((in->n_days_sys == nullptr) != (in->n_outputs_sys == nullptr))
+        return nbt_fail(-14, "inputs.n_days_sys and inputs.n_outputs_sys go together");
+    if (in->n_days_sys && (cfg->flags & (NBT_F_RV | NBT_F_ORBIT | NBT_F_SERIES | NBT_F_LS_RV)))
+        return nbt_fail(-14, "per-system output grids cannot be combined with the [n_outputs][B] products (RV, orbit, series)");
+    return 0;
+}
+
+int nbt_plan_tt(const nbt_config* cfg, const nbt_inputs* in, int64_t* tt_offsets) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
-    if (!params || !tt_offsets) return nbt_fail(-10, "nbt_plan_tt: NULL argument");
+    if (!in || !in->params || !tt_offsets) return nbt_fail(-10, "nbt_plan_tt: NULL argument");
+    if ((rc = check_grids(cfg, in)) != 0) return rc;
+    const double* params = in->params;
     const int B = cfg->n_systems, N = cfg->n_bodies, Np = N - 1;
     int64_t off = 0, capmax = 1;
-    for (int b = 0; b < B; b++)
+    for (int b = 0; b < B; b++) {
+        const double nd = grid_days(cfg, in, b);
+        const int no = grid_outputs(cfg, in, b);
+        if (!(nd > 0.0) || no < 2) return nbt_fail(-14, "system %d: n_days must be > 0 and n_outputs >= 2", b);
         for (int j = 0; j < Np; j++) {
             tt_offsets[(size_t)b * Np + j] = off;
             const double P = params[((size_t)b * N + j + 1) * NBT_NPAR + NBT_P_P];
             int64_t cap = 3;
             if (P > 0.0 && std::isfinite(P)) {
-                double c = ceil(1.05 * cfg->n_days / P) + 3.0;
-                if (c > (double)cfg->n_outputs) c = (double)cfg->n_outputs; // at most one transit per interval
+                double c = ceil(1.05 * nd / P) + 3.0;
+                if (c > (double)no) c = (double)no; // at most one transit per interval
                 cap = (int64_t)c;
             }
             if ((cfg->flags & NBT_F_PLANET1_ONLY) && j > 0) cap = 1;
             off += cap;
             capmax = std::max(capmax, cap);
         }
+    }
     tt_offsets[(size_t)B * Np] = off;
     if (capmax > INT32_MAX) return nbt_fail(-11, "tt capacity overflow");
     return (int)capmax;
 }
 
-int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* substeps, int32_t* order) {
+int nbt_plan_order(const nbt_config* cfg, const nbt_inputs* in, int32_t* order) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
-    if (!order) return nbt_fail(-10, "nbt_plan_order: NULL argument");
+    if (!in || !order) return nbt_fail(-10, "nbt_plan_order: NULL argument");
+    const double* params = in->params;
+    const int32_t* substeps = in->substeps;
+    const int32_t* nos = in->n_outputs_sys;
     const int B = cfg->n_systems, N = cfg->n_bodies;
     std::iota(order, order + B, 0);
     // key 1: sub-steps, heaviest first (blocks are dispatched in index order, so the long
     // systems start first and a warp's lanes run equal trip counts);
     // key 2: Hill-unstable systems first within a group, so that the lanes that may break (and stop) or
-    // fall back to the slow Kepler path share warps instead of each stalling a healthy warp.
+    // fall back to the slow Kepler path share warps instead of each stalling a healthy warp;
+    // key 3 (per-system grids): longer grids first, so that the lanes of a warp finish together.
     std::vector<uint8_t> unstable(params ? B : 0);
     if (params)
         for (int b = 0; b < B; b++) unstable[b] = hill_separation(params + (size_t)b * N * NBT_NPAR, N) < 4.0 ? 1 : 0;
@@ -1217,12 +1366,13 @@ int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* s
         const int ka = substeps ? substeps[a] : 1, kb = substeps ? substeps[b] : 1;
         if (ka != kb) return ka > kb;
         if (params && unstable[a] != unstable[b]) return unstable[a] > unstable[b];
+        if (nos && nos[a] != nos[b]) return nos[a] > nos[b];
         return false;
     });
     // The multi-step groups (k >= 2) are the critical path of a launch, and a warp's slow-path excursions
     // add up over its lanes (measured: 32 unstable k = 3 systems in one warp run 73 ms, each alone 51 ms, a
     // warp of stable ones 53 ms): there the unstable systems are spread evenly over the group's warps instead.
-    if (params && substeps) {
+    if (params && substeps && !nos) {
         std::vector<int32_t> tmp;
         for (int g0 = 0; g0 < B;) {
             const int k = substeps[order[g0]];
@@ -1253,10 +1403,10 @@ int nbt_plan_order(const nbt_config* cfg, const double* params, const int32_t* s
  * thread's for Np = 2, so the lanes kernel only pays where one thread per system is issue-bound or
  * spills: every system when Np >= 5 (k_integrate<5..8> spill), or when Np >= 3 and the batch leaves
  * most SM sub-partitions empty (B <= 4096: single-system latency improves 1.7x at Np = 3). */
-int nbt_plan_lanes(const nbt_config* cfg, const int32_t* substeps, const int32_t* order) {
+int nbt_plan_lanes(const nbt_config* cfg, const nbt_inputs* in) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
-    (void)substeps; (void)order;
+    (void)in;
     const int B = cfg->n_systems, Np = cfg->n_bodies - 1;
     if (Np <= 1 || B == 0) return 0;
     if (Np >= 5) return B;
@@ -1281,18 +1431,29 @@ int nbt_plan_ls(const nbt_config* cfg, const int64_t* tt_offsets, int64_t* ls_of
 
 /* Sub-step rule, calibrated against the oracle (tests/calibrate_substeps.py).
  * The binding tolerance is the orbit-averaged e to 1e-8 relative; the composition error scales
- * with (dt_sub / P_innermost)^order, so k = ceil(step * R(scheme) / P_min).  Hill-unstable pairs
- * (Delta < 2 sqrt 3) get no extra resolution: they are chaotic and no step size gives parity. */
-int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* substeps) {
+ * with (dt_sub / P_innermost)^order, so k = ceil(step * R(scheme) / P_min).  Systems outside the calibrated
+ * envelope (NBT_S_UNCALIBRATED: close pairs, e > 0.1, heavy planets) get the same rule — their error is set by
+ * chaotic amplification, which no a-priori rule predicts; engine.run_verified checks them by step doubling. */
+int nbt_plan_substeps(const nbt_config* cfg, const nbt_inputs* in, int32_t* substeps) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
-    if (!params || !substeps) return nbt_fail(-10, "nbt_plan_substeps: NULL argument");
-    static const double R[NBT_SCHEME_COUNT + 1] = {8000.0, 400.0, 800.0, 57.5, 250.0, 57.5, 57.5}; /* P_min / dt_sub */
+    if (!in || !in->params || !substeps) return nbt_fail(-10, "nbt_plan_substeps: NULL argument");
+    if ((rc = check_grids(cfg, in)) != 0) return rc;
+    const double* params = in->params;
+    /* P_min / dt_sub per scheme id (WH2, Y4, SABA4, M64, C4, SBABC3, AUTO, IAS15 (unused), WHFAST (dt = 1e-3 d)) */
+    static const double R[9] = {8000.0, 400.0, 800.0, 57.5, 250.0, 57.5, 57.5, 0.0, 0.0};
     const int B = cfg->n_systems, N = cfg->n_bodies;
-    const double step = cfg->n_days / (double)(cfg->n_outputs - 1);
     const bool automatic = cfg->scheme == NBT_SCHEME_AUTO;
     for (int b = 0; b < B; b++) {
         const double* par = params + (size_t)b * N * NBT_NPAR;
+        const double step = grid_days(cfg, in, b) / (double)(grid_outputs(cfg, in, b) - 1);
+        if (cfg->scheme == NBT_SCHEME_WHFAST) {   /* full steps of REBOUND's default dt = 1e-3 d per output interval */
+            double k = floor(step / 1e-3 * (1.0 + 1e-12));
+            if (k > 1e9) k = 1e9;
+            substeps[b] = (int32_t)k;
+            continue;
+        }
+        if (cfg->scheme == NBT_SCHEME_IAS15) { substeps[b] = 1; continue; }
         double pmin = INFINITY;
         for (int j = 1; j < N; j++) {
             const double P = par[j * NBT_NPAR + NBT_P_P];
@@ -1311,14 +1472,23 @@ int nbt_plan_substeps(const nbt_config* cfg, const double* params, int32_t* subs
     return 0;
 }
 
-int64_t nbt_count_steps(const nbt_config* cfg, const int32_t* substeps) {
+int64_t nbt_count_steps(const nbt_config* cfg, const nbt_inputs* in) {
     if (check_cfg(cfg)) return -1;
-    const int64_t S = scheme_stages(cfg->scheme), per = (int64_t)cfg->n_outputs - 1;
-    if (cfg->substeps > 0 || !substeps) return (int64_t)cfg->n_systems * per * S * std::max(cfg->substeps, 1);
+    const int32_t* substeps = in ? in->substeps : nullptr;
+    const int64_t S = scheme_stages(cfg->scheme);
     const int64_t S_alt = cfg->scheme == NBT_SCHEME_AUTO ? scheme_stages(NBT_SCHEME_C4) : S;
     int64_t tot = 0;
-    for (int b = 0; b < cfg->n_systems; b++) tot += substeps[b] < 0 ? -(int64_t)substeps[b] * S_alt : (int64_t)substeps[b] * S;
-    return tot * per;
+    for (int b = 0; b < cfg->n_systems; b++) {
+        const int64_t per = (int64_t)grid_outputs(cfg, in, b) - 1;
+        int64_t k = (cfg->substeps > 0 || !substeps) ? std::max(cfg->substeps, 1) : substeps[b];
+        tot += per * (k < 0 ? -k * S_alt : k * S);
+    }
+    return tot;
+}
+
+int nbt_uncalibrated(const double* params_one, int n_bodies) {
+    if (!params_one || n_bodies < 2 || n_bodies > NBT_MAX_BODIES) return 0;
+    return ::nbt_uncalibrated_impl(params_one, n_bodies) ? 1 : 0;
 }
 
 static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, void* cuda_stream,
@@ -1329,8 +1499,28 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
     const bool scan = scan_series != nullptr;
     if (scan && !scan_times) return nbt_fail(-10, "nbt_analyze: times is required");
     if (!in->params || !in->tt_offsets) return nbt_fail(-10, "nbt_run: params and tt_offsets are required");
-    if (!out->tt || !out->ttv || !out->n_tt || !out->period || !out->t0 || !out->ttv_max || !out->status)
-        return nbt_fail(-10, "nbt_run: tt, ttv, n_tt, period, t0, ttv_max, status are required");
+    if (!out->status) return nbt_fail(-10, "nbt_run: status is required");
+    if ((cfg->flags & NBT_F_DEVICE_PTRS) && (!out->tt || !out->ttv || !out->n_tt || !out->period || !out->t0 || !out->ttv_max))
+        return nbt_fail(-10, "nbt_run: with device pointers tt, ttv, n_tt, period, t0, ttv_max are required (the kernels write them)");
+    if ((rc = check_grids(cfg, in)) != 0) return rc;
+    if (scan && in->n_days_sys) return nbt_fail(-14, "nbt_analyze: per-system grids are not supported");
+    if (cfg->flags & NBT_F_LOGLIKE) {
+        const nbt_like* L = in->like;
+        if (!L || !out->loglike) return nbt_fail(-15, "nbt_run: NBT_F_LOGLIKE needs inputs.like and outputs.loglike");
+        if (L->n_data < 0 || (L->kind != NBT_LIKE_NESTED && L->kind != NBT_LIKE_TTVFIT))
+            return nbt_fail(-15, "nbt_run: bad nbt_like (kind %d, n_data %d)", L->kind, L->n_data);
+        if (L->kind == NBT_LIKE_NESTED && (!L->c0 || !L->c1 || (L->n_data > 0 && (!L->x || !L->y || !L->yerr))))
+            return nbt_fail(-15, "nbt_run: NBT_LIKE_NESTED needs c0, c1, x, y, yerr");
+        if (L->kind == NBT_LIKE_NESTED && L->loss != NBT_LOSS_LINEAR && L->loss != NBT_LOSS_SOFT_L1)
+            return nbt_fail(-15, "nbt_run: unknown loss %d", L->loss);
+        if (L->kind == NBT_LIKE_TTVFIT && (L->n_data < 1 || !L->has_data || !L->tc || !L->tc_err || !L->orbit))
+            return nbt_fail(-15, "nbt_run: NBT_LIKE_TTVFIT needs has_data, tc, tc_err, orbit and n_data >= 1");
+    }
+    if ((cfg->flags & NBT_F_LS_PEAKS) && (!(cfg->flags & NBT_F_LS_OC) || !out->ls_oc_peaks || !in->ls_offsets))
+        return nbt_fail(-16, "nbt_run: NBT_F_LS_PEAKS needs NBT_F_LS_OC, inputs.ls_offsets and outputs.ls_oc_peaks");
+    if ((cfg->flags & NBT_F_LS_PEAKS) && (cfg->flags & NBT_F_DEVICE_PTRS) && (!out->ls_oc_power || !out->ls_oc_nfreq))
+        return nbt_fail(-16, "nbt_run: with device pointers NBT_F_LS_PEAKS needs ls_oc_power and ls_oc_nfreq as scratch");
+    if (!scan && cfg->scheme == NBT_SCHEME_WHFAST) return nbt_fail(-7, "NBT_SCHEME_WHFAST is not available in this build");
     if ((cfg->flags & NBT_F_MEANS) && (!out->mean_a || !out->mean_e || !out->mean_inc))
         return nbt_fail(-10, "nbt_run: NBT_F_MEANS needs mean_a, mean_e, mean_inc");
     if (!scan && cfg->substeps <= 0 && !in->substeps) return nbt_fail(-12, "nbt_run: cfg.substeps <= 0 needs inputs.substeps");
@@ -1375,6 +1565,7 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
                                   ? nbt_ls_nfreq(cfg->n_days - cfg->n_days / (double)(NO - 1), cfg->ls_rv_minfreq,
                                                  cfg->ls_rv_maxfreq, cfg->ls_samples_per_peak) : 0;
         Arena ar;
+        const int fl0 = cfg->flags;
         struct Buf { size_t off, bytes; const void* h_in; void* h_out; };
         auto mk = [&](size_t bytes, const void* hin, void* hout, bool enabled) {
             Buf b{0, 0, nullptr, nullptr};
@@ -1382,7 +1573,22 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
             return b;
         };
         const int fl = cfg->flags;
+        const nbt_like* HL = (fl0 & NBT_F_LOGLIKE) ? in->like : nullptr;
+        const bool nested = HL && HL->kind == NBT_LIKE_NESTED, ttvfit = HL && HL->kind == NBT_LIKE_TTVFIT;
+        const size_t nd = HL ? (size_t)HL->n_data : 0;
         Buf b_params = mk((size_t)B * N * NBT_NPAR * 8, in->params, nullptr, true);
+        Buf b_nds = mk((size_t)B * 8, in->n_days_sys, nullptr, !scan && in->n_days_sys != nullptr);
+        Buf b_nos = mk((size_t)B * 4, in->n_outputs_sys, nullptr, !scan && in->n_outputs_sys != nullptr);
+        Buf b_lc0 = mk((size_t)B * 8, HL ? HL->c0 : nullptr, nullptr, nested);
+        Buf b_lc1 = mk((size_t)B * 8, HL ? HL->c1 : nullptr, nullptr, nested);
+        Buf b_lx = mk(nd * 8, HL ? HL->x : nullptr, nullptr, nested);
+        Buf b_ly = mk(nd * 8, HL ? HL->y : nullptr, nullptr, nested);
+        Buf b_le = mk(nd * 8, HL ? HL->yerr : nullptr, nullptr, nested);
+        Buf b_lhas = mk((size_t)Np * 4, HL ? HL->has_data : nullptr, nullptr, ttvfit);
+        Buf b_ltc = mk((size_t)Np * nd * 8, HL ? HL->tc : nullptr, nullptr, ttvfit);
+        Buf b_lte = mk((size_t)Np * nd * 8, HL ? HL->tc_err : nullptr, nullptr, ttvfit);
+        Buf b_lorb = mk(nd * 4, HL ? HL->orbit : nullptr, nullptr, ttvfit);
+        Buf b_ll = mk((size_t)B * 8, nullptr, out->loglike, HL != nullptr);
         Buf b_sub = mk((size_t)B * 4, in->substeps, nullptr, !scan && cfg->substeps <= 0);
         Buf b_order = mk((size_t)B * 4, in->order, nullptr, !scan && in->order != nullptr);
         Buf b_times = mk((size_t)NO * 8, scan_times, nullptr, scan);
@@ -1406,12 +1612,15 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         Buf b_orb = mk(nq * B * Np * 2 * 8, nullptr, out->orbit_xz, (fl & NBT_F_ORBIT) && out->orbit_xz);
         Buf b_ser = scan ? mk((size_t)NO * B * W * 8, scan_series, nullptr, true)
                          : mk((size_t)NO * B * W * 8, nullptr, out->series, (fl & NBT_F_SERIES) && out->series);
-        Buf b_lsp = mk((size_t)nls * 8, nullptr, out->ls_oc_power, nls > 0 && out->ls_oc_power);
-        Buf b_lsn = mk((size_t)nsp * 4, nullptr, out->ls_oc_nfreq, nls > 0 && out->ls_oc_nfreq);
+        const bool peaks = (fl & NBT_F_LS_PEAKS) != 0;
+        Buf b_lsp = mk((size_t)nls * 8, nullptr, out->ls_oc_power, nls > 0 && (out->ls_oc_power || peaks));
+        Buf b_lsn = mk((size_t)nsp * 4, nullptr, out->ls_oc_nfreq, nls > 0 && (out->ls_oc_nfreq || peaks));
+        Buf b_lspk = mk((size_t)nsp * NBT_LS_NPEAKS * 2 * 8, nullptr, out->ls_oc_peaks, nls > 0 && peaks);
         Buf b_lsrv = mk((size_t)B * nf_rv * 8, nullptr, out->ls_rv_power, need_rv_ws && (fl & NBT_F_LS_RV) && out->ls_rv_power);
         NBT_CUDA(cudaMallocAsync((void**)&arena, ar.size ? ar.size : 256, st));
         auto dp = [&](const Buf& b) -> void* { return b.bytes ? (void*)(arena + b.off) : nullptr; };
-        Buf* ins[] = {&b_params, &b_sub, &b_order, &b_tto, &b_lso, &b_times, &b_ser};
+        Buf* ins[] = {&b_params, &b_sub, &b_order, &b_tto, &b_lso, &b_times, &b_ser, &b_nds, &b_nos,
+                      &b_lc0, &b_lc1, &b_lx, &b_ly, &b_le, &b_lhas, &b_ltc, &b_lte, &b_lorb};
         for (Buf* b : ins)
             if (b->bytes && b->h_in) NBT_CUDA(cudaMemcpyAsync(dp(*b), b->h_in, b->bytes, cudaMemcpyHostToDevice, st));
         // NaN-fill the CSR transit buffers (all-ones bytes are a NaN): unused capacity reads as NaN
@@ -1422,6 +1631,17 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         din.params = (const double*)dp(b_params); din.substeps = (const int32_t*)dp(b_sub);
         din.order = (const int32_t*)dp(b_order); din.tt_offsets = (const int64_t*)dp(b_tto);
         din.ls_offsets = (const int64_t*)dp(b_lso);
+        din.n_days_sys = (const double*)dp(b_nds); din.n_outputs_sys = (const int32_t*)dp(b_nos);
+        nbt_like dlike;
+        memset(&dlike, 0, sizeof dlike);
+        din.like = nullptr;
+        if (HL) {
+            dlike.kind = HL->kind; dlike.loss = HL->loss; dlike.n_data = HL->n_data;
+            dlike.c0 = (const double*)dp(b_lc0); dlike.c1 = (const double*)dp(b_lc1); dlike.x = (const double*)dp(b_lx);
+            dlike.y = (const double*)dp(b_ly); dlike.yerr = (const double*)dp(b_le); dlike.has_data = (const int32_t*)dp(b_lhas);
+            dlike.tc = (const double*)dp(b_ltc); dlike.tc_err = (const double*)dp(b_lte); dlike.orbit = (const int32_t*)dp(b_lorb);
+            din.like = &dlike;
+        }
         nbt_outputs dout;
         memset(&dout, 0, sizeof dout);
         dout.tt = (double*)dp(b_tt); dout.ttv = (double*)dp(b_ttv); dout.n_tt = (int32_t*)dp(b_ntt);
@@ -1431,6 +1651,7 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         dout.rv = (double*)dp(b_rv); dout.rv_max = (double*)dp(b_rvmax); dout.orbit_xz = (double*)dp(b_orb);
         dout.series = (double*)dp(b_ser); dout.ls_oc_power = (double*)dp(b_lsp); dout.ls_oc_nfreq = (int32_t*)dp(b_lsn);
         dout.ls_rv_power = (double*)dp(b_lsrv);
+        dout.ls_oc_peaks = (double*)dp(b_lspk); dout.loglike = (double*)dp(b_ll);
         SideStream* side = nullptr;
         NBT_CUDA(get_side(cfg->device, &side));
         NBT_CUDA(cudaEventCreateWithFlags(&ev_fit, cudaEventDisableTiming));
@@ -1453,8 +1674,8 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         NBT_CUDA(enqueue_path(&hcfg, &din, &dout, (double*)dp(b_rvws), st, scan ? (const double*)dp(b_ser) : nullptr,
                               (const double*)dp(b_times), scan_dt, ev_fit, n_ls, ls_bounds, ev_ls));
         // products that are final after k_fit go back on the side stream, overlapping k_ls_oc / the RV stages
-        Buf* early[] = {&b_tt, &b_ttv, &b_ntt, &b_per, &b_t0, &b_max, &b_ma, &b_me, &b_mi, &b_mo, &b_stat, &b_orb, &b_ser};
-        Buf* late[] = {&b_rv, &b_rvmax, &b_lsp, &b_lsn, &b_lsrv};
+        Buf* early[] = {&b_ll, &b_tt, &b_ttv, &b_ntt, &b_per, &b_t0, &b_max, &b_ma, &b_me, &b_mi, &b_mo, &b_stat, &b_orb, &b_ser};
+        Buf* late[] = {&b_rv, &b_rvmax, &b_lsp, &b_lsn, &b_lsrv, &b_lspk};
         NBT_CUDA(cudaStreamWaitEvent(side->st[0], ev_fit, 0));
         for (Buf* b : early)
             if (b->bytes && b->h_out) NBT_CUDA(cudaMemcpyAsync(b->h_out, dp(*b), b->bytes, cudaMemcpyDeviceToHost, side->st[0]));
@@ -1537,11 +1758,12 @@ done:
 
 int nbt_chi2(const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt, int32_t n_systems,
              int32_t n_planets, const double* c0, const double* c1, const double* x, const double* y,
-             const double* yerr, int32_t n_data, double* loglike, int device, int device_ptrs,
+             const double* yerr, int32_t n_data, int32_t loss, double* loglike, int device, int device_ptrs,
              void* cuda_stream) {
     int rc = 0;
     if (!ttv || !tt_offsets || !n_tt || !c0 || !c1 || !x || !y || !yerr || !loglike)
         return nbt_fail(-10, "nbt_chi2: NULL argument");
+    if (loss != NBT_LOSS_LINEAR && loss != NBT_LOSS_SOFT_L1) return nbt_fail(-11, "nbt_chi2: unknown loss %d", loss);
     if (n_systems < 0 || n_planets < 1 || n_data < 0) return nbt_fail(-11, "nbt_chi2: bad sizes");
     if (nbt_device_count() <= 0) return nbt_fail(-100, "nbt_chi2: no CUDA device (there is no CPU fallback)");
     if (n_systems == 0) return 0;
@@ -1579,7 +1801,7 @@ int nbt_chi2(const double* ttv, const int64_t* tt_offsets, const int32_t* n_tt, 
             k_y = (double*)(arena + o_y); k_e = (double*)(arena + o_e); k_ll = (double*)(arena + o_ll);
         }
         k_chi2<<<(n_systems + 127) / 128, 128, 0, st>>>(k_ttv, k_off, k_n, n_systems, n_planets, k_c0, k_c1, k_x, k_y, k_e,
-                                                       n_data, k_ll);
+                                                       n_data, loss, k_ll);
         NBT_CUDA(cudaGetLastError());
         if (!device_ptrs) {
             NBT_CUDA(cudaMemcpyAsync(loglike, k_ll, (size_t)n_systems * 8, cudaMemcpyDeviceToHost, st));

@@ -70,6 +70,49 @@ NBT_HD double nbt_rcp_from(double x, double y0) {
     return fma(y0, fma(e, e, e), y0);
 }
 
+// x^(-3/2) straight from the MUFU seed: y^3 (1 + 3/2 e + 15/8 e^2), e = 1 - x y^2 — one instruction less than
+// nbt_rsqrt followed by two multiplications, and it is what every pair force needs
+NBT_HD double nbt_rsqrt3(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double y2 = y * y;
+    const double e = fma(-x, y2, 1.0);
+    const double y3 = y2 * y;
+    return fma(y3 * e, fma(1.875, e, 1.5), y3);
+#else
+    const double y = 1.0 / sqrt(x);
+    return y * y * y;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Literal constants of the hot loop.  In device code they are read from the constant bank: ptxas folds a
+// __constant__ double into the DFMA / DMUL as a c[bank][offset] operand, whereas a 64-bit literal is rebuilt
+// in a register pair by two IMAD.MOV per use (ncu, round 1: 10 % of the warp instructions of k_integrate<2>
+// were such moves) and costs a third register operand (DFMA with three distinct register operands issues
+// every 2.68 instead of 2 cycles, profiles/README.md).
+// ---------------------------------------------------------------------------------------------
+#define NBT_KLIST(X)                                                                                  \
+    X(c2_1, -1.0 / 24.0) X(c2_2, 1.0 / 720.0) X(c2_3, -1.0 / 40320.0) X(c2_4, 1.0 / 3628800.0)        \
+    X(c2_5, -1.0 / 479001600.0) X(c2_6, 1.0 / 87178291200.0)                                          \
+    X(c3_0, 1.0 / 6.0) X(c3_1, -1.0 / 120.0) X(c3_2, 1.0 / 5040.0) X(c3_3, -1.0 / 362880.0)           \
+    X(c3_4, 1.0 / 39916800.0) X(c3_5, -1.0 / 6227020800.0) X(c3_6, 1.0 / 1307674368000.0)             \
+    X(m6, -1.0 / 6.0) X(i24, 1.0 / 24.0) X(i3, 1.0 / 3.0)
+#if defined(__CUDACC__)
+#define NBT_KDEV(name, val) __constant__ double nbt_kd_##name = (val);
+NBT_KLIST(NBT_KDEV)
+#undef NBT_KDEV
+#endif
+#define NBT_KHOST(name, val) static const double nbt_kh_##name = (val);
+NBT_KLIST(NBT_KHOST)
+#undef NBT_KHOST
+#if defined(__CUDA_ARCH__)
+#define NBT_K(name) nbt_kd_##name
+#else
+#define NBT_K(name) nbt_kh_##name
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Kepler drift of one Jacobi coordinate by h (either sign) under mu = G M_i.
 //   universal Kepler equation  F(X) = r0 X + eta G2 + zeta G3 - h = 0,   G_k = X^k c_k(beta X^2)
@@ -79,20 +122,28 @@ NBT_HD double nbt_rcp_from(double x, double y0) {
 // Taylor shift of G1..G3 to the corrected X.  If the correction is not small the (warp-
 // divergent, rare) safe loop below iterates to convergence and flags NBT_S_KEPLER on failure.
 // ---------------------------------------------------------------------------------------------
+template <bool ESTRIN = true>
 NBT_HD void nbt_stumpff(double z, double& c2, double& c3) {
     // c2 = 1/2! - z/4! + z^2/6! - ...,  c3 = 1/3! - z/5! + z^2/7! - ...   (|z| <~ 0.5)
-    // Estrin's scheme: dependency depth 3 instead of Horner's 6 (the stage is latency-bound when
-    // few warps are resident, e.g. the long systems at the tail of a launch)
-    const double z2 = z * z, z4 = z2 * z2;
-    {
-        const double p01 = fma(z, -1.0 / 24.0, 0.5), p23 = fma(z, -1.0 / 40320.0, 1.0 / 720.0),
-                     p45 = fma(z, -1.0 / 479001600.0, 1.0 / 3628800.0);
-        c2 = fma(z4, fma(z2, 1.0 / 87178291200.0, p45), fma(z2, p23, p01));
-    }
-    {
-        const double p01 = fma(z, -1.0 / 120.0, 1.0 / 6.0), p23 = fma(z, -1.0 / 362880.0, 1.0 / 5040.0),
-                     p45 = fma(z, -1.0 / 6227020800.0, 1.0 / 39916800.0);
-        c3 = fma(z4, fma(z2, 1.0 / 1307674368000.0, p45), fma(z2, p23, p01));
+    if (ESTRIN) {
+        // Estrin's scheme: dependency depth 3 instead of Horner's 6 (the latency variant: few warps resident)
+        const double z2 = z * z, z4 = z2 * z2;
+        {
+            const double p01 = fma(z, NBT_K(c2_1), 0.5), p23 = fma(z, NBT_K(c2_3), NBT_K(c2_2)),
+                         p45 = fma(z, NBT_K(c2_5), NBT_K(c2_4));
+            c2 = fma(z4, fma(z2, NBT_K(c2_6), p45), fma(z2, p23, p01));
+        }
+        {
+            const double p01 = fma(z, NBT_K(c3_1), NBT_K(c3_0)), p23 = fma(z, NBT_K(c3_3), NBT_K(c3_2)),
+                         p45 = fma(z, NBT_K(c3_5), NBT_K(c3_4));
+            c3 = fma(z4, fma(z2, NBT_K(c3_6), p45), fma(z2, p23, p01));
+        }
+    } else {
+        // Horner: the same twelve FP64 instructions, but one constant-bank operand per FMA and no coefficient
+        // held in a register (Estrin's p23 / p45 need one each): the register-starved kernels (Np >= 3, the
+        // throughput variant) interleave enough chains of their own
+        c2 = fma(fma(fma(fma(fma(fma(z, NBT_K(c2_6), NBT_K(c2_5)), z, NBT_K(c2_4)), z, NBT_K(c2_3)), z, NBT_K(c2_2)), z, NBT_K(c2_1)), z, 0.5);
+        c3 = fma(fma(fma(fma(fma(fma(z, NBT_K(c3_6), NBT_K(c3_5)), z, NBT_K(c3_4)), z, NBT_K(c3_3)), z, NBT_K(c3_2)), z, NBT_K(c3_1)), z, NBT_K(c3_0));
     }
 }
 
@@ -185,139 +236,132 @@ NBT_HD void nbt_kepler_mid(double mu, double h, double r0, double eta, double be
     if (!ok) nbt_kepler_safe(mu, h, r0, eta, beta, zeta, X, G1, G2, G3, r, status);
 }
 
-// out-of-line twin of the fallback: with two planets per thread the hot loop fits the instruction
-// caches better when the (never taken) fallback is a call instead of two inlined copies
-// (measured on B200: +5 % at Np = 2, -3.5 % at Np = 3, so COLD is chosen by Np)
-NBT_HD_COLD void nbt_kepler_safe_cold(double mu, double h, double r0, double eta, double beta, double zeta,
-                                      double& X, double& G1, double& G2, double& G3, double& r, int& status) {
-    nbt_kepler_mid(mu, h, r0, eta, beta, zeta, X, G1, G2, G3, r, status);
-}
+// The one-shot solve in two phases, no branch inside either.
+//   nbt_kepler_solve: Kepler's equation — first guess, Stumpff functions, one quartic correction d, Taylor shift of
+//                     G1..G3 and r to X + d, Gauss f and g (in `m`); returns whether the convergence test held.
+//   nbt_kepler_apply: the new position / velocity / radius, written in place (12 FMAs).
+// Between the two the caller redoes the rare failures out of line (middle path / fallback, nbt_kepler_finish)
+// and makes their `m` the identity update (nbt_kepler_identity), so that nothing is selected or copied on the
+// hot path: the drifts of a group of planets are two basic blocks whose dependency chains interleave.
+// Written for few FP64 issue slots — a lone warp already fills the FP64 pipe of its SM sub-partition —:
+// scalings by literals ride on FMAs, the 1/r0-scaled series coefficients are formed once, literals come from the
+// constant bank.
+struct nbt_kepler_mid_t { double fm1, g, fd, gdm1, r, ir; };   // Gauss f - 1, g, fdot, gdot - 1; new radius and its reciprocal
 
-template <bool COLD = false>
-NBT_HD void nbt_kepler_drift(double mu, double h, double& x, double& y, double& z, double& vx,
-                             double& vy, double& vz, double& r0io, double& ir0io, int& status) {
-    // Written for a short dependency chain (see nbt_stumpff): everything that depends only on the
-    // carried radius and h is formed first, polynomials are evaluated Estrin/Horner-in-the-small-
-    // variable, and the post-correction radius is Taylor-shifted in parallel with G1..G3.
-    const double ir0 = ir0io, r0 = r0io;
+template <bool ESTRIN = true>
+NBT_HD bool nbt_kepler_solve(double mu, double h, double x, double y, double z, double vx, double vy, double vz,
+                             double r0, double ir0, nbt_kepler_mid_t& m) {
     const double s = h * ir0, s2 = s * s;
-    const double kA = 0.5 * ir0, kB = (1.0 / 6.0) * ir0, kB5 = (5.0 / 6.0) * ir0, kC = (-1.0 / 24.0) * ir0;
     const double mi0 = -mu * ir0;
     const double v02 = fma(vx, vx, fma(vy, vy, vz * vz));
     const double eta = fma(x, vx, fma(y, vy, z * vz));
-    const double beta = fma(2.0 * mu, ir0, -v02);
+    const double beta = fma(-2.0, mi0, -v02);
     const double zeta = fma(-beta, r0, mu);
     const double be = beta * eta;
-
     // X0: reversion of h = r0 X + eta X^2/2 + zeta X^3/6 - beta eta X^4/24 ...
-    //   X = s - A s^2 + (2A^2 - B) s^3 + (-5A^3 + 5AB - C) s^4
-    const double A = eta * kA, AA = A * A;
-    const double Bc = zeta * kB, B5 = zeta * kB5, Cc = be * kC;
-    const double k3 = fma(2.0, AA, -Bc);
-    const double k4 = fma(A, fma(-5.0, AA, B5), -Cc);
-    double X = fma(s2, fma(s, fma(s, k4, k3), -A), s);
+    //   X = s - A s^2 + (2A^2 - B) s^3 + (-5A^3 + 5AB - C) s^4,  A = eta/2r0, B = zeta/6r0, C = -beta eta/24r0
+    const double e1 = eta * ir0, z1 = zeta * ir0, b1 = beta * e1;
+    const double e2 = e1 * e1, z6 = NBT_K(m6) * z1, he = 0.5 * e1;
+    const double k3 = fma(0.5, e2, z6);
+    const double k4 = fma(he, fma(-5.0, z6, -1.25 * e2), NBT_K(i24) * b1);
+    const double X = fma(s2, fma(s, fma(s, k4, k3), -he), s);
 
     const double X2 = X * X, X3 = X2 * X;
     const double zz = beta * X2;
     const double base = fma(r0, X, -h);
     double c2, c3;
-    nbt_stumpff(zz, c2, c3);
+    nbt_stumpff<ESTRIN>(zz, c2, c3);
     const double G0 = fma(-zz, c2, 1.0);
-    double G1 = X * fma(-zz, c3, 1.0), G2 = X2 * c2, G3 = X3 * c3;
+    const double G1 = X * fma(-zz, c3, 1.0), G2 = X2 * c2, G3 = X3 * c3;
     const double F = fma(zeta, G3, fma(eta, G2, base));
-    double r = fma(eta, G1, fma(zeta, G2, r0));                 // dF/dX
+    const double r1 = fma(eta, G1, fma(zeta, G2, r0));          // dF/dX
     const double Fpp = fma(eta, G0, zeta * G1);                 // d2F/dX2
     const double Fppp = fma(zeta, G0, -be * G1);                // d3F/dX3
-    double ir = nbt_rcp(r);
-    const double u = -F * ir;
-    const double a2 = (0.5 * ir) * Fpp, a3 = ((1.0 / 6.0) * ir) * Fppp;
-    const double d = u * fma(u, fma(u, fma(2.0 * a2, a2, -a3), -a2), 1.0);
-
-    if (fabs(d) <= 2e-4 * fabs(X) && zz < 0.5 && zz > -0.5) {
-        // shift G1..G3 and r from X to X + d (Horner in d):  dG_k/dX = G_{k-1},  dG0/dX = -beta G1,
-        // dr/dX = Fpp, d2r/dX2 = Fppp, d3r/dX3 = -beta Fpp
-        const double nb6 = (-1.0 / 6.0) * beta;
-        const double hG0 = 0.5 * G0, hG1 = 0.5 * G1;
-        const double nG3 = fma(d, fma(d, fma(d, (1.0 / 6.0) * G0, hG1), G2), G3);
-        const double nG2 = fma(d, fma(d, fma(d, nb6 * G1, hG0), G1), G2);
-        const double nG1 = fma(d, fma(d, fma(d, nb6 * G0, -beta * hG1), G0), G1);
-        r = fma(d, fma(d, fma(d, nb6 * Fpp, 0.5 * Fppp), Fpp), r);
-        G1 = nG1; G2 = nG2; G3 = nG3;
-        ir = nbt_rcp_from(r, ir);
-    } else {
-        X += d;
-        if (COLD) nbt_kepler_safe_cold(mu, h, r0, eta, beta, zeta, X, G1, G2, G3, r, status);   // middle path + fallback
-        else nbt_kepler_safe(mu, h, r0, eta, beta, zeta, X, G1, G2, G3, r, status);
-        ir = 1.0 / r;
-    }
+    const double ir1 = nbt_rcp(r1);
+    // quartic correction d = u (1 - a2 u + (2 a2^2 - a3) u^2), u = -F/r1, a2 = Fpp/(2 r1), a3 = Fppp/(6 r1)
+    const double u = -F * ir1;
+    const double w = ir1 * Fpp, v6 = ir1 * Fppp, hw = 0.5 * w;
+    const double d = u * fma(u, fma(u, fma(hw, w, NBT_K(m6) * v6), -hw), 1.0);
+    // shift G1..G3 and r from X to X + d (Horner in d):  dG_k/dX = G_{k-1},  dG0/dX = -beta G1,
+    // dr/dX = Fpp, d2r/dX2 = Fppp, d3r/dX3 = -beta Fpp
+    const double hd = 0.5 * d, td = NBT_K(i3) * d;
+    const double bG1 = beta * G1, bG0 = beta * G0, bF = beta * Fpp;
+    const double nG3 = fma(d, fma(hd, fma(td, G0, G1), G2), G3);
+    const double nG2 = fma(d, fma(hd, fma(-td, bG1, G0), G1), G2);
+    const double nG1 = fma(d, fma(-hd, fma(td, bG0, bG1), G0), G1);
+    const double r = fma(d, fma(hd, fma(-td, bF, Fppp), Fpp), r1);
+    const double ir = nbt_rcp_from(r, ir1);
     // Gauss f, g in the round-off-friendly "minus one" form
+    m.fm1 = mi0 * nG2;
+    m.g = fma(-mu, nG3, h);
+    m.fd = (mi0 * nG1) * ir;
+    m.gdm1 = (-mu * nG2) * ir;
+    m.r = r; m.ir = ir;
+    return fabs(d) <= 2e-4 * fabs(X) && zz < 0.5 && zz > -0.5;
+}
+
+NBT_HD void nbt_kepler_apply(const nbt_kepler_mid_t& m, double& x, double& y, double& z, double& vx, double& vy,
+                             double& vz, double& r_out, double& ir_out) {
+    const double nx = fma(m.fm1, x, fma(m.g, vx, x)), ny = fma(m.fm1, y, fma(m.g, vy, y)), nz = fma(m.fm1, z, fma(m.g, vz, z));
+    vx = fma(m.fd, x, fma(m.gdm1, vx, vx));
+    vy = fma(m.fd, y, fma(m.gdm1, vy, vy));
+    vz = fma(m.fd, z, fma(m.gdm1, vz, vz));
+    x = nx; y = ny; z = nz;
+    r_out = m.r; ir_out = m.ir;
+}
+
+// `m` of a planet whose drift is already done (by nbt_kepler_finish): nbt_kepler_apply leaves its state alone
+NBT_HD void nbt_kepler_identity(double r, double ir, nbt_kepler_mid_t& m) {
+    m.fm1 = 0.0; m.g = 0.0; m.fd = 0.0; m.gdm1 = 0.0; m.r = r; m.ir = ir;
+}
+
+// slow continuation of a drift whose one-shot solve missed its tolerance (out of line: never taken in normal
+// steps): the middle path, then the bracketed Newton.  Everything goes in and out BY VALUE: a reference to the
+// caller's state would pin the whole state array to local memory on the hot path (ptxas stores it before every
+// potential call).
+struct nbt_body { double x, y, z, vx, vy, vz, r, ir; int status; };
+
+NBT_HD_COLD nbt_body nbt_kepler_finish(double mu, double h, double x, double y, double z, double vx, double vy,
+                                       double vz, double r0, double ir0) {
+    nbt_body o;
+    o.status = 0;
+    const double mi0 = -mu * ir0;
+    const double v02 = fma(vx, vx, fma(vy, vy, vz * vz));
+    const double eta = fma(x, vx, fma(y, vy, z * vz));
+    const double beta = fma(-2.0, mi0, -v02);
+    const double zeta = fma(-beta, r0, mu);
+    // first guess: the cubic reversion of the one-shot solve
+    const double s = h * ir0;
+    const double A = 0.5 * eta * ir0, Bc = zeta * ir0 / 6.0;
+    double X = s * (1.0 + s * (-A + s * (2.0 * A * A - Bc)));
+    double G1 = 0.0, G2 = 0.0, G3 = 0.0, r = r0;
+    nbt_kepler_mid(mu, h, r0, eta, beta, zeta, X, G1, G2, G3, r, o.status);
+    const double ir = 1.0 / r;
     const double fm1 = mi0 * G2;
     const double g = fma(-mu, G3, h);
     const double fd = (mi0 * G1) * ir;
     const double gdm1 = (-mu * G2) * ir;
-    const double nx = fma(fm1, x, fma(g, vx, x)), ny = fma(fm1, y, fma(g, vy, y)),
-                 nz = fma(fm1, z, fma(g, vz, z));
-    vx = fma(fd, x, fma(gdm1, vx, vx));
-    vy = fma(fd, y, fma(gdm1, vy, vy));
-    vz = fma(fd, z, fma(gdm1, vz, vz));
-    x = nx; y = ny; z = nz;
-    r0io = r; ir0io = ir;
+    o.x = fma(fm1, x, fma(g, vx, x)); o.y = fma(fm1, y, fma(g, vy, y)); o.z = fma(fm1, z, fma(g, vz, z));
+    o.vx = fma(fd, x, fma(gdm1, vx, vx)); o.vy = fma(fd, y, fma(gdm1, vy, vy)); o.vz = fma(fd, z, fma(gdm1, vz, vz));
+    o.r = r; o.ir = ir;
+    return o;
 }
 
-// Branch-free form of the one-shot solve: the same arithmetic as the fast path of nbt_kepler_drift,
-// committed through selects only when the convergence test holds; returns that test.  With no branch
-// inside, the drifts of all planets of a stage form ONE basic block, so the compiler interleaves
-// their dependency chains end to end (a lone warp is latency-bound: profiles/README.md); the caller
-// re-runs the rare failures through nbt_kepler_drift afterwards.
-NBT_HD bool nbt_kepler_drift_fast(double mu, double h, double& x, double& y, double& z, double& vx,
-                                  double& vy, double& vz, double& r0io, double& ir0io) {
-    const double ir0 = ir0io, r0 = r0io;
-    const double s = h * ir0, s2 = s * s;
-    const double kA = 0.5 * ir0, kB = (1.0 / 6.0) * ir0, kB5 = (5.0 / 6.0) * ir0, kC = (-1.0 / 24.0) * ir0;
-    const double mi0 = -mu * ir0;
-    const double v02 = fma(vx, vx, fma(vy, vy, vz * vz));
-    const double eta = fma(x, vx, fma(y, vy, z * vz));
-    const double beta = fma(2.0 * mu, ir0, -v02);
-    const double zeta = fma(-beta, r0, mu);
-    const double be = beta * eta;
-    const double A = eta * kA, AA = A * A;
-    const double Bc = zeta * kB, B5 = zeta * kB5, Cc = be * kC;
-    const double k3 = fma(2.0, AA, -Bc);
-    const double k4 = fma(A, fma(-5.0, AA, B5), -Cc);
-    const double X = fma(s2, fma(s, fma(s, k4, k3), -A), s);
-    const double X2 = X * X, X3 = X2 * X;
-    const double zz = beta * X2;
-    const double base = fma(r0, X, -h);
-    double c2, c3;
-    nbt_stumpff(zz, c2, c3);
-    const double G0 = fma(-zz, c2, 1.0);
-    const double G1 = X * fma(-zz, c3, 1.0), G2 = X2 * c2, G3 = X3 * c3;
-    const double F = fma(zeta, G3, fma(eta, G2, base));
-    const double r1 = fma(eta, G1, fma(zeta, G2, r0));
-    const double Fpp = fma(eta, G0, zeta * G1);
-    const double Fppp = fma(zeta, G0, -be * G1);
-    const double ir1 = nbt_rcp(r1);
-    const double u = -F * ir1;
-    const double a2 = (0.5 * ir1) * Fpp, a3 = ((1.0 / 6.0) * ir1) * Fppp;
-    const double d = u * fma(u, fma(u, fma(2.0 * a2, a2, -a3), -a2), 1.0);
-    const bool ok = fabs(d) <= 2e-4 * fabs(X) && zz < 0.5 && zz > -0.5;
-    const double nb6 = (-1.0 / 6.0) * beta;
-    const double hG0 = 0.5 * G0, hG1 = 0.5 * G1;
-    const double nG3 = fma(d, fma(d, fma(d, (1.0 / 6.0) * G0, hG1), G2), G3);
-    const double nG2 = fma(d, fma(d, fma(d, nb6 * G1, hG0), G1), G2);
-    const double nG1 = fma(d, fma(d, fma(d, nb6 * G0, -beta * hG1), G0), G1);
-    const double r = fma(d, fma(d, fma(d, nb6 * Fpp, 0.5 * Fppp), Fpp), r1);
-    const double ir = nbt_rcp_from(r, ir1);
-    const double fm1 = mi0 * nG2;
-    const double g = fma(-mu, nG3, h);
-    const double fd = (mi0 * nG1) * ir;
-    const double gdm1 = (-mu * nG2) * ir;
-    const double nx = fma(fm1, x, fma(g, vx, x)), ny = fma(fm1, y, fma(g, vy, y)), nz = fma(fm1, z, fma(g, vz, z));
-    const double nvx = fma(fd, x, fma(gdm1, vx, vx)), nvy = fma(fd, y, fma(gdm1, vy, vy)), nvz = fma(fd, z, fma(gdm1, vz, vz));
-    x = ok ? nx : x; y = ok ? ny : y; z = ok ? nz : z;
-    vx = ok ? nvx : vx; vy = ok ? nvy : vy; vz = ok ? nvz : vz;
-    r0io = ok ? r : r0; ir0io = ok ? ir : ir0;
-    return ok;
+// r0 / ir0 = |r| and 1/|r| of the incoming position, carried from the end of the previous drift (a kick
+// does not move positions) and refreshed from x, y, z at every output sample; on return they hold the new
+// radius and its reciprocal.  Branchy form (the throughput variant at Np <= 2, the lanes kernel): one-shot
+// solve, else middle path + fallback out of line.
+template <bool ESTRIN>   // the polynomial scheme of the caller's kernel family (Np <= 2: Estrin), so that the branchy and the
+                         // branch-free form of one Np give bit-identical results
+NBT_HD void nbt_kepler_drift(double mu, double h, double& x, double& y, double& z, double& vx,
+                             double& vy, double& vz, double& r0io, double& ir0io, int& status) {
+    nbt_kepler_mid_t m;
+    if (nbt_kepler_solve<ESTRIN>(mu, h, x, y, z, vx, vy, vz, r0io, ir0io, m)) {
+        nbt_kepler_apply(m, x, y, z, vx, vy, vz, r0io, ir0io);
+    } else {
+        const nbt_body o = nbt_kepler_finish(mu, h, x, y, z, vx, vy, vz, r0io, ir0io);
+        x = o.x; y = o.y; z = o.z; vx = o.vx; vy = o.vy; vz = o.vz; r0io = o.r; ir0io = o.ir; status |= o.status;
+    }
 }
 
 // |r| and 1/|r| from the coordinates (start of a run and at every output sample)
@@ -341,6 +385,7 @@ struct nbt_consts {
     double GM[NP];     // G * M_i, M_i = m_0 + ... + m_i          (Kepler mu of Jacobi coordinate i)
     double mr[NP];     // m_i / M_i                               (Jacobi <-> heliocentric shifts)
     double Gm[NP + 1]; // G * m_k for k = 0..NP                   (pair forces)
+    double k02, k12;   // NP == 2: G m_0 M_2 / M_1, G m_1 M_2 / M_1 (closed form of nbt_accel)
 };
 
 // Jacobi accelerations from the interaction Hamiltonian
@@ -350,25 +395,42 @@ template <int NP>
 NBT_HD void nbt_accel(const nbt_state<NP>& s, const nbt_consts<NP>& c, double (&ax)[NP],
                       double (&ay)[NP], double (&az)[NP]) {
     if (NP == 1) { ax[0] = ay[0] = az[0] = 0.0; return; }
+    if (NP == 2) {
+        // two planets, everything substituted (21 DMUL + 22 DFMA + 3 DADD instead of 31 + 19 + 12 in the general form):
+        //   q2 = r'_2 + (m1/M1) r'_1,  d = q2 - r'_1
+        //   a'_1 = G m2 ( d/|d|^3 - q2/|q2|^3 )
+        //   a'_2 = G M2 r'_2/|r'_2|^3 - (G m0 M2/M1) q2/|q2|^3 - (G m1 M2/M1) d/|d|^3
+        const double qx = fma(c.mr[0], s.x[0], s.x[1]), qy = fma(c.mr[0], s.y[0], s.y[1]), qz = fma(c.mr[0], s.z[0], s.z[1]);
+        const double dx = qx - s.x[0], dy = qy - s.y[0], dz = qz - s.z[0];
+        const double w02 = nbt_rsqrt3(fma(qx, qx, fma(qy, qy, qz * qz)));
+        const double w12 = nbt_rsqrt3(fma(dx, dx, fma(dy, dy, dz * dz)));
+        const double ir = s.ir[1];
+        const double c2 = c.GM[1] * ir * (ir * ir);
+        const double t12 = c.Gm[2] * w12, t02 = c.Gm[2] * w02;
+        const double u02 = c.k02 * w02, u12 = c.k12 * w12;
+        ax[0] = fma(t12, dx, -t02 * qx); ay[0] = fma(t12, dy, -t02 * qy); az[0] = fma(t12, dz, -t02 * qz);
+        ax[1] = fma(-u12, dx, fma(-u02, qx, c2 * s.x[1]));
+        ay[1] = fma(-u12, dy, fma(-u02, qy, c2 * s.y[1]));
+        az[1] = fma(-u12, dz, fma(-u02, qz, c2 * s.z[1]));
+        return;
+    }
     double qx[NP], qy[NP], qz[NP];
     {   // heliocentric positions: q_i = r'_i + S_{i-1},  S_i = S_{i-1} + (m_i/M_i) r'_i
-        double Sx = 0.0, Sy = 0.0, Sz = 0.0;
+        qx[0] = s.x[0]; qy[0] = s.y[0]; qz[0] = s.z[0];
+        double Sx = c.mr[0] * s.x[0], Sy = c.mr[0] * s.y[0], Sz = c.mr[0] * s.z[0];
 #pragma unroll
-        for (int i = 0; i < NP; i++) {
+        for (int i = 1; i < NP; i++) {
             qx[i] = s.x[i] + Sx; qy[i] = s.y[i] + Sy; qz[i] = s.z[i] + Sz;
-            Sx = fma(c.mr[i], s.x[i], Sx); Sy = fma(c.mr[i], s.y[i], Sy); Sz = fma(c.mr[i], s.z[i], Sz);
+            if (i + 1 < NP) { Sx = fma(c.mr[i], s.x[i], Sx); Sy = fma(c.mr[i], s.y[i], Sy); Sz = fma(c.mr[i], s.z[i], Sz); }
         }
     }
     double a0x = 0.0, a0y = 0.0, a0z = 0.0; // star
     double px[NP], py[NP], pz[NP];          // planets (inertial accelerations, included pairs only)
-#pragma unroll
-    for (int i = 0; i < NP; i++) px[i] = py[i] = pz[i] = 0.0;
+    px[0] = py[0] = pz[0] = 0.0;
 #pragma unroll
     for (int i = 1; i < NP; i++) { // star - planet i (i >= 2 in 1-based numbering)
-        const double r2 = fma(qx[i], qx[i], fma(qy[i], qy[i], qz[i] * qz[i]));
-        const double ir = nbt_rsqrt(r2);
-        const double ir2 = ir * ir;
-        const double fs = (c.Gm[i + 1] * ir) * ir2, fp = (-c.Gm[0] * ir) * ir2;
+        const double w = nbt_rsqrt3(fma(qx[i], qx[i], fma(qy[i], qy[i], qz[i] * qz[i])));
+        const double fs = c.Gm[i + 1] * w, fp = -c.Gm[0] * w;
         a0x = fma(fs, qx[i], a0x); a0y = fma(fs, qy[i], a0y); a0z = fma(fs, qz[i], a0z);
         px[i] = fp * qx[i]; py[i] = fp * qy[i]; pz[i] = fp * qz[i];
     }
@@ -377,10 +439,8 @@ NBT_HD void nbt_accel(const nbt_state<NP>& s, const nbt_consts<NP>& c, double (&
 #pragma unroll
         for (int j = i + 1; j < NP; j++) {
             const double dx = qx[j] - qx[i], dy = qy[j] - qy[i], dz = qz[j] - qz[i];
-            const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
-            const double ir = nbt_rsqrt(r2);
-            const double ir2 = ir * ir;
-            const double fi = (c.Gm[j + 1] * ir) * ir2, fj = (-c.Gm[i + 1] * ir) * ir2;
+            const double w = nbt_rsqrt3(fma(dx, dx, fma(dy, dy, dz * dz)));
+            const double fi = c.Gm[j + 1] * w, fj = -c.Gm[i + 1] * w;
             px[i] = fma(fi, dx, px[i]); py[i] = fma(fi, dy, py[i]); pz[i] = fma(fi, dz, pz[i]);
             px[j] = fma(fj, dx, px[j]); py[j] = fma(fj, dy, py[j]); pz[j] = fma(fj, dz, pz[j]);
         }
@@ -389,7 +449,7 @@ NBT_HD void nbt_accel(const nbt_state<NP>& s, const nbt_consts<NP>& c, double (&
 #pragma unroll
     for (int i = 0; i < NP; i++) {
         double jx = px[i] - Ax, jy = py[i] - Ay, jz = pz[i] - Az;
-        Ax = fma(c.mr[i], jx, Ax); Ay = fma(c.mr[i], jy, Ay); Az = fma(c.mr[i], jz, Az);
+        if (i + 1 < NP) { Ax = fma(c.mr[i], jx, Ax); Ay = fma(c.mr[i], jy, Ay); Az = fma(c.mr[i], jz, Az); }
         if (i >= 1) { // + G M_i r'_i / r'_i^3
             const double ir = s.ir[i];
             const double f = (c.GM[i] * ir) * (ir * ir);
@@ -513,6 +573,8 @@ NBT_HD void nbt_setup(const double* par, nbt_state<NP>& s, nbt_consts<NP>& c) {
         s.vz[i] = v0 * (vq * si);
         nbt_radius(s.x[i], s.y[i], s.z[i], s.r[i], s.ir[i]);
     }
+    c.k02 = c.k12 = 0.0;
+    if (NP == 2) { const double q = c.GM[1] / c.GM[0]; c.k02 = c.Gm[0] * q; c.k12 = c.Gm[1] * q; }
 }
 
 // one composition step of size dt; (ax,ay,az) holds the acceleration at the current positions
@@ -532,10 +594,13 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
     }
     for (int st = 0; st < sc.S; st++) {
         const double h = sc.a[st] * dt;
-        if (NP >= 3) {   // branch-free drifts NBT_DRIFT_GROUP planets at a time (one basic block each), failures redone
-            constexpr int GR = NBT_DRIFT_GROUP(NP);
+        if (NP >= 3 || LAT) {
+            // branch-free drifts, NBT_DRIFT_GROUP planets at a time: solve (one basic block), the rare failures redone out
+            // of line, apply (one basic block) — see nbt_kepler_solve
+            constexpr int GR = (NP <= 2) ? NP : NBT_DRIFT_GROUP(NP);
 #pragma unroll
             for (int i0 = 0; i0 < NP; i0 += GR) {
+                nbt_kepler_mid_t m[GR];
                 bool ok[GR];
                 bool all_ok = true;
 #pragma unroll
@@ -543,7 +608,7 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
                     ok[q] = true;
                     if (i0 + q < NP) {
                         const int i = i0 + q;
-                        ok[q] = nbt_kepler_drift_fast(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i]);
+                        ok[q] = nbt_kepler_solve<(NP <= 2)>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], m[q]);
                     }
                     all_ok = all_ok && ok[q];
                 }
@@ -552,26 +617,23 @@ NBT_HD void nbt_step(nbt_state<NP>& s, const nbt_consts<NP>& c, const nbt_scheme
                     for (int q = 0; q < GR; q++)
                         if (i0 + q < NP && !ok[q]) {
                             const int i = i0 + q;
-                            nbt_kepler_drift<true>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
+                            const nbt_body o = nbt_kepler_finish(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i]);
+                            s.x[i] = o.x; s.y[i] = o.y; s.z[i] = o.z; s.vx[i] = o.vx; s.vy[i] = o.vy; s.vz[i] = o.vz;
+                            s.r[i] = o.r; s.ir[i] = o.ir; status |= o.status;
+                            nbt_kepler_identity(o.r, o.ir, m[q]);
                         }
                 }
-            }
-        } else if (LAT && NP <= 2) {   // branch-free drifts in one basic block, rare failures redone afterwards
-            bool ok[NP], all_ok = true;
 #pragma unroll
-            for (int i = 0; i < NP; i++) {
-                ok[i] = nbt_kepler_drift_fast(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i]);
-                all_ok = all_ok && ok[i];
-            }
-            if (!all_ok) {
-#pragma unroll
-                for (int i = 0; i < NP; i++)
-                    if (!ok[i]) nbt_kepler_drift<true>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
+                for (int q = 0; q < GR; q++)
+                    if (i0 + q < NP) {
+                        const int i = i0 + q;
+                        nbt_kepler_apply(m[q], s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i]);
+                    }
             }
         } else {
 #pragma unroll
             for (int i = 0; i < NP; i++)
-                nbt_kepler_drift<(NP <= 2 || NP >= 4)>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
+                nbt_kepler_drift<(NP <= 2)>(c.GM[i], h, s.x[i], s.y[i], s.z[i], s.vx[i], s.vy[i], s.vz[i], s.r[i], s.ir[i], status);
         }
         nbt_accel_grad<NP>(s, c, sc.g[st + 1] * dt * dt, ax, ay, az);
         const double kb = sc.b[st + 1] * dt;
@@ -613,6 +675,13 @@ NBT_HD double nbt_acos(double x) {
 // Jacobi osculating elements with REBOUND's conventions [3P] (primary = COM of lower-index
 // bodies, mu = G M_i): what ps[j].P/a/e/inc/Omega/omega/M return at nbody/simulation.py:150.
 // ---------------------------------------------------------------------------------------------
+// REBOUND moves f, l, M, theta and omega (not Omega, pomega) into [0, 2 pi) at the end of its orbit conversion
+// (reb_tools_mod2pi: fmod, then + 2 pi if negative) [3P]
+NBT_HD double nbt_mod2pi(double f) {
+    f = fmod(f, 2.0 * NBT_PI);
+    return (f < 0.0) ? f + 2.0 * NBT_PI : f;
+}
+
 NBT_HD double nbt_acos2(double num, double den, double disamb) {
     const double cth = num * nbt_rcp(den);
     double val;
@@ -673,6 +742,7 @@ NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, doub
             o.omega = (ez < 0.0) ? -val : val;
         }
         if (o.e <= 1e-8) o.omega = 0.0;
+        o.omega = nbt_mod2pi(o.omega);
         if (MODE >= 2) {
             const double vr = rv * ir;
             const double nmm = o.a / fabs(o.a) * sqrt(fabs(mu / (o.a * o.a * o.a)));
@@ -686,6 +756,7 @@ NBT_HD_COLD nbt_orbit nbt_elements(double mu, double x, double y, double z, doub
                 if (vr < 0.0) ea = -ea;
                 o.M = o.e * sinh(ea) - ea;
             }
+            o.M = nbt_mod2pi(o.M);
         }
     }
     return o;
@@ -722,7 +793,7 @@ NBT_HD bool nbt_elements_fast(double mu, double x, double y, double z, double vx
         const double cth = (nx * ex + ny * ey) * nbt_rsqrt(den2);
         ok = ok && den2 > 0.0 && cth > -1.0 && cth < 1.0;
         const double val = nbt_acos(cth);
-        omega = (ez < 0.0) ? -val : val;
+        omega = (ez < 0.0) ? 2.0 * NBT_PI - val : val;   // in [0, 2 pi) like nbt_mod2pi (val > 0 here: |cth| < 1)
     }
     return ok;
 }
@@ -759,6 +830,8 @@ struct nbt_run_args {
     const int32_t* substeps;   // [B] or nullptr
     const int32_t* order;      // [B] launch order (systems sorted by substeps) or nullptr
     const int64_t* tt_offsets; // [B*NP+1]
+    const double* n_days_sys;      // [B] per-system grids, or nullptr (uniform n_days / n_outputs)
+    const int32_t* n_outputs_sys;  // [B]
     // outputs
     double* tt; int32_t* n_tt;
     double* mean_a; double* mean_e; double* mean_inc; double* mean_omega;
@@ -771,6 +844,44 @@ struct nbt_run_args {
     nbt_scheme scheme_alt;  // NBT_SCHEME_AUTO: C4, for the trailing launch-order slots of a launch (whole blocks)
 };
 
+// NaN in every optional-series sample from output o on of a system that stopped (the buffers are caller-owned and
+// reused: whatever they held before must not pass for a trajectory)
+// (pointers by value: a reference to the kernel's argument block would force a copy of it into local memory)
+NBT_HD_COLD void nbt_fill_broken(double* rv, double* orbit_xz, double* series, int B, int NP, int orbit_stride, int sys, int o0, int NO) {
+    const int W = 3 + 10 * NP;
+    for (int o = o0; o < NO; o++) {
+        if (rv && o > 0) rv[(size_t)(o - 1) * B + sys] = NAN;
+        if (orbit_xz && (o % orbit_stride) == 0) {
+            double* dst = orbit_xz + (((size_t)(o / orbit_stride) * B + sys) * NP) * 2;
+            for (int q = 0; q < 2 * NP; q++) dst[q] = NAN;
+        }
+        if (series) {
+            double* row = series + ((size_t)o * B + sys) * W;
+            for (int q = 0; q < W; q++) row[q] = NAN;
+        }
+    }
+}
+
+// Is a system outside the envelope the sub-step rule was calibrated on?  A planet pair closer than
+// 4 mutual Hill radii ((a_j - a_i) / R_H, R_H = ((m_i + m_j) / 3 M*)^(1/3) (a_i + a_j) / 2, a ~ P^(2/3)), an
+// eccentricity above 0.1, or a planet heavier than 0.013 M*.  par: [n_bodies][NBT_NPAR].
+NBT_HD_COLD bool nbt_uncalibrated_impl(const double* par, int N) {
+    const double Ms = par[NBT_P_M];
+    bool out = false;
+    for (int j = 1; j < N; j++) {
+        const double Pj = par[j * NBT_NPAR + NBT_P_P], mj = par[j * NBT_NPAR + NBT_P_M];
+        if (par[j * NBT_NPAR + NBT_P_E] > 0.1 || mj > 0.013 * Ms) out = true;
+        for (int i = 1; i < j; i++) {
+            const double Pi = par[i * NBT_NPAR + NBT_P_P];
+            if (!(Pi > 0.0) || !(Pj > 0.0) || !(Ms > 0.0)) continue;
+            const double ai = cbrt(Pi * Pi), aj = cbrt(Pj * Pj);
+            const double rh = cbrt((par[i * NBT_NPAR + NBT_P_M] + mj) / (3.0 * Ms)) * 0.5 * (ai + aj);
+            if (fabs(aj - ai) < 4.0 * rh) out = true;
+        }
+    }
+    return out;
+}
+
 // SERIES = the NBT_F_SERIES variant (full element set per sample, generate() compatibility); it is a
 // separate instantiation so that its large code stays out of the instruction caches of the batched path
 template <int NP, bool SERIES, bool LAT = false>
@@ -779,11 +890,13 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, const nbt_scheme& sc, int
     nbt_consts<NP> c;
     const double* par = A.params + (size_t)sys * (NP + 1) * NBT_NPAR;
     nbt_setup<NP>(par, s, c);
-    int status = 0;
-    const int NO = A.n_outputs, B = A.B;
+    int status = nbt_uncalibrated_impl(par, NP + 1) ? NBT_S_UNCALIBRATED : 0;
+    const int B = A.B;
+    const int NO = (A.n_outputs_sys != nullptr) ? A.n_outputs_sys[sys] : A.n_outputs;     // generate_simulations.py:45-50
+    const double n_days = (A.n_days_sys != nullptr) ? A.n_days_sys[sys] : A.n_days;
     const int kraw = (A.substeps != nullptr) ? A.substeps[sys] : A.substeps_all;
     const int k = kraw < 0 ? -kraw : kraw;
-    const double step = A.n_days / (double)(NO - 1);
+    const double step = n_days / (double)(NO - 1);
     const double dt = step / (double)k;
     const bool want_means = (A.flags & NBT_F_MEANS) != 0;
     const bool want_omega = (A.flags & NBT_F_MEAN_OMEGA) != 0;
@@ -791,7 +904,7 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, const nbt_scheme& sc, int
     const bool want_orbit = (A.flags & NBT_F_ORBIT) != 0 && A.orbit_xz != nullptr;
     const bool want_series = SERIES;
     const int n_tt_planets = (A.flags & NBT_F_PLANET1_ONLY) ? 1 : NP;
-    const double rv_scale = 1.496e11 * ((double)NO / (A.n_days * 24.0 * 60.0 * 60.0)); // simulation.py:157,186
+    const double rv_scale = 1.496e11 * ((double)NO / (n_days * 24.0 * 60.0 * 60.0)); // simulation.py:157,186
     const int W = 3 + 10 * NP;
 
     double ax[NP], ay[NP], az[NP];
@@ -808,7 +921,7 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, const nbt_scheme& sc, int
         if (o > 0) {
             for (int sub = 0; sub < k; sub++) nbt_step<NP, LAT>(s, c, sc, dt, ax, ay, az, status);
         }
-        const double t = (o == NO - 1) ? A.n_days : (double)o * step;
+        const double t = (o == NO - 1) ? n_days : (double)o * step;
         if (o > 0) { // refresh the carried radii from the coordinates (bounds their round-off drift)
 #pragma unroll
             for (int j = 0; j < NP; j++) nbt_radius(s.x[j], s.y[j], s.z[j], s.r[j], s.ir[j]);
@@ -826,6 +939,8 @@ NBT_HD void nbt_simulate_system(const nbt_run_args& A, const nbt_scheme& sc, int
         // lane idles instead of dragging the warp through the slow fallback for the rest of the run
         if (!isfinite(Sx + Svx) || (status & (NBT_S_KEPLER | NBT_S_NONFINITE))) {
             status |= NBT_S_NONFINITE;
+            if (want_rv || want_orbit || want_series)   // the samples that will never come read NaN
+                nbt_fill_broken(want_rv ? A.rv : nullptr, want_orbit ? A.orbit_xz : nullptr, want_series ? A.series : nullptr, B, NP, A.orbit_stride, sys, o, NO);
             break;
         }
         if (o > 0) {

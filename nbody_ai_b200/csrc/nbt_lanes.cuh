@@ -133,11 +133,13 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, const nbt_scheme& sc, i
         vy = v0 * (sO * vp + cO * vq * ci);
         vz = v0 * (vq * si);
     }
-    int status = 0;
-    const int NO = A.n_outputs, B = A.B;
+    int status = (j == 0 && nbt_uncalibrated_impl(par, NP + 1)) ? NBT_S_UNCALIBRATED : 0;
+    const int B = A.B;
+    const int NO = (A.n_outputs_sys != nullptr) ? A.n_outputs_sys[sys] : A.n_outputs;
+    const double n_days = (A.n_days_sys != nullptr) ? A.n_days_sys[sys] : A.n_days;
     const int kraw = (A.substeps != nullptr) ? A.substeps[sys] : A.substeps_all;
     const int k = kraw < 0 ? -kraw : kraw;
-    const double step = A.n_days / (double)(NO - 1);
+    const double step = n_days / (double)(NO - 1);
     const double dt = step / (double)k;
     const bool want_means = (A.flags & NBT_F_MEANS) != 0;
     const bool want_omega = (A.flags & NBT_F_MEAN_OMEGA) != 0;
@@ -145,7 +147,7 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, const nbt_scheme& sc, i
     const bool want_orbit = (A.flags & NBT_F_ORBIT) != 0 && A.orbit_xz != nullptr;
     const bool want_series = SERIES;
     const bool tt_on = !((A.flags & NBT_F_PLANET1_ONLY) && j > 0);
-    const double rv_scale = 1.496e11 * ((double)NO / (A.n_days * 24.0 * 60.0 * 60.0));
+    const double rv_scale = 1.496e11 * ((double)NO / (n_days * 24.0 * 60.0 * 60.0));
     const int W = 3 + 10 * NP;
 
     double rj, irj;
@@ -167,14 +169,14 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, const nbt_scheme& sc, i
                     vx = fma(kb, ax, vx); vy = fma(kb, ay, vy); vz = fma(kb, az, vz);
                 }
                 for (int st = 0; st < sc.S; st++) {
-                    nbt_kepler_drift(GMj, sc.a[st] * dt, x, y, z, vx, vy, vz, rj, irj, status);
+                    nbt_kepler_drift<(NP <= 2)>(GMj, sc.a[st] * dt, x, y, z, vx, vy, vz, rj, irj, status);
                     nbt_accel_lane_grad<NP>(gmask, base, j, x, y, z, irj, mr, Gm, GMj, sc.g[st + 1] * dt * dt, ax, ay, az);
                     const double kb = sc.b[st + 1] * dt;
                     vx = fma(kb, ax, vx); vy = fma(kb, ay, vy); vz = fma(kb, az, vz);
                 }
             }
         }
-        const double t = (o == NO - 1) ? A.n_days : (double)o * step;
+        const double t = (o == NO - 1) ? n_days : (double)o * step;
         if (o > 0) nbt_radius(x, y, z, rj, irj);   // refresh the carried radius from the coordinates
         // heliocentric x, vx of this planet and the star's barycentric position (group prefix sums)
         double Sx = 0.0, Svx = 0.0, Sy = 0.0, Sz = 0.0, dx = 0.0, dvx = 0.0, hy = 0.0, hz = 0.0;
@@ -191,7 +193,11 @@ __device__ void nbt_simulate_lane(const nbt_run_args& A, const nbt_scheme& sc, i
         }
         const double xs = -Sx;
         const bool bad = !isfinite(Sx + Svx) || (status & (NBT_S_KEPLER | NBT_S_NONFINITE));
-        if (__any_sync(gmask, bad)) { status |= NBT_S_NONFINITE; break; } // whole group stops together
+        if (__any_sync(gmask, bad)) {                                      // whole group stops together
+            status |= NBT_S_NONFINITE;
+            if (j == 0) nbt_fill_broken(want_rv ? A.rv : nullptr, want_orbit ? A.orbit_xz : nullptr, want_series ? A.series : nullptr, B, NP, A.orbit_stride, sys, o, NO);
+            break;
+        }
         if (o > 0) {
             if (tt_on && dx_prev >= 0.0 && dx <= 0.0) {                    // simulation.py:168
                 const double t0 = nbt_crossing_time(A.tt_mode, t_prev, t, dx_prev, dx, dvx_prev, dvx);  // tools.py:61-65

@@ -30,25 +30,78 @@ def _as_params(params):
     return p
 
 
+class Likelihood:
+    """The likelihood nbt_run evaluates behind the forward model (NBT_F_LOGLIKE): either
+    nested.py:85-95 (`nested`: planet-1 O-C against epochs x, times y, errors yerr, linear term c1*x + c0 per
+    forward model) or ttv_fit.py:58-94 (`ttvfit`: observed mid-transit times of every planet with data)."""
+
+    def __init__(self, kind, **kw):
+        self.kind = kind
+        f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i4 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        if kind == "nested":
+            self.x, self.y, self.yerr = f8(kw["x"]), f8(kw["y"]), f8(kw["yerr"])
+            self.c0, self.c1 = f8(kw["c0"]), f8(kw["c1"])
+            self.loss = _abi.LOSSES[kw.get("loss", "linear")]
+            self.n_data = len(self.x)
+            assert len(self.y) == len(self.yerr) == self.n_data and self.c0.shape == self.c1.shape
+        elif kind == "ttvfit":
+            self.has_data, self.orbit = i4(kw["has_data"]), i4(kw["orbit"])
+            self.tc, self.tc_err = f8(kw["tc"]), f8(kw["tc_err"])
+            self.loss = 0
+            self.n_data = len(self.orbit)
+            assert self.tc.shape == self.tc_err.shape == (len(self.has_data), self.n_data)
+        else:
+            raise ValueError("likelihood kind must be 'nested' or 'ttvfit'")
+
+    ARRAYS = (("c0", C.c_double), ("c1", C.c_double), ("x", C.c_double), ("y", C.c_double), ("yerr", C.c_double),
+              ("has_data", C.c_int32), ("tc", C.c_double), ("tc_err", C.c_double), ("orbit", C.c_int32))
+
+    def struct(self, pointer_of=None):
+        """nbt_like over this object's host arrays (or over `pointer_of(name, array)` for device copies)."""
+        L = _abi.nbt_like()
+        L.kind = _abi.LIKE_NESTED if self.kind == "nested" else _abi.LIKE_TTVFIT
+        L.loss, L.n_data = int(self.loss), int(self.n_data)
+        for name, ct in self.ARRAYS:
+            a = getattr(self, name, None)
+            if a is not None:
+                setattr(L, name, _abi.ptr(a, ct) if pointer_of is None else pointer_of(name, a, ct))
+        return L
+
+
 class Plan:
-    """Configuration + CSR layout of one nbt_run call (host planning through libnbt's helpers)."""
+    """Configuration + CSR layout of one nbt_run call (host planning through libnbt's helpers).
+
+    n_days / n_outputs: scalars (one output grid for the whole batch) or arrays [B] — every system on its own grid
+    np.linspace(0, n_days[b], n_outputs[b]) (simulations/generate_simulations.py:45-50), still one launch."""
 
     def __init__(self, params, n_days, n_outputs, substeps=None, scheme=SCHEME_AUTO,
-                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True, lanes=None):
+                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True, lanes=None, likelihood=None):
         lib = _abi.load()
         self.params = _as_params(params)
         B, N, _ = self.params.shape
         if isinstance(scheme, str):
             scheme = SCHEMES[scheme]
+        self.n_days_sys = self.n_outputs_sys = None
+        if np.ndim(n_days) > 0 or np.ndim(n_outputs) > 0:
+            self.n_days_sys = np.ascontiguousarray(np.broadcast_to(np.asarray(n_days, dtype=np.float64), (B,)))
+            self.n_outputs_sys = np.ascontiguousarray(np.broadcast_to(np.asarray(n_outputs, dtype=np.int32), (B,)))
+            n_days = float(self.n_days_sys.max()) if B else 1.0
+            n_outputs = int(self.n_outputs_sys.max()) if B else 2
+            if B and int(self.n_outputs_sys.min()) < 2:
+                raise ValueError("Noutputs must be >= 2")
         if int(n_outputs) < 2:
             raise ValueError("Noutputs must be >= 2")
+        self.likelihood = likelihood
+        if likelihood is not None:
+            flags |= _abi.F_LOGLIKE
         self.cfg = _abi.make_config(B, N, n_days, n_outputs, substeps=0, scheme=scheme,
                                     tt_mode=tt_mode, flags=flags, device=device)
         self.B, self.N, self.Np = B, N, N - 1
         # composition steps per output interval
         if substeps is None:
             self.substeps = np.zeros(B, dtype=np.int32)
-            _abi.check(lib.nbt_plan_substeps(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.substeps, C.c_int32)), lib)
+            _abi.check(lib.nbt_plan_substeps(C.byref(self.cfg), C.byref(self._inputs()), _abi.ptr(self.substeps, C.c_int32)), lib)
         elif np.isscalar(substeps):
             self.cfg.substeps = int(substeps)
             self.substeps = None
@@ -64,10 +117,9 @@ class Plan:
             self.cfg.alt_systems = int((self.substeps < 0).sum())
             if np.array_equal(self.order, np.arange(B, dtype=np.int32)):
                 self.order = None
-        if sort and (B > 32 or marked):
+        if sort and (B > 32 or marked) and scheme not in (_abi.SCHEME_IAS15, _abi.SCHEME_WHFAST):
             self.order = np.zeros(B, dtype=np.int32)
-            nalt = lib.nbt_plan_order(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.substeps, C.c_int32),
-                                      _abi.ptr(self.order, C.c_int32))
+            nalt = lib.nbt_plan_order(C.byref(self.cfg), C.byref(self._inputs()), _abi.ptr(self.order, C.c_int32))
             if nalt < 0:
                 _abi.check(nalt, lib)
             self.cfg.alt_systems = int(nalt) if self.cfg.scheme == SCHEME_AUTO else 0
@@ -75,13 +127,13 @@ class Plan:
                 self.order = None
         # which systems run one planet per lane (long ones / small batches), see nbt_plan_lanes
         if lanes is None:
-            lanes = lib.nbt_plan_lanes(C.byref(self.cfg), _abi.ptr(self.substeps, C.c_int32), _abi.ptr(self.order, C.c_int32))
+            lanes = lib.nbt_plan_lanes(C.byref(self.cfg), C.byref(self._inputs()))
             if lanes < 0:
                 _abi.check(lanes, lib)
         self.cfg.lanes_systems = int(min(max(int(lanes), 0), B))
         # CSR capacities of the transit products
         self.tt_offsets = np.zeros(B * self.Np + 1, dtype=np.int64)
-        cap = lib.nbt_plan_tt(C.byref(self.cfg), _abi.ptr(self.params), _abi.ptr(self.tt_offsets, C.c_int64))
+        cap = lib.nbt_plan_tt(C.byref(self.cfg), C.byref(self._inputs()), _abi.ptr(self.tt_offsets, C.c_int64))
         if cap < 0:
             _abi.check(cap, lib)
         self.cfg.tt_cap_max = cap
@@ -89,19 +141,35 @@ class Plan:
         if flags & F_LS_OC:
             self.ls_offsets = np.zeros(B * self.Np + 1, dtype=np.int64)
             _abi.check(lib.nbt_plan_ls(C.byref(self.cfg), _abi.ptr(self.tt_offsets, C.c_int64), _abi.ptr(self.ls_offsets, C.c_int64)), lib)
-        self.n_steps = int(lib.nbt_count_steps(C.byref(self.cfg), _abi.ptr(self.substeps, C.c_int32)))
+        self.n_steps = int(lib.nbt_count_steps(C.byref(self.cfg), C.byref(self._inputs())))
         self.rv_nfreq = 0
         if flags & F_LS_RV:
             step = float(n_days) / (int(n_outputs) - 1)
             self.rv_nfreq = int(lib.nbt_ls_nfreq(float(n_days) - step, self.cfg.ls_rv_minfreq, self.cfg.ls_rv_maxfreq,
                                                  self.cfg.ls_samples_per_peak))
 
+    def _inputs(self):
+        """nbt_inputs over whatever host planning arrays exist so far (for the nbt_plan_* helpers)."""
+        inp = _abi.nbt_inputs()
+        inp.params = _abi.ptr(self.params)
+        inp.substeps = _abi.ptr(getattr(self, "substeps", None), C.c_int32)
+        inp.order = _abi.ptr(getattr(self, "order", None), C.c_int32)
+        inp.n_days_sys = _abi.ptr(self.n_days_sys)
+        inp.n_outputs_sys = _abi.ptr(self.n_outputs_sys, C.c_int32)
+        return inp
+
+    def uncalibrated(self):
+        """Mask of the systems outside the envelope the sub-step rule was calibrated on (what nbt_run reports as
+        NBT_S_UNCALIBRATED: a pair inside 4 mutual Hill radii, e > 0.1 or m_planet / m_star > 0.013)."""
+        lib = _abi.load()
+        return np.array([lib.nbt_uncalibrated(_abi.ptr(self.params[b]), self.N) for b in range(self.B)], dtype=bool)
+
     def pin(self):
         """Move the plan's input arrays into page-locked host memory (torch), so that the H2D
         copies inside nbt_run are true asynchronous DMA."""
         import torch
         self._pinned = []
-        for name in ("params", "substeps", "order", "tt_offsets", "ls_offsets"):
+        for name in ("params", "substeps", "order", "tt_offsets", "ls_offsets", "n_days_sys", "n_outputs_sys"):
             a = getattr(self, name)
             if a is not None:
                 t = torch.from_numpy(a).pin_memory()
@@ -113,20 +181,39 @@ class Plan:
     def times(self):
         return np.linspace(0.0, self.cfg.n_days, self.cfg.n_outputs)  # simulation.py:135
 
+    def times_of(self, b):
+        if self.n_days_sys is None:
+            return self.times
+        return np.linspace(0.0, self.n_days_sys[b], self.n_outputs_sys[b])
+
+
+OUTPUT_NAMES = (("tt", C.c_double), ("ttv", C.c_double), ("n_tt", C.c_int32), ("period", C.c_double),
+                ("t0", C.c_double), ("ttv_max", C.c_double), ("mean_a", C.c_double),
+                ("mean_e", C.c_double), ("mean_inc", C.c_double), ("mean_omega", C.c_double),
+                ("status", C.c_int32), ("rv", C.c_double), ("rv_max", C.c_double),
+                ("orbit_xz", C.c_double), ("series", C.c_double), ("ls_oc_power", C.c_double),
+                ("ls_oc_nfreq", C.c_int32), ("ls_rv_power", C.c_double), ("ls_oc_peaks", C.c_double),
+                ("loglike", C.c_double))
+
 
 class Buffers:
-    """Caller-owned host output buffers of one Plan (numpy; pinned when torch+CUDA is present)."""
+    """Caller-owned host output buffers of one Plan (numpy; pinned when torch+CUDA is present).
 
-    def __init__(self, plan, pinned=False):
+    skip: names of products the caller does not want back (tt, ttv, n_tt, period, t0, ttv_max, ls_oc_power,
+    ls_oc_nfreq): they are left NULL in nbt_outputs — computed on the device, never copied to the host."""
+
+    def __init__(self, plan, pinned=False, skip=()):
         self.plan = plan
         B, Np, NO = plan.B, plan.Np, plan.cfg.n_outputs
         fl = plan.cfg.flags
         self._keep = []
+        skip = set(skip)
         z = lambda shape, dt=np.float64: self._alloc(shape, dt, pinned)
+        zs = lambda name, shape, dt=np.float64: None if name in skip else self._alloc(shape, dt, pinned)
         ntot = int(plan.tt_offsets[-1])
-        self.tt = z(ntot); self.ttv = z(ntot)
-        self.n_tt = z(B * Np, np.int32)
-        self.period = z(B * Np); self.t0 = z(B * Np); self.ttv_max = z(B * Np)
+        self.tt = zs("tt", ntot); self.ttv = zs("ttv", ntot)
+        self.n_tt = zs("n_tt", B * Np, np.int32)
+        self.period = zs("period", B * Np); self.t0 = zs("t0", B * Np); self.ttv_max = zs("ttv_max", B * Np)
         self.mean_a = z(B * Np); self.mean_e = z(B * Np); self.mean_inc = z(B * Np)
         self.mean_omega = z(B * Np)
         self.status = z(B, np.int32)
@@ -135,9 +222,11 @@ class Buffers:
         nq = (NO + plan.cfg.orbit_stride - 1) // plan.cfg.orbit_stride
         self.orbit_xz = z((nq, B, Np, 2)) if fl & F_ORBIT else None
         self.series = z((NO, B, 3 + 10 * Np)) if fl & F_SERIES else None
-        self.ls_oc_power = z(int(plan.ls_offsets[-1])) if fl & F_LS_OC else None
-        self.ls_oc_nfreq = z(B * Np, np.int32) if fl & F_LS_OC else None
+        self.ls_oc_power = zs("ls_oc_power", int(plan.ls_offsets[-1])) if fl & F_LS_OC else None
+        self.ls_oc_nfreq = zs("ls_oc_nfreq", B * Np, np.int32) if fl & F_LS_OC else None
         self.ls_rv_power = z((B, plan.rv_nfreq)) if fl & F_LS_RV else None
+        self.ls_oc_peaks = z((B * Np, _abi.LS_NPEAKS, 2)) if fl & _abi.F_LS_PEAKS else None
+        self.loglike = z(B) if fl & _abi.F_LOGLIKE else None
 
     def _alloc(self, shape, dtype, pinned):
         if pinned:
@@ -156,15 +245,16 @@ class Buffers:
         inp.order = _abi.ptr(p.order, C.c_int32)
         inp.tt_offsets = _abi.ptr(p.tt_offsets, C.c_int64)
         inp.ls_offsets = _abi.ptr(p.ls_offsets, C.c_int64)
+        inp.n_days_sys = _abi.ptr(p.n_days_sys)
+        inp.n_outputs_sys = _abi.ptr(p.n_outputs_sys, C.c_int32)
+        like = None
+        if p.likelihood is not None:
+            like = p.likelihood.struct()
+            inp.like = C.pointer(like)
         out = _abi.nbt_outputs()
-        for name, ct in (("tt", C.c_double), ("ttv", C.c_double), ("n_tt", C.c_int32), ("period", C.c_double),
-                         ("t0", C.c_double), ("ttv_max", C.c_double), ("mean_a", C.c_double),
-                         ("mean_e", C.c_double), ("mean_inc", C.c_double), ("mean_omega", C.c_double),
-                         ("status", C.c_int32), ("rv", C.c_double), ("rv_max", C.c_double),
-                         ("orbit_xz", C.c_double), ("series", C.c_double), ("ls_oc_power", C.c_double),
-                         ("ls_oc_nfreq", C.c_int32), ("ls_rv_power", C.c_double)):
+        for name, ct in OUTPUT_NAMES:
             setattr(out, name, _abi.ptr(getattr(self, name), ct))
-        self._structs = (inp, out, par)  # keep alive
+        self._structs = (inp, out, par, like)  # keep alive
         return inp, out
 
     # ---- views -------------------------------------------------------------------------
@@ -221,6 +311,155 @@ def run_batch(params, n_days, n_outputs, **kw):
 
 
 # -------------------------------------------------------------------------------------------
+# Verified mode.  The sub-step rule is calibrated on well-separated systems; for the ones nbt_run flags
+# NBT_S_UNCALIBRATED (a pair inside 4 mutual Hill radii, e > 0.1, a heavy planet) the truncation error of a
+# fixed-step composition is amplified by the system's own sensitivity, which nothing predicts a priori.  So they
+# are checked the way one checks any integration: again at twice the resolution.  Where the two runs agree to
+# half a parity tolerance the finer one is kept; the rest (close encounters, chaotic pairs: a few per thousand
+# systems of the reference's priors) are re-integrated with the reference's own integrator, IAS15, on the GPU.
+# -------------------------------------------------------------------------------------------
+VERIFY_TOL = dict(tt_s=1.0, oc_min=1e-3, a_rel=1e-8, e_rel=1e-8)      # BASELINE.json:north_star
+
+
+def _grids_of(plan, idx):
+    if plan.n_days_sys is None:
+        return plan.cfg.n_days, plan.cfg.n_outputs
+    return plan.n_days_sys[idx], plan.n_outputs_sys[idx]
+
+
+def _csr_index(offsets, Np, rows):
+    """Flat indices of the CSR slices of systems `rows` (all their planets), in order."""
+    lo = offsets[rows * Np]
+    hi = offsets[rows * Np + Np]
+    n = hi - lo
+    return np.repeat(lo - np.concatenate(([0], np.cumsum(n)[:-1])), n) + np.arange(int(n.sum()))
+
+
+def splice(dst, rows, src):
+    """Overwrite the results of systems `rows` of Buffers `dst` with systems 0..len(rows)-1 of Buffers `src` (a run of
+    the same systems on the same output grids, so every CSR capacity matches)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    dp, sp = dst.plan, src.plan
+    Np = dp.Np
+    q = np.arange(len(rows), dtype=np.int64)
+    d_tt, s_tt = _csr_index(dp.tt_offsets, Np, rows), _csr_index(sp.tt_offsets, Np, q)
+    assert len(d_tt) == len(s_tt), "splice: transit capacities differ"
+    for name in ("tt", "ttv"):
+        if getattr(dst, name) is not None and getattr(src, name) is not None:
+            getattr(dst, name)[d_tt] = getattr(src, name)[s_tt]
+    if dst.ls_oc_power is not None and src.ls_oc_power is not None:
+        dst.ls_oc_power[_csr_index(dp.ls_offsets, Np, rows)] = src.ls_oc_power[_csr_index(sp.ls_offsets, Np, q)]
+    d_sp = (rows[:, None] * Np + np.arange(Np)[None]).ravel()
+    s_sp = (q[:, None] * Np + np.arange(Np)[None]).ravel()
+    for name in ("n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega", "ls_oc_nfreq", "ls_oc_peaks"):
+        if getattr(dst, name) is not None and getattr(src, name) is not None:
+            getattr(dst, name)[d_sp] = getattr(src, name)[s_sp]
+    for name in ("status", "rv_max", "loglike", "ls_rv_power"):
+        if getattr(dst, name) is not None and getattr(src, name) is not None:
+            getattr(dst, name)[rows] = getattr(src, name)[q]
+    for name in ("rv", "orbit_xz", "series"):
+        if getattr(dst, name) is not None and getattr(src, name) is not None:
+            getattr(dst, name)[:, rows] = getattr(src, name)[:, q]
+
+
+def disagreement(a, rows_a, b, tol=VERIFY_TOL):
+    """Worst difference, in units of the parity tolerances, between systems `rows_a` of Buffers `a` and systems
+    0.. of Buffers `b` (same systems, same grids): max over transit times [s], O-C [min], mean a and mean e
+    (relative, e with the 1e-4 floor of the parity tests).  inf where transit counts differ or a run broke."""
+    pa, pb = a.plan, b.plan
+    Np = pa.Np
+    out = np.zeros(len(rows_a))
+    bad = _abi.S_NONFINITE | _abi.S_UNBOUND | _abi.S_KEPLER | _abi.S_TT_OVERFLOW
+    for q, r in enumerate(rows_a):
+        w = 0.0
+        if (a.status[r] | b.status[q]) & bad:
+            out[q] = np.inf
+            continue
+        for j in range(Np):
+            if a.n_tt[r * Np + j] != b.n_tt[q * Np + j]:
+                w = np.inf
+                break
+            n = a.n_transits(r, j)
+            if n:
+                w = max(w, np.abs(a.tt_of(r, j) - b.tt_of(q, j)).max() * 86400 / tol["tt_s"])
+            if n >= 3:
+                w = max(w, np.abs(a.ttv_of(r, j) - b.ttv_of(q, j)).max() * 1440 / tol["oc_min"])
+            if pa.cfg.flags & F_MEANS:
+                sa, sb = r * Np + j, q * Np + j
+                w = max(w, abs(a.mean_a[sa] / b.mean_a[sb] - 1) / tol["a_rel"],
+                        abs(a.mean_e[sa] - b.mean_e[sb]) / max(b.mean_e[sb], 1e-4) / tol["e_rel"])
+        out[q] = w if np.isfinite(w) else np.inf
+    return out
+
+
+def run_verified(plan, buffers=None, accept=0.5, fallback="ias15", report=None):
+    """nbt_run + verification of the systems flagged NBT_S_UNCALIBRATED (see above).  Returns the Buffers of `plan`
+    with the verified systems' results replaced by the finer / IAS15 run; a system that could not be settled keeps
+    NBT_S_UNRESOLVED in its status (fallback=None).  report: dict that receives the counts."""
+    if plan.likelihood is not None:
+        raise ValueError("run_verified compares transit products: run it without a fused likelihood")
+    buffers = run(plan, buffers)
+    risky = np.flatnonzero(buffers.status & _abi.S_UNCALIBRATED)
+    info = dict(systems=int(plan.B), flagged=int(len(risky)), accepted_doubling=0, ias15=0, unresolved=0)
+    if report is not None:
+        report.update(info)
+    if len(risky) == 0 or plan.cfg.scheme in (_abi.SCHEME_IAS15, _abi.SCHEME_WHFAST):
+        return buffers
+    nd, no = _grids_of(plan, risky)
+    flags = plan.cfg.flags & ~(F_DEVICE_PTRS | _abi.F_TIMING)
+    k = np.abs(plan.substeps[risky]) if plan.substeps is not None else np.full(len(risky), max(plan.cfg.substeps, 1))
+    scheme = _abi.SCHEME_SBABC3 if plan.cfg.scheme == SCHEME_AUTO else plan.cfg.scheme
+    twin = run(Plan(plan.params[risky], nd, no, substeps=(2 * k).astype(np.int32), scheme=scheme, tt_mode=plan.cfg.tt_mode,
+                    flags=flags, device=plan.cfg.device))
+    d = disagreement(buffers, risky, twin)
+    ok = d <= accept
+    splice(buffers, risky[ok], _subset(twin, np.flatnonzero(ok)))
+    info["accepted_doubling"] = int(ok.sum())
+    rest = risky[~ok]
+    if len(rest):
+        if fallback == "ias15":
+            nd, no = _grids_of(plan, rest)
+            ias = run(Plan(plan.params[rest], nd, no, scheme=_abi.SCHEME_IAS15, tt_mode=plan.cfg.tt_mode, flags=flags,
+                           device=plan.cfg.device, sort=False, lanes=0))
+            splice(buffers, rest, ias)
+            info["ias15"] = int(len(rest))
+        else:
+            buffers.status[rest] |= _abi.S_UNRESOLVED
+            info["unresolved"] = int(len(rest))
+    if report is not None:
+        report.update(info)
+    return buffers
+
+
+def _subset(buf, rows):
+    """Buffers holding systems `rows` of `buf` re-packed as systems 0..len(rows)-1 (for splice)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    p = buf.plan
+    nd, no = _grids_of(p, rows)
+    sub = Buffers(Plan(p.params[rows], nd, no, substeps=1, scheme=_abi.SCHEME_SBABC3, tt_mode=p.cfg.tt_mode,
+                       flags=p.cfg.flags & ~(F_DEVICE_PTRS | _abi.F_TIMING), device=p.cfg.device, sort=False, lanes=0))
+    Np = p.Np
+    q = np.arange(len(rows), dtype=np.int64)
+    s_tt, d_tt = _csr_index(p.tt_offsets, Np, rows), _csr_index(sub.plan.tt_offsets, Np, q)
+    for name in ("tt", "ttv"):
+        if getattr(buf, name) is not None:
+            getattr(sub, name)[d_tt] = getattr(buf, name)[s_tt]
+    if buf.ls_oc_power is not None:
+        sub.ls_oc_power[_csr_index(sub.plan.ls_offsets, Np, q)] = buf.ls_oc_power[_csr_index(p.ls_offsets, Np, rows)]
+    s_sp = (rows[:, None] * Np + np.arange(Np)[None]).ravel()
+    for name in ("n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega", "ls_oc_nfreq", "ls_oc_peaks"):
+        if getattr(buf, name) is not None and getattr(sub, name) is not None:
+            getattr(sub, name)[...] = getattr(buf, name)[s_sp]
+    for name in ("status", "rv_max", "loglike", "ls_rv_power"):
+        if getattr(buf, name) is not None and getattr(sub, name) is not None:
+            getattr(sub, name)[...] = getattr(buf, name)[rows]
+    for name in ("rv", "orbit_xz", "series"):
+        if getattr(buf, name) is not None and getattr(sub, name) is not None:
+            getattr(sub, name)[...] = getattr(buf, name)[:, rows]
+    return sub
+
+
+# -------------------------------------------------------------------------------------------
 # Multi-GPU: shard by system index, one process per GPU, no collective on the data path.
 # -------------------------------------------------------------------------------------------
 def shard_range(n_systems, rank, world_size):
@@ -240,7 +479,9 @@ def system_cost(params, n_days, n_outputs, scheme=SCHEME_AUTO):
         scheme = SCHEMES[scheme]
     cfg = _abi.make_config(B, N, n_days, n_outputs, substeps=0, scheme=scheme)
     k = np.zeros(B, dtype=np.int32)
-    _abi.check(lib.nbt_plan_substeps(C.byref(cfg), _abi.ptr(params), _abi.ptr(k, C.c_int32)), lib)
+    inp = _abi.nbt_inputs()
+    inp.params = _abi.ptr(params)
+    _abi.check(lib.nbt_plan_substeps(C.byref(cfg), C.byref(inp), _abi.ptr(k, C.c_int32)), lib)
     stages = {0: 1, 1: 3, 2: 4, 3: 4, 4: 2, 5: 3, 6: 3}[int(scheme)]
     return np.where(k < 0, -2.0 * k, float(stages) * k) + 1.0
 
@@ -301,6 +542,13 @@ class DeviceBuffers:
         up = lambda a: None if a is None else torch.from_numpy(a).to(dev)
         self.params, self.substeps, self.order = up(plan.params), up(plan.substeps), up(plan.order)
         self.tt_offsets, self.ls_offsets = up(plan.tt_offsets), up(plan.ls_offsets)
+        self.n_days_sys, self.n_outputs_sys = up(plan.n_days_sys), up(plan.n_outputs_sys)
+        self.like_arrays, self.like = {}, None
+        if plan.likelihood is not None:      # device copies of the likelihood's arrays; the struct itself stays on the host
+            def dev_ptr(name, a, ct):
+                self.like_arrays[name] = torch.from_numpy(a).to(dev)
+                return self._p(self.like_arrays[name], ct)
+            self.like = plan.likelihood.struct(dev_ptr)
         for name, dt, key in self._OUT:
             setattr(self, name, torch.zeros(max(sizes[key], 1), dtype=torch.float64 if dt == "f8" else torch.int32, device=dev))
         f8 = lambda *shape: torch.zeros(*shape, dtype=torch.float64, device=dev)
@@ -312,6 +560,12 @@ class DeviceBuffers:
         self.ls_oc_power = f8(max(int(plan.ls_offsets[-1]), 1)) if fl & F_LS_OC else None
         self.ls_oc_nfreq = torch.zeros(B * Np, dtype=torch.int32, device=dev) if fl & F_LS_OC else None
         self.ls_rv_power = f8(B, plan.rv_nfreq) if fl & F_LS_RV else None
+        self.ls_oc_peaks = f8(B * Np, _abi.LS_NPEAKS, 2) if fl & _abi.F_LS_PEAKS else None
+        self.loglike = f8(B) if fl & _abi.F_LOGLIKE else None
+
+    def set_params(self, params):
+        """New parameter values for the same plan (a sampler's next batch): one H2D copy."""
+        self.params.copy_(self.torch.from_numpy(_as_params(params)), non_blocking=True)
 
     @staticmethod
     def _p(t, ct):
@@ -324,21 +578,19 @@ class DeviceBuffers:
         inp.order = self._p(self.order, C.c_int32)
         inp.tt_offsets = self._p(self.tt_offsets, C.c_int64)
         inp.ls_offsets = self._p(self.ls_offsets, C.c_int64)
+        inp.n_days_sys = self._p(self.n_days_sys, C.c_double)
+        inp.n_outputs_sys = self._p(self.n_outputs_sys, C.c_int32)
+        if self.like is not None:
+            inp.like = C.pointer(self.like)
         out = _abi.nbt_outputs()
-        for name, ct in (("tt", C.c_double), ("ttv", C.c_double), ("n_tt", C.c_int32), ("period", C.c_double),
-                         ("t0", C.c_double), ("ttv_max", C.c_double), ("mean_a", C.c_double),
-                         ("mean_e", C.c_double), ("mean_inc", C.c_double), ("mean_omega", C.c_double),
-                         ("status", C.c_int32), ("rv", C.c_double), ("rv_max", C.c_double),
-                         ("orbit_xz", C.c_double), ("series", C.c_double), ("ls_oc_power", C.c_double),
-                         ("ls_oc_nfreq", C.c_int32), ("ls_rv_power", C.c_double)):
+        for name, ct in OUTPUT_NAMES:
             setattr(out, name, self._p(getattr(self, name), ct))
         return inp, out
 
     def to_host(self):
         """Copy every output into a host Buffers (for checks)."""
         hb = Buffers(self.plan)
-        for name in ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega",
-                     "status", "rv", "rv_max", "orbit_xz", "series", "ls_oc_power", "ls_oc_nfreq", "ls_rv_power"):
+        for name, _ in OUTPUT_NAMES:
             t = getattr(self, name)
             h = getattr(hb, name)
             if t is not None and h is not None:

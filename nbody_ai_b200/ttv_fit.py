@@ -52,10 +52,18 @@ class NbodyLikelihood:
             par[:, idx, cols[key]] = thetas[:, c]
         return par
 
-    def loglike_batch(self, thetas):
-        """chi2 of ttv_fit.py:58-94 for every row of `thetas`."""
+    def loglike_batch(self, thetas, fused=True):
+        """chi2 of ttv_fit.py:58-94 for every row of `thetas`.  fused (default): one nbt_run with the likelihood chained
+        behind the forward model on the device — only loglike[B] comes back; fused=False keeps the two-call form
+        (nbt_run, then nbt_ttvfit_loglike on the returned transit times)."""
         lib = _abi.load()
         par = self.params_for(thetas)
+        if fused:
+            like = engine.Likelihood("ttvfit", has_data=self.has, tc=self.tc, tc_err=self.err, orbit=self.orbit)
+            plan = engine.Plan(par, self.sim_time, int(self.sim_time * 24), flags=0, device=self.device, likelihood=like)   # :59
+            buf = engine.Buffers(plan, skip=("tt", "ttv", "n_tt", "period", "t0", "ttv_max"))
+            engine.run(plan, buf)
+            return buf.loglike.copy()
         plan = engine.Plan(par, self.sim_time, int(self.sim_time * 24), flags=0, device=self.device)   # :59
         buf = engine.run(plan)
         out = np.zeros(plan.B)

@@ -45,6 +45,10 @@ def lib():
         L.nbo_lomb_scargle.argtypes = [_dp, _dp, C.c_int, C.c_double, C.c_double, C.c_int64, _dp]
         L.nbo_loglike.restype = C.c_double
         L.nbo_loglike.argtypes = [_dp, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, C.c_int]
+        L.nbo_loglike_loss.restype = C.c_double
+        L.nbo_loglike_loss.argtypes = [_dp, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, C.c_int, C.c_int]
+        L.nbo_refined_transit_times.restype = C.c_int
+        L.nbo_refined_transit_times.argtypes = [_dp, C.c_int, C.c_double, C.c_int, C.c_int, _dp, C.c_int]
         L.nbo_run.argtypes = [C.POINTER(_abi.nbt_config), C.POINTER(_abi.nbt_inputs),
                               C.POINTER(_abi.nbt_outputs), C.c_int, _lp]
         L.nbo_max_threads.restype = C.c_int
@@ -104,9 +108,19 @@ def lomb_scargle(t, y, minfreq=1.0 / 365, maxfreq=0.5, samples_per_peak=10):
     return minfreq + df * np.arange(nf), power
 
 
-def loglike(ttv, c0, c1, x, y, yerr):
+def loglike(ttv, c0, c1, x, y, yerr, loss="linear"):
     ttv, x, y, yerr = (np.ascontiguousarray(a, dtype=np.float64) for a in (ttv, x, y, yerr))
-    return lib().nbo_loglike(_abi.ptr(ttv), len(ttv), c0, c1, _abi.ptr(x), _abi.ptr(y), _abi.ptr(yerr), len(x))
+    return lib().nbo_loglike_loss(_abi.ptr(ttv), len(ttv), c0, c1, _abi.ptr(x), _abi.ptr(y), _abi.ptr(yerr), len(x),
+                                  _abi.LOSSES[loss])
+
+
+def refined_transit_times(params, n_days, n_outputs, planet):
+    """True roots of x_planet - x_star on the IAS15 trajectory (bracketed on the output grid, Newton-refined)."""
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    out = np.zeros(int(n_outputs))
+    n = lib().nbo_refined_transit_times(_abi.ptr(params), params.shape[0], float(n_days), int(n_outputs), int(planet),
+                                        _abi.ptr(out), len(out))
+    return out[:n].copy()
 
 
 def run(cfg, params, buffers, n_threads=0):

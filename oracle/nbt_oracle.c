@@ -360,6 +360,13 @@ static double acos2(double num, double den, double disamb) {
 
 typedef struct { double P, a, e, inc, Omega, omega, M; } orbit_t;
 
+/* [3P] REBOUND (reb_tools_particle_to_orbit, 3.x) ends with "move some of the angles into [0,2pi) range": f, l, M,
+ * theta and omega go through reb_tools_mod2pi (fmod, + 2 pi if negative); Omega and pomega do not. */
+static double mod2pi(double f) {
+    f = fmod(f, 2.0 * PI);
+    return (f < 0.0) ? f + 2.0 * PI : f;
+}
+
 static orbit_t state_to_orbit(double mu, const double* d, const double* w) {
     const double MIN_INC = 1e-8, MIN_ECC = 1e-8;
     orbit_t o;
@@ -401,6 +408,8 @@ static orbit_t state_to_orbit(double mu, const double* d, const double* w) {
         if (o.e <= MIN_ECC) { o.omega = 0.0; }
     }
     (void)f;
+    o.omega = mod2pi(o.omega);
+    o.M = mod2pi(o.M);
     return o;
 }
 
@@ -464,6 +473,52 @@ long nbo_integrate_series(const double* params, int n_bodies, double n_days, int
     long ns = I->n_steps;
     free(I);
     return ns;
+}
+
+/* TRUE mid-transit times of one planet (0-based index j among the planets): the roots of x_planet(t) - x_star(t)
+ * with falling sign on the IAS15 trajectory itself, bracketed on the same output grid as transit_times() and
+ * refined by a safeguarded Newton iteration that re-integrates from the bracket's left sample to every trial
+ * time.  This is what NBT_TT_REFINED approximates (north_star item 2); the reference itself never computes it.
+ * Returns the number of crossings (out holds at most cap of them). */
+int nbo_refined_transit_times(const double* params, int n_bodies, double n_days, int n_outputs, int j,
+                              double* out, int cap) {
+    sys_t s;
+    build_system(params, n_bodies, &s);
+    ias15_t* I = (ias15_t*)malloc(sizeof(ias15_t));
+    ias15_t* P = (ias15_t*)malloc(sizeof(ias15_t));
+    ias15_t* Q = (ias15_t*)malloc(sizeof(ias15_t));
+    ias15_init(I, &s);
+    I->max_steps = 400L * n_outputs + 100000L;
+    double step = n_days / (double)(n_outputs - 1);
+    int c = 0, ip = 3 * (j + 1);
+    double prev = 0.0, t_prev = 0.0;
+    for (int o = 0; o < n_outputs && !I->gave_up; o++) {
+        double t = (o == n_outputs - 1) ? n_days : o * step;
+        if (o > 0) memcpy(P, I, sizeof(ias15_t));
+        ias15_integrate_to(I, t);
+        double cur = I->s.x[ip] - I->s.x[0];
+        if (o > 0 && prev >= 0.0 && cur <= 0.0) {
+            double lo = t_prev, hi = t, flo = prev, fhi = cur;
+            double tr = lo + (hi - lo) * flo / (flo - fhi);
+            if (!(tr >= lo && tr <= hi)) tr = 0.5 * (lo + hi);
+            for (int it = 0; it < 60; it++) {
+                memcpy(Q, P, sizeof(ias15_t));
+                ias15_integrate_to(Q, tr);
+                double f = Q->s.x[ip] - Q->s.x[0], fp = Q->s.v[ip] - Q->s.v[0];
+                if (f > 0.0) { lo = tr; flo = f; } else { hi = tr; fhi = f; }
+                double tn = tr - f / fp;
+                if (!(tn > lo && tn < hi)) tn = 0.5 * (lo + hi);
+                double dtn = fabs(tn - tr);
+                tr = tn;
+                if (dtn < 1e-13 || f == 0.0) break;
+            }
+            if (c < cap) out[c] = tr;
+            c++;
+        }
+        prev = cur; t_prev = t;
+    }
+    free(I); free(P); free(Q);
+    return c;
 }
 
 /* transit_times(xp, xs, times): simulation.py:163-170 with find_zero of tools.py:61-65 */
@@ -563,6 +618,30 @@ void nbo_lomb_scargle(const double* t, const double* y, int n, double f0, double
 }
 
 /* nested.py:85-95 myloglike for one forward model */
+static double loss_fn(int loss, double z) { /* nested.py:79-82 */
+    return loss == NBT_LOSS_SOFT_L1 ? 2.0 * (sqrt(1.0 + z) - 1.0) : z;
+}
+
+double nbo_loglike_loss(const double* ttv, int n_ttv, double c0, double c1, const double* x,
+                        const double* y, const double* yerr, int n_data, int loss) {
+    int ok = 1;
+    for (int i = 0; i < n_data; i++) if ((int)x[i] >= n_ttv || (int)x[i] < -n_ttv) ok = 0;
+    double s = 0;
+    if (ok) {
+        for (int i = 0; i < n_data; i++) {
+            int k = (int)x[i]; if (k < 0) k += n_ttv;
+            double r = (y[i] - (c1 * x[i] + c0) - ttv[k]) / yerr[i];
+            s += loss_fn(loss, r * r);
+        }
+        return -0.5 * s;
+    }
+    for (int i = 0; i < n_ttv && i < n_data; i++) {
+        double r = (y[i] - (c1 * x[i] + c0) - ttv[i]) / yerr[i];
+        s += loss_fn(loss, r * r);
+    }
+    return -10.0 * s;
+}
+
 double nbo_loglike(const double* ttv, int n_ttv, double c0, double c1, const double* x,
                    const double* y, const double* yerr, int n_data) {
     int ok = 1;
@@ -596,7 +675,10 @@ typedef struct {
 } run_ctx;
 
 static void run_one(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* out, int b, int64_t* steps) {
-    const int B = cfg->n_systems, N = cfg->n_bodies, Np = N - 1, NO = cfg->n_outputs;
+    const int B = cfg->n_systems, N = cfg->n_bodies, Np = N - 1;
+    /* per-system grid (simulations/generate_simulations.py:45-50) or the uniform one */
+    const int NO = in->n_outputs_sys ? in->n_outputs_sys[b] : cfg->n_outputs;
+    const double n_days = in->n_days_sys ? in->n_days_sys[b] : cfg->n_days;
     const int W = 3 + 10 * Np;
     const int stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
     int64_t total_steps = 0;
@@ -606,9 +688,9 @@ static void run_one(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         double* times = (double*)malloc(sizeof(double) * NO);
         double* col_p = (double*)malloc(sizeof(double) * NO);
         double* col_s = (double*)malloc(sizeof(double) * NO);
-        total_steps += nbo_integrate_series(par, N, cfg->n_days, NO, series, NULL);
-        double step = cfg->n_days / (double)(NO - 1);
-        for (int o = 0; o < NO; o++) times[o] = (o == NO - 1) ? cfg->n_days : o * step;
+        total_steps += nbo_integrate_series(par, N, n_days, NO, series, NULL);
+        double step = n_days / (double)(NO - 1);
+        for (int o = 0; o < NO; o++) times[o] = (o == NO - 1) ? n_days : o * step;
         int status = 0;
         for (int o = 0; o < NO; o++) {
             col_s[o] = series[(size_t)o * W];
@@ -616,7 +698,7 @@ static void run_one(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         }
         /* RV = np.diff(star x) * 1.496e11 * dt, dt = Noutputs/(Ndays*86400)  (simulation.py:157,186) */
         if ((cfg->flags & NBT_F_RV) && out->rv) {
-            double dtc = (double)NO / (cfg->n_days * 24.0 * 60.0 * 60.0);
+            double dtc = (double)NO / (n_days * 24.0 * 60.0 * 60.0);
             double* rvs = (double*)malloc(sizeof(double) * (NO - 1));
             for (int o = 0; o + 1 < NO; o++) {
                 rvs[o] = (col_s[o + 1] - col_s[o]) * 1.496e11 * dtc;

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../nbody_ai_b200/csrc/nbt_core.cuh"
+#include "../../nbody_ai_b200/csrc/nbt_ias15.cuh"
 
 template <int NP>
 static void run_np(const nbt_run_args& A, int first, int count) {
@@ -23,12 +24,26 @@ extern "C" int hostsim_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outp
     std::memset(&A, 0, sizeof A);
     A.params = in->params; A.substeps = (cfg->substeps > 0) ? nullptr : in->substeps; A.order = in->order;
     A.tt_offsets = in->tt_offsets;
+    A.n_days_sys = in->n_days_sys; A.n_outputs_sys = in->n_outputs_sys;
     A.tt = out->tt; A.n_tt = out->n_tt; A.mean_a = out->mean_a; A.mean_e = out->mean_e;
     A.mean_inc = out->mean_inc; A.mean_omega = out->mean_omega; A.status = out->status;
     A.rv = out->rv; A.orbit_xz = out->orbit_xz; A.series = out->series;
     A.B = cfg->n_systems; A.n_outputs = cfg->n_outputs; A.substeps_all = cfg->substeps;
     A.tt_mode = cfg->tt_mode; A.flags = cfg->flags; A.orbit_stride = cfg->orbit_stride > 0 ? cfg->orbit_stride : 4;
     A.n_days = cfg->n_days;
+    if (cfg->scheme == NBT_SCHEME_IAS15) {   // the reference's own integrator, one system at a time (k_integrate_ias15)
+        nbt_ias15_tables T;
+        nbt_ias15_make_tables(T);
+        for (int b = 0; b < A.B; b++)
+            switch (cfg->n_bodies - 1) {
+            case 1: nbt_simulate_system_ias15<1>(A, T, b); break;
+            case 2: nbt_simulate_system_ias15<2>(A, T, b); break;
+            case 3: nbt_simulate_system_ias15<3>(A, T, b); break;
+            case 4: nbt_simulate_system_ias15<4>(A, T, b); break;
+            default: return -1;
+            }
+        return 0;
+    }
     // NBT_SCHEME_AUTO as in enqueue_path: the trailing cfg.alt_systems launch slots take C4, the rest SBABC3
     const bool automatic = cfg->scheme == NBT_SCHEME_AUTO;
     int nalt = automatic ? cfg->alt_systems : 0;
@@ -59,6 +74,7 @@ extern "C" int hostsim_run_scheme(const nbt_config* cfg, const nbt_inputs* in, n
     std::memset(&A, 0, sizeof A);
     A.params = in->params; A.substeps = (cfg->substeps > 0) ? nullptr : in->substeps; A.order = in->order;
     A.tt_offsets = in->tt_offsets;
+    A.n_days_sys = in->n_days_sys; A.n_outputs_sys = in->n_outputs_sys;
     A.tt = out->tt; A.n_tt = out->n_tt; A.mean_a = out->mean_a; A.mean_e = out->mean_e;
     A.mean_inc = out->mean_inc; A.mean_omega = out->mean_omega; A.status = out->status;
     A.rv = out->rv; A.orbit_xz = out->orbit_xz; A.series = out->series;
@@ -84,7 +100,7 @@ extern "C" int hostsim_kepler(double mu, double h, double* state6) {
     int status = 0;
     double r, ir;
     nbt_radius(state6[0], state6[1], state6[2], r, ir);
-    nbt_kepler_drift(mu, h, state6[0], state6[1], state6[2], state6[3], state6[4], state6[5], r, ir, status);
+    nbt_kepler_drift<true>(mu, h, state6[0], state6[1], state6[2], state6[3], state6[4], state6[5], r, ir, status);
     return status;
 }
 

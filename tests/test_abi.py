@@ -30,9 +30,11 @@ def test_struct_layout_matches_header(nbt):
     cfg = _abi.make_config(1, 3, 10.0, 11, substeps=1)
     off = np.zeros(3, dtype=np.int64)
     par = workloads.c1_params(1)[:, :3].copy()
-    assert nbt.nbt_plan_tt(C.byref(cfg), _abi.ptr(par), _abi.ptr(off, C.c_int64)) > 0
+    inp = _abi.nbt_inputs()
+    inp.params = _abi.ptr(par)
+    assert nbt.nbt_plan_tt(C.byref(cfg), C.byref(inp), _abi.ptr(off, C.c_int64)) > 0
     cfg.struct_size += 4
-    assert nbt.nbt_plan_tt(C.byref(cfg), _abi.ptr(par), _abi.ptr(off, C.c_int64)) == -2
+    assert nbt.nbt_plan_tt(C.byref(cfg), C.byref(inp), _abi.ptr(off, C.c_int64)) == -2
     assert b"struct_size" in nbt.nbt_last_error()
 
 
@@ -80,7 +82,61 @@ def test_invalid_arguments(nbt):
     with pytest.raises(ValueError):
         _abi.objects_to_params([{'m': 1.0}, {'m': 1e-3}])          # planet without a period
     with pytest.raises(ValueError):
-        _abi.objects_to_params([{'m': 1.0}, {'m': 1e-3, 'P': 3.0, 'a': 0.04}])  # unsupported key
+        _abi.objects_to_params([{'m': 1.0}, {'m': 1e-3, 'P': 3.0, 'a': 0.04}])  # both P and a (rebound.add raises too)
+    with pytest.raises(ValueError):
+        _abi.objects_to_params([{'m': 1.0}, {'m': 1e-3, 'P': 3.0, 'l': 0.1}])   # unsupported key
+    # a semi-major axis instead of a period: the Jacobi mu of rebound.add
+    p = _abi.objects_to_params([{'m': 1.0}, {'m': 1e-3, 'a': 0.05}, {'m': 2e-3, 'a': 0.1}])
+    assert abs(p[1, 1] - 2 * np.pi * np.sqrt(0.05 ** 3 / (_abi.NBT_G * 1.001))) < 1e-14
+    assert abs(p[2, 1] - 2 * np.pi * np.sqrt(0.1 ** 3 / (_abi.NBT_G * 1.003))) < 1e-14
+    # per-system grids come in pairs and exclude the [n_outputs][B] products; likelihood needs its arrays
+    plan = engine.Plan(par, 365.0, 8760)
+    buf = engine.Buffers(plan)
+    inp, out = buf.as_structs()
+    nd = np.full(plan.B, 100.0)
+    inp.n_days_sys = _abi.ptr(nd)
+    assert nbt.nbt_run(C.byref(plan.cfg), C.byref(inp), C.byref(out), None) == -14
+    plan.cfg.flags |= _abi.F_LOGLIKE
+    inp.n_days_sys = _abi.ptr(None)
+    assert nbt.nbt_run(C.byref(plan.cfg), C.byref(inp), C.byref(out), None) == -15
+    plan.cfg.flags = _abi.F_LS_PEAKS
+    assert nbt.nbt_run(C.byref(plan.cfg), C.byref(inp), C.byref(out), None) == -16
+
+
+def test_per_system_grids_plan(nbt):
+    """Every draw of the training-set generator has its own grid (generate_simulations.py:45-50): the planner sizes
+    capacities, sub-steps and step counts per system."""
+    par = workloads.random_systems(64, 2, seed=5)
+    nd = par[:, 1, 1] * 50
+    no = np.round(nd * 24).astype(np.int32)
+    plan = engine.Plan(par, nd, no, flags=_abi.F_PLANET1_ONLY)
+    assert plan.cfg.n_outputs == no.max() and plan.cfg.n_days == nd.max()
+    cap = np.diff(plan.tt_offsets).reshape(-1, 2)
+    assert np.array_equal(cap[:, 0], np.minimum(np.ceil(1.05 * nd / par[:, 1, 1]) + 3, no)) and np.all(cap[:, 1] == 1)
+    k = plan.substeps
+    step = nd / (no - 1)
+    assert np.array_equal(np.abs(k), np.maximum(np.ceil(step * 57.5 / par[:, 1:, 1].min(1)), 1))
+    assert plan.n_steps == int((np.where(k > 0, 3 * k, -2 * k) * (no - 1)).sum())
+    assert np.array_equal(plan.times_of(3), np.linspace(0, nd[3], no[3]))
+    # uniform arrays are the scalar plan
+    uni = engine.Plan(par, np.full(64, 100.0), np.full(64, 2401), flags=_abi.F_PLANET1_ONLY)
+    sca = engine.Plan(par, 100.0, 2401, flags=_abi.F_PLANET1_ONLY)
+    assert np.array_equal(uni.tt_offsets, sca.tt_offsets) and np.array_equal(uni.substeps, sca.substeps) and uni.n_steps == sca.n_steps
+
+
+def test_uncalibrated_envelope(nbt):
+    par = workloads.c1_params(1)[0]
+    assert nbt.nbt_uncalibrated(_abi.ptr(par), 4) == 0
+    q = par.copy(); q[2, 2] = 0.2
+    assert nbt.nbt_uncalibrated(_abi.ptr(q), 4) == 1                 # e > 0.1
+    q = par.copy(); q[2, 0] = 0.02 * q[0, 0]
+    assert nbt.nbt_uncalibrated(_abi.ptr(q), 4) == 1                 # heavy planet
+    q = par.copy(); q[2, 1] = 4.2
+    assert nbt.nbt_uncalibrated(_abi.ptr(q), 4) == 1                 # pair inside 4 mutual Hill radii
+    rs = workloads.random_systems(2000, 2, seed=9)
+    plan = engine.Plan(rs, 365.0, 8760)
+    frac = plan.uncalibrated().mean()
+    assert 0.03 < frac < 0.25
 
 
 def test_objects_to_params_defaults():
