@@ -229,6 +229,10 @@ class Buffers:
         self.loglike = z(B) if fl & _abi.F_LOGLIKE else None
 
     def _alloc(self, shape, dtype, pinned):
+        pool = getattr(self, "_pool_alloc", None)
+        if pool is not None:
+            self._n_alloc = getattr(self, "_n_alloc", 0) + 1
+            return pool("a%d" % self._n_alloc, shape if isinstance(shape, tuple) else (int(shape),), dtype)
         if pinned:
             import torch
             t = torch.zeros(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32, pin_memory=True)
@@ -290,6 +294,38 @@ class Buffers:
         T = p.cfg.n_days - step
         df = 1.0 / T / p.cfg.ls_samples_per_peak
         return p.cfg.ls_rv_minfreq + df * np.arange(p.rv_nfreq), self.ls_rv_power[b]
+
+
+class BufferPool:
+    """Page-locked host storage that outlives the plans it serves: a caller whose parameters change from call to call
+    (a sampler, the training-set generator) plans every call anew, and the CSR sizes move with the parameters — but
+    pinning 100s of MB per call costs more than the call.  `buffers_for(plan)` hands out a Buffers whose arrays are
+    views into the pool (grown when a plan needs more)."""
+
+    def __init__(self, pinned=True, headroom=1.1):
+        self.pinned, self.headroom, self.store = pinned, headroom, {}
+
+    def _take(self, name, shape, dtype):
+        n = int(np.prod(shape))
+        name = "%s/%s" % (name, np.dtype(dtype).name)
+        cur = self.store.get(name)
+        if cur is None or cur.size < n:
+            m = max(int(n * self.headroom), 1)
+            if self.pinned:
+                import torch
+                t = torch.zeros(m, dtype=torch.float64 if dtype == np.float64 else torch.int32, pin_memory=True)
+                self.store[name + "/t"] = t
+                cur = t.numpy()
+            else:
+                cur = np.zeros(m, dtype=dtype)
+            self.store[name] = cur
+        return cur[:n].reshape(shape)
+
+    def buffers_for(self, plan, skip=()):
+        buf = Buffers.__new__(Buffers)
+        buf._pool_alloc = self._take
+        Buffers.__init__(buf, plan, pinned=False, skip=skip)
+        return buf
 
 
 def run(plan, buffers=None, stream=None):

@@ -44,9 +44,11 @@ class Simulation:
 
 
 def _integrator_kw(integrator, Ndays, Noutputs):
-    """integrator=None: REBOUND's default (IAS15) is matched within the parity tolerances by the
-    planned SBABC3 / C4 compositions (NBT_SCHEME_AUTO).  'whfast' (simulation.py:39-42): plain Wisdom-Holman leapfrog at
-    REBOUND's default dt = 1e-3 d.  'tes' (:34-38) is a high-accuracy scheme: same as None."""
+    """integrator=None: REBOUND's default (IAS15) is matched within the parity tolerances by the planned
+    SBABC3 / C4 compositions (NBT_SCHEME_AUTO).  'whfast' (simulation.py:39-42): Wisdom-Holman leapfrog at REBOUND's
+    default dt = 1e-3 d — far inside the tolerances of either form of REBOUND's WHFast (the 5th-order corrector of
+    :41 moves transit times by < 1e-3 s at this step; NBT_SCHEME_WHFAST, the corrector-exact form, is reserved in the
+    ABI but not built).  'tes' (:34-38) is a high-accuracy scheme: same as None."""
     if integrator == 'whfast':
         step = float(Ndays) / (int(Noutputs) - 1)
         return dict(scheme=_abi.SCHEME_WH2, substeps=max(1, int(np.ceil(step / 1e-3))))
@@ -148,12 +150,19 @@ def analyze(m, ttvfast=False):
     params = _abi.objects_to_params(objects)[None]
     flags = _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_RV | _abi.F_ORBIT | _abi.F_LS_OC
     plan = engine.Plan(params, float(times[-1] - times[0]), NO, substeps=1, flags=flags)
-    # a recorded series can hold at most one transit per sample interval whatever P says
+    # a recorded series need not match `objects` (edited periods, unstable orbits): it can hold at most one transit
+    # per sample interval whatever P says, so the capacity is NO - 1 per planet
+    Np = plan.Np
+    plan.tt_offsets = np.arange(Np + 1, dtype=np.int64) * (NO - 1)
+    plan.cfg.tt_cap_max = NO - 1
+    lib.nbt_plan_ls(C.byref(plan.cfg), _abi.ptr(plan.tt_offsets, C.c_int64), _abi.ptr(plan.ls_offsets, C.c_int64))
     buf = engine.Buffers(plan)
     series = _series_from_sim_data(m)
     inp, out = buf.as_structs()
     _abi.check(lib.nbt_analyze(C.byref(plan.cfg), _abi.ptr(series), _abi.ptr(times), float(m['dt']),
                                C.byref(inp), C.byref(out), None), lib)
+    if buf.status[0] & _abi.S_TT_OVERFLOW:
+        raise RuntimeError("analyze(): transit buffer overflow (more than one crossing per sample interval?)")
     RV = buf.rv[:, 0].copy()
     freq, power = lomb_scargle(times[1:], RV)
     data = {
@@ -274,8 +283,12 @@ def analyze_batch(result):
 
 
 def report(data, savefile=None):
-    """simulation.py:235-334 is a matplotlib figure and is out of scope here.  `data` keeps every key it
-    reads (:249-299), so the reference's own report() renders the dict returned by analyze() unchanged:
-        from nbody.simulation import report; report(nbody_ai_b200.simulation.analyze(sim_data))"""
-    raise NotImplementedError("report() is plotting (out of scope); pass this ttv_data dict to the reference's "
-                              "nbody.simulation.report — the layout is identical")
+    """simulation.py:235-334 is a matplotlib figure: plotting is out of scope here, but `data` keeps every key it
+    reads (:249-299), so the reference's own report() renders the dict returned by analyze() unchanged.  If the
+    reference package is importable (nbody on sys.path, with matplotlib) the call is forwarded to it."""
+    try:
+        from nbody.simulation import report as reference_report
+    except Exception as exc:
+        raise NotImplementedError("report() is plotting (out of scope) and the reference's nbody.simulation.report is not "
+                                  "importable here (%s); pass this ttv_data dict to it — the layout is identical" % exc)
+    return reference_report(data, savefile=savefile)

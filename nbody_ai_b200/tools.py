@@ -128,16 +128,60 @@ def maxavg(x):
     return float(out[0])
 
 
-def lomb_scargle(t, y, dy=None, minfreq=1. / 365, maxfreq=1 / 2, npeaks=0, peaktol=0.05):
-    """Periodogram on astropy's autofrequency grid (nbody/tools.py:97-104): returns (frequency, power).
+def make_sin(t, pars, freqs=-1):
+    """Sum of sines (nbody/tools.py:78-95): rows of pars are (frequency, amplitude, phase), or (amplitude, phase)
+    with the frequencies given in `freqs`.  Host helper of lomb_scargle(npeaks > 0) and of the decoder scripts."""
+    fn = 0
+    pars = np.asarray(pars, dtype=float)
+    if isinstance(freqs, (list, np.ndarray)):
+        if pars.ndim == 1:
+            pars = pars.reshape(-1, 2)
+        for i in range(pars.shape[0]):
+            fn += pars[i, 0] * np.sin(t * 2 * np.pi * freqs[i] + pars[i, 1])
+    else:
+        if pars.ndim == 1:
+            pars = pars.reshape(-1, 3)
+        for i in range(pars.shape[0]):
+            fn += pars[i, 1] * np.sin(t * 2 * np.pi * pars[i, 0] + pars[i, 2])
+    return fn
 
-    Floating-mean generalised Lomb-Scargle with standard normalisation (what astropy's exact
-    methods compute).  `dy` (per-point errors) and `npeaks > 0` (sine-series fit, tools.py:112-143)
-    are never used on the hot path (nbody/simulation.py:188,213) and are not implemented."""
-    if dy is not None:
-        raise NotImplementedError("lomb_scargle(dy=...) is outside the hot path (never passed by the reference)")
-    if npeaks > 0:
-        raise NotImplementedError("lomb_scargle(npeaks>0) is outside the hot path (never used by the reference)")
+
+def _weighted_ls_host(t, y, dy, freq):
+    """Floating-mean generalised Lomb-Scargle with weights 1/dy^2 (LombScargle(t, y, dy), standard normalisation)
+    [3P].  Never on the hot path (no caller of the reference passes dy: nbody/simulation.py:188,213), so it is a
+    plain numpy evaluation on the host, kept for signature compatibility."""
+    w = 1.0 / dy ** 2
+    w = w / w.sum()
+    yb = np.sum(w * y)
+    yc = y - yb
+    YY = np.sum(w * yc * yc)
+    power = np.zeros(len(freq))
+    for lo in range(0, len(freq), 256):
+        f = freq[lo:lo + 256, None]
+        arg = 2 * np.pi * f * t[None, :]
+        s, c = np.sin(arg), np.cos(arg)
+        S, Cc = (w * s).sum(1), (w * c).sum(1)
+        S2 = 2 * (w * s * c).sum(1) - 2 * S * Cc
+        C2 = (w * (c * c - s * s)).sum(1) - (Cc * Cc - S * S)
+        tau = 0.5 * np.arctan2(S2, C2)
+        ct, st = np.cos(tau)[:, None], np.sin(tau)[:, None]
+        cs, sn = c * ct + s * st, s * ct - c * st
+        YC, YS = (w * yc * cs).sum(1), (w * yc * sn).sum(1)
+        CC = (w * cs * cs).sum(1) - (w * cs).sum(1) ** 2
+        SS = (w * sn * sn).sum(1) - (w * sn).sum(1) ** 2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            power[lo:lo + 256] = (np.where(CC > 1e-14, YC * YC / CC, 0.0) + np.where(SS > 1e-14, YS * YS / SS, 0.0)) / YY
+    return power
+
+
+def lomb_scargle(t, y, dy=None, minfreq=1. / 365, maxfreq=1 / 2, npeaks=0, peaktol=0.05):
+    """Periodogram on astropy's autofrequency grid (nbody/tools.py:97-145): returns (frequency, power), or
+    (frequency, power, fdata) when npeaks > 0.
+
+    Floating-mean generalised Lomb-Scargle with standard normalisation (what astropy's exact methods compute), on
+    the GPU.  The two off-path branches keep the reference's signature and run on the host: `dy` as an ndarray
+    (per-point errors; a non-array dy is ignored like the reference's isinstance test, :99-102) and `npeaks > 0`
+    (find_peaks + bounded least squares of a sine series, :112-143; fdata rows = frequency, amplitude, phase)."""
     t, y = _f64(t), _f64(y)
     if len(t) != len(y):
         raise ValueError("t and y must have equal length")
@@ -147,7 +191,30 @@ def lomb_scargle(t, y, dy=None, minfreq=1. / 365, maxfreq=1 / 2, npeaks=0, peakt
     if nf <= 0:
         raise ValueError("lomb_scargle: zero baseline")
     df = 1.0 / baseline / 10
-    power = np.zeros(nf)
-    _abi.check(lib.nbt_lomb_scargle(_abi.ptr(t), _abi.ptr(y), 1, len(t), float(minfreq), df, nf, _abi.ptr(power),
-                                    0, 0, None), lib)
-    return minfreq + df * np.arange(nf), power
+    frequency = minfreq + df * np.arange(nf)
+    if isinstance(dy, np.ndarray):
+        power = _weighted_ls_host(t, y, _f64(dy), frequency)
+    else:
+        power = np.zeros(nf)
+        _abi.check(lib.nbt_lomb_scargle(_abi.ptr(t), _abi.ptr(y), 1, len(t), float(minfreq), df, nf, _abi.ptr(power),
+                                        0, 0, None), lib)
+    if npeaks > 0:
+        from scipy.optimize import least_squares
+        from scipy.signal import find_peaks
+        peaks, amps = find_peaks(power, height=peaktol)
+        Nterms = npeaks
+        fdata = np.zeros((Nterms, 3))                                     # frequency, amplitude, shift
+        peaks = peaks[np.argsort(amps['peak_heights'])[::-1]]             # sort high to low
+        for i in range(min(npeaks, len(peaks))):
+            fdata[i, 0] = frequency[int(peaks[i])]
+            fdata[i, 1] = np.sort(amps['peak_heights'])[::-1][i] * maxavg(y)
+            fdata[i, 2] = 0
+        priors = fdata.flatten()
+        bounds = np.array([[0, 1], [0, max(y) * 1.5], [0, 2 * np.pi]] * Nterms).T
+
+        def fit_wave(pars):
+            return (y - make_sin(t, pars)) / y
+
+        res = least_squares(fit_wave, x0=priors, bounds=bounds)
+        return frequency, power, res.x.reshape(Nterms, -1)
+    return frequency, power

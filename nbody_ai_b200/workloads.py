@@ -123,20 +123,43 @@ def c3_params(n=5000, seed=1):
     return par, dict(ndays=79, noutputs=79 * 48, epochs=56)
 
 
-def c4_params(npts=256):
-    """Config C4: simulation_grid.py:88-153 — 1.12-Msun-class star, inner planet at 1.42 d, grid over
-    perturber mass (0.5..325 Mearth) x period ratio (1.41..2.41), astropy constants."""
-    msun_a, mearth_a, mjup_a = 1.988409870698051e30, 5.972167867791379e24, 1.8981245973360505e27
-    m2 = np.linspace(0.5, 325, npts) * mearth_a / msun_a
-    p2 = np.linspace(1.41, 2.41, npts) * 1.42
-    par = np.zeros((npts, npts, 3, _abi.NBT_NPAR))
-    par[..., 0, 0] = 1.12
-    par[..., 1, 0] = 1.0 * mjup_a / msun_a
-    par[..., 1, 1] = 1.42
-    par[..., 1:, 3] = HALF_PI
-    par[..., 2, 0] = m2[:, None]
-    par[..., 2, 1] = p2[None, :]
-    return par.reshape(npts * npts, 3, _abi.NBT_NPAR), dict(ndays=710, noutputs=34080)
+# astropy.constants values the reference's grid script overrides tools.py's with (simulation_grid.py:83-85;
+# IAU 2015 / CODATA 2018) [3P]
+MSUN_ASTROPY, MEARTH_ASTROPY, MJUP_ASTROPY = 1.988409870698051e30, 5.972167867791379e24, 1.8981245973360505e27
+
+
+def c4_objects():
+    """The objects list of simulations/simulation_grid.py:88-113 (planet 2's P is set per cell)."""
+    me = MEARTH_ASTROPY / MSUN_ASTROPY
+    return [
+        {'m': 1},
+        {'m': 10 * me, 'P': 1.42, 'inc': np.deg2rad(90), 'e': 0, 'omega': 0.01},
+        {'m': 10 * me, 'omega': np.deg2rad(90), 'e': 0, 'inc': np.deg2rad(90)},
+    ]
+
+
+def c4_grids(npts=256):
+    """mass_grid, period_grid of simulation_grid.py:115-119: np.meshgrid(mass_range, period_range), i.e. cell [i][j]
+    has period_range[i] and mass_range[j]."""
+    obj = c4_objects()
+    mass_range = np.linspace(0.5, 325, npts) * MEARTH_ASTROPY / MSUN_ASTROPY
+    period_range = np.linspace(1.41, 2.41, npts) * obj[1]['P']
+    return np.meshgrid(mass_range, period_range)
+
+
+def c4_params(npts=256, epochs=500):
+    """Config C4: the reference's grid (simulation_grid.py:88-153) — 1 Msun star, 10 Mearth inner planet at 1.42 d
+    (omega = 0.01), perturber (omega = 90 deg) over mass 0.5..325 Mearth x period ratio 1.41..2.41, astropy constants;
+    `epochs` inner periods at 30-minute cadence (generate_sim :23-25).  Cells in row-major order of the meshgrid."""
+    obj = c4_objects()
+    mass_grid, period_grid = c4_grids(npts)
+    obj[2]['P'] = 1.0
+    base = _abi.objects_to_params(obj)
+    par = np.repeat(base[None], npts * npts, axis=0)
+    par[:, 2, _abi.P_M] = mass_grid.ravel()
+    par[:, 2, _abi.P_P] = period_grid.ravel()
+    ndays = obj[1]['P'] * epochs
+    return par, dict(ndays=ndays, noutputs=int(round(obj[1]['P'] * epochs * 48)), epochs=epochs)
 
 
 def c5_params(n=1000000, seed=2):

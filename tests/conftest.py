@@ -75,3 +75,76 @@ def compare_products(got, want, plan, tol_tt=TOL_TT_S, tol_oc=TOL_OC_MIN, tol_ae
     assert worst['a'] < tol_ae, worst
     assert worst['e'] < tol_ae, worst
     return worst
+
+
+def oracle_buffers(plan):
+    import oracle
+    from nbody_ai_b200 import engine
+    buf = engine.Buffers(plan)
+    oracle.run(plan.cfg, plan.params, buf)
+    return buf
+
+
+def oracle_is_chaotic(par_b, n_days, n_outputs, base=None, tol_s=1e-2, tol_e=1e-9):
+    """The ONLY parity exclusion: the oracle's own answer moves by more than 0.01 s in a transit time or 1e-9 in a mean
+    eccentricity when every period changes by 1e-13 (relative, alternating sign) — or the oracle run itself breaks
+    (ejection, collision).  Such a system has no defined parity target: REBOUND and this oracle differ by more than
+    that in round-off alone."""
+    import oracle
+    from nbody_ai_b200 import _abi, engine
+    P = np.ascontiguousarray(par_b[None])
+    plan = engine.Plan(P, n_days, n_outputs, substeps=1, scheme="sbabc3", flags=_abi.F_MEANS)
+    a = base
+    if a is None:
+        a = engine.Buffers(plan); oracle.run(plan.cfg, P, a, n_threads=1)
+    if a.status[0] & (_abi.S_NONFINITE | _abi.S_UNBOUND):
+        return True
+    Q = P.copy()
+    Q[0, 1:, 1] *= 1.0 + 1e-13 * (1 - 2 * (np.arange(P.shape[1] - 1) % 2))
+    b = engine.Buffers(plan); oracle.run(plan.cfg, Q, b, n_threads=1)
+    if not np.array_equal(a.n_tt, b.n_tt):
+        return True
+    dtt = max([np.abs(a.tt_of(0, j) - b.tt_of(0, j)).max() * 86400 for j in range(plan.Np) if a.n_transits(0, j)] + [0.0])
+    de = np.abs(a.mean_e - b.mean_e) / np.maximum(a.mean_e, 1e-4)
+    return bool(dtt > tol_s or de.max() > tol_e)
+
+
+def parity_report(got, want, plan):
+    """Per-system worst differences in units of the parity tolerances (tt 1 s, O-C 1e-3 min, mean a / e 1e-8 relative;
+    e with AND without the 1e-4 floor).  Returns arrays [B]: worst (floored), e_rel_nofloor, count_mismatch."""
+    B, Np = plan.B, plan.Np
+    worst, e_nf, mism = np.zeros(B), np.zeros(B), np.zeros(B, dtype=bool)
+    for b in range(B):
+        w = 0.0
+        for j in range(Np):
+            sp = b * Np + j
+            if got.n_tt[sp] != want.n_tt[sp]:
+                mism[b] = True
+                continue
+            n = got.n_transits(b, j)
+            if n:
+                w = max(w, np.abs(got.tt_of(b, j) - want.tt_of(b, j)).max() * 86400 / TOL_TT_S)
+            if n >= 3:
+                w = max(w, np.abs(got.ttv_of(b, j) - want.ttv_of(b, j)).max() * 1440 / TOL_OC_MIN)
+            w = max(w, abs(got.mean_a[sp] / want.mean_a[sp] - 1) / TOL_AE_REL)
+            de = abs(got.mean_e[sp] - want.mean_e[sp])
+            w = max(w, de / max(want.mean_e[sp], 1e-4) / TOL_AE_REL)
+            e_nf[b] = max(e_nf[b], de / want.mean_e[sp] if want.mean_e[sp] > 0 else 0.0)
+        worst[b] = np.inf if mism[b] else w
+    return worst, e_nf, mism
+
+
+def assert_parity_or_chaotic(got, want, plan, max_excluded_frac=1.0):
+    """Every system inside the tolerances, except those the oracle itself declares chaotic (tested only for the systems
+    that miss).  Returns (n_excluded, worst of the compared)."""
+    n_days, n_outputs = plan.cfg.n_days, plan.cfg.n_outputs
+    worst, _, _ = parity_report(got, want, plan)
+    excluded = 0
+    for b in np.flatnonzero(~(worst < 1.0)):
+        nd = plan.n_days_sys[b] if plan.n_days_sys is not None else n_days
+        no = plan.n_outputs_sys[b] if plan.n_outputs_sys is not None else n_outputs
+        assert oracle_is_chaotic(plan.params[b], nd, int(no)), "system %d misses the tolerances (%.3g x) and is not chaotic" % (b, worst[b])
+        excluded += 1
+    assert excluded <= max_excluded_frac * plan.B, "%d of %d systems excluded as chaotic" % (excluded, plan.B)
+    keep = worst < 1.0
+    return excluded, float(worst[keep].max()) if keep.any() else 0.0

@@ -9,7 +9,8 @@ import pytest
 
 import oracle
 from nbody_ai_b200 import _abi, engine, nested, simulation, tools, workloads
-from conftest import TOL_OC_MIN, TOL_TT_S, compare_products, golden
+from conftest import (TOL_OC_MIN, TOL_TT_S, assert_parity_or_chaotic, compare_products, golden, oracle_is_chaotic,
+                      parity_report)
 
 pytestmark = pytest.mark.gpu
 FULL = _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC
@@ -22,8 +23,10 @@ def oracle_run(plan):
 
 
 def regular(par):
-    """Drop strongly interacting pairs (period ratio < 1.8): chaotic on year time-scales, no two
-    integrators agree there (the reference rejects them by TTV amplitude)."""
+    """Well-separated systems only (period ratio > 1.8).  A WORKLOAD filter for the tests that compare two GPU code
+    paths bit for bit or to round-off (lanes vs thread kernel, schemes, shards): there a system that breaks up would
+    only test NaN handling.  It is NOT used where the GPU is compared with the oracle — those tests take every
+    system the priors produce, run the verified mode and exclude only what the oracle itself declares chaotic."""
     keep = np.ones(len(par), dtype=bool)
     for j in range(2, par.shape[1]):
         keep &= par[:, j, 1] / par[:, j - 1, 1] > 1.8
@@ -63,39 +66,44 @@ def test_readme_g1_vs_oracle_and_fixture(gpu_lib):
 
 
 def test_c2_small_fixture(gpu_lib):
-    """48 seeded C2 systems, 60 d at 1 h: GPU vs the committed oracle outputs."""
+    """48 seeded C2 systems, 60 d at 1 h: GPU (verified mode) vs the committed oracle outputs — every system."""
     g = golden("c2_small.npz")
     plan = engine.Plan(g["params"], float(g["n_days"]), int(g["n_outputs"]), flags=FULL)
     assert np.array_equal(plan.tt_offsets, g["tt_offsets"]) and np.array_equal(plan.ls_offsets, g["ls_offsets"])
-    got = engine.run(plan)
+    got = engine.run_verified(plan)
     want = engine.Buffers(plan)
     for k in ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega",
               "status", "ls_oc_power", "ls_oc_nfreq"):
         getattr(want, k)[...] = g[k]
-    ratio = g["params"][:, 2, 1] / g["params"][:, 1, 1]
-    skip = set(np.nonzero(ratio < 1.8)[0].tolist())
-    compare_products(got, want, plan, skip=skip)
-    for b in range(plan.B):
-        if b in skip:
-            continue
+    excluded, _ = assert_parity_or_chaotic(got, want, plan, max_excluded_frac=0.1)
+    worst, _, _ = parity_report(got, want, plan)
+    for b in np.flatnonzero(worst < 1.0):
         assert np.array_equal(got.ls_oc_nfreq[b * 2:b * 2 + 2], want.ls_oc_nfreq[b * 2:b * 2 + 2])
         for j in range(2):
             if got.n_transits(b, j) >= 3:
                 assert np.abs(got.ls_oc_of(b, j)[1] - want.ls_oc_of(b, j)[1]).max() < 1e-5
                 assert abs(got.ttv_max[b * 2 + j] - want.ttv_max[b * 2 + j]) * 1440 < TOL_OC_MIN
-        assert abs(got.mean_omega[b * 2 + 1] - want.mean_omega[b * 2 + 1]) < 1e-4
+        dom = abs(got.mean_omega[b * 2 + 1] - want.mean_omega[b * 2 + 1])
+        assert dom < 1e-4 or abs(dom - 2 * np.pi / plan.cfg.n_outputs) < 1e-4      # one sample on the other side of the 0 / 2 pi cut
 
 
 @pytest.mark.parametrize("n_planets,seed,n", [(2, 101, 96), (3, 102, 64), (4, 103, 48)])
 def test_random_systems_vs_oracle(gpu_lib, n_planets, seed, n):
-    """Seeded draws of the reference priors (extended outward for 3-4 planets), 1-year 1-hour
-    integrations with the planner's sub-steps; ragged batch sizes (not multiples of the block)."""
-    par = regular(workloads.random_systems(n, n_planets, seed))[: n - 5]
+    """Seeded draws of the reference priors (extended outward for 3-4 planets), 1-year 1-hour integrations, ragged
+    batch sizes (not multiples of the block): EVERY draw, verified mode; only oracle-chaotic systems are excluded.
+    The fast mode is held to the same bar on the systems it does not flag NBT_S_UNCALIBRATED."""
+    par = workloads.random_systems(n, n_planets, seed)[: n - 5]
     plan = engine.Plan(par, 365.0, 8760, flags=FULL)
-    got = engine.run(plan)
     want = oracle_run(plan)
+    fast = engine.run(plan)
+    worst, _, _ = parity_report(fast, want, plan)
+    clean = (fast.status & _abi.S_UNCALIBRATED) == 0
+    assert clean.sum() > 0.5 * plan.B and np.all(worst[clean] < 1.0), "an unflagged system misses the tolerances in the fast mode"
+    rep = {}
+    got = engine.run_verified(plan, report=rep)
+    assert rep["flagged"] == int((~clean).sum())
+    assert_parity_or_chaotic(got, want, plan, max_excluded_frac=0.25)
     ok = [b for b in range(plan.B) if not (want.status[b] & (_abi.S_NONFINITE | _abi.S_UNBOUND))]
-    compare_products(got, want, plan, skip=set(range(plan.B)) - set(ok))
     assert np.array_equal(got.status[ok] & _abi.S_FEW_TRANSITS, want.status[ok] & _abi.S_FEW_TRANSITS)
 
 
@@ -273,12 +281,9 @@ def test_full_size_invariants(gpu_lib):
             assert sub.mean_e[q * 2 + j] == host.mean_e[b * 2 + j] and sub.ttv_max[q * 2 + j] == host.ttv_max[b * 2 + j]
     # omega-sweep structure: variants of one draw share star/planet-1 parameters
     assert np.array_equal(par[0:7, 1, :], np.repeat(par[0:1, 1, :], 7, axis=0))
-    # stratified oracle sample
-    pick = regular(par[::1400])
-    p2 = engine.Plan(pick, 365.0, 8760, flags=FULL)
-    got, want = engine.run(p2), oracle_run(p2)
-    ok = {b for b in range(p2.B) if not (want.status[b] & (_abi.S_NONFINITE | _abi.S_UNBOUND))}
-    compare_products(got, want, p2, skip=set(range(p2.B)) - ok)
+    # stratified oracle sample: every 700th system, whatever it is (verified mode; only oracle-chaotic ones excluded)
+    p2 = engine.Plan(par[::700], 365.0, 8760, flags=FULL)
+    assert_parity_or_chaotic(engine.run_verified(p2), oracle_run(p2), p2, max_excluded_frac=0.1)
 
 
 def test_auto_scheme_agrees_with_sbabc3(gpu_lib):
@@ -449,41 +454,61 @@ def test_in_process_multi_gpu_sharding(gpu_lib):
 
 def test_c5_full_length_four_planets(gpu_lib):
     """BASELINE config 5 at full length (1095 d @ 1 h, 26 280 outputs, four planets, priors extended
-    outward): a 2048-system slice on the GPU, a stratified sample against the oracle, and batch
-    invariance of the sample (same bits whether run inside the slice or alone)."""
+    outward): a 2048-system slice on the GPU, every 64th system against the oracle in verified mode (no period-ratio
+    cut: only oracle-chaotic systems are excluded), and batch invariance (same bits inside the slice or alone)."""
     par = workloads.c5_params(2048, seed=2)
     plan = engine.Plan(par, 1095.0, 26280, flags=_abi.F_MEANS, lanes=0)
     got = engine.run(plan)
     pick = np.arange(0, 2048, 64)
-    pick = np.array([b for b in pick if np.all(par[b, 2:, 1] / par[b, 1:-1, 1] > 1.8)])[:20]
     sub_plan = engine.Plan(par[pick], 1095.0, 26280, substeps=plan.substeps[pick], flags=_abi.F_MEANS, lanes=0)
     sub, want = engine.run(sub_plan), oracle_run(sub_plan)
-    ok = {q for q in range(len(pick)) if not (want.status[q] & (_abi.S_NONFINITE | _abi.S_UNBOUND))}
-    assert len(ok) >= 10
-    compare_products(sub, want, sub_plan, skip=set(range(len(pick))) - ok)
     for q, b in enumerate(pick):
         for j in range(4):
             assert np.array_equal(sub.tt_of(q, j), got.tt_of(b, j))
-            assert sub.mean_a[q * 4 + j] == got.mean_a[b * 4 + j]
+            assert sub.mean_a[q * 4 + j] == got.mean_a[b * 4 + j] or (sub.status[q] & _abi.S_NONFINITE)
+    ver = engine.run_verified(sub_plan)
+    excluded, _ = assert_parity_or_chaotic(ver, want, sub_plan, max_excluded_frac=0.35)
+    assert len(pick) - excluded >= 20
 
 
-def test_c4_grid_cells_full_length(gpu_lib):
-    """BASELINE config 4 at full length (500 epochs of the 1.42 d planet at 30 min = 34 080 outputs):
-    a 6 x 6 sub-grid; planet-1 transit times and O-C against the oracle."""
-    par, meta = workloads.c4_params(npts=6)
-    plan = engine.Plan(par, meta["ndays"], meta["noutputs"], flags=_abi.F_PLANET1_ONLY, lanes=0)
-    got = engine.run(plan)
-    pick = np.arange(0, 36, 5)
-    sub_plan = engine.Plan(par[pick], meta["ndays"], meta["noutputs"], substeps=plan.substeps[pick],
-                           flags=_abi.F_PLANET1_ONLY | _abi.F_MEANS, lanes=0)
-    sub, want = engine.run(sub_plan), oracle_run(sub_plan)
-    for q, b in enumerate(pick):
-        if par[b, 2, 1] / par[b, 1, 1] < 1.8 or (want.status[q] & (_abi.S_NONFINITE | _abi.S_UNBOUND)):
+def test_c4_reference_grid_full_length(gpu_lib):
+    """BASELINE config 4 as the reference defines it (simulation_grid.py:88-118: 1 Msun, 10 Mearth inner planet at
+    1.42 d, omega 0.01 / 90 deg, astropy constants), full length (500 epochs at 30 min = 34 080 outputs): a 32 x 32
+    grid over the WHOLE period-ratio range 1.41-2.41 = 1024 cells against the oracle, transit times, O-C and the
+    k_grid_post products (softmax amplitude, dominant periodicity) included."""
+    from scipy.signal import find_peaks
+    from nbody_ai_b200 import grid
+    par, meta = workloads.c4_params(npts=32)
+    assert par[0, 0, 0] == 1 and abs(par[0, 1, 0] * workloads.MSUN_ASTROPY / workloads.MEARTH_ASTROPY - 10) < 1e-12
+    assert par[0, 1, 5] == 0.01 and abs(par[0, 2, 5] - np.pi / 2) < 1e-15
+    ratio = par[:, 2, 1] / par[:, 1, 1]
+    assert abs(ratio.min() - 1.41) < 1e-12 and abs(ratio.max() - 2.41) < 1e-12 and (ratio < 1.8).mean() > 0.35
+    plan = engine.Plan(par, meta["ndays"], meta["noutputs"], flags=_abi.F_PLANET1_ONLY | _abi.F_MEANS, lanes=0)
+    want = oracle_run(plan)
+    got = engine.run_verified(plan)
+    excluded, worst = assert_parity_or_chaotic(got, want, plan, max_excluded_frac=0.02)
+    assert np.all((got.n_tt[::2] >= 495) & (got.n_tt[::2] <= 505))
+    # grid post-processing on the same cells (fast mode inside generate_sim_batch) vs the reference's own calls on the
+    # ORACLE's transit times
+    r = grid.generate_sim_batch(par, epochs=meta["epochs"], n_order=4)
+    pw, _, _ = parity_report(r["buffers"], want, plan)
+    checked = 0
+    for b in range(0, plan.B, 8):
+        if not pw[b] < 1.0:
             continue
-        assert sub.n_tt[q * 2] == want.n_tt[q * 2] and 495 <= sub.n_tt[q * 2] <= 505
-        assert np.abs(sub.tt_of(q, 0) - want.tt_of(q, 0)).max() * 86400 < TOL_TT_S
-        assert np.abs(sub.ttv_of(q, 0) - want.ttv_of(q, 0)).max() * 1440 < TOL_OC_MIN
-        assert np.array_equal(sub.tt_of(q, 0), got.tt_of(b, 0))
+        Tc = want.tt_of(b, 0)
+        n = len(Tc)
+        orbit = np.arange(n)
+        t0, per = np.linalg.lstsq(np.vstack([np.ones(n), orbit]).T, Tc, rcond=None)[0]
+        ttv = Tc - per * orbit - t0
+        assert abs(r["ttv_max"][b] - np.percentile(np.abs(ttv), 95) * 0.5) * 1440 < TOL_OC_MIN
+        freq, power = oracle.lomb_scargle(orbit.astype(float), ttv, 1. / (1.5 * meta["epochs"]), 1. / 2.1, 20)
+        peaks, amps = find_peaks(power, height=0.05)
+        if len(peaks) and amps['peak_heights'].max() > 0.2:      # the dominant periodicity (the reference's maps) agrees
+            top = peaks[np.argmax(amps['peak_heights'])]
+            assert r["n_peaks"][b] >= 1 and abs(r["peak_periods"][b, 0] * freq[top] - 1) < 1e-6
+        checked += 1
+    assert checked >= 100
 
 
 def test_ttv_fit_vectorised_likelihood(gpu_lib):
