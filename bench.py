@@ -5,18 +5,27 @@ TTV sims/s at 1/2/4/8 B200 beside the host CPU).
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
 
-Workload (config C2 of BASELINE.json): random 2-planet systems from the priors of
-randomize() (nbody/simulation.py:54-129) with the omega sweep of
-simulations/generate_simulations.py:83-107 — 10 000 draws x (1 + 6 omega variants) = 70 000
-simulations per GPU per step; 365 d sampled hourly (8760 outputs); products per planet: transit
-times, linear ephemeris, O-C, maxavg, O-C periodogram, means of a/e/inc/omega.  A step is one
-pass of the whole path over that batch.  Weak scaling: every rank owns its own 70 000 systems.
+Headline workload (`value`, `e2e`, `roofline`): config C2 of BASELINE.json (configs[1]) — random
+2-planet systems from the priors of randomize() (nbody/simulation.py:54-129) with the omega sweep of
+simulations/generate_simulations.py:83-107: 10 000 draws x (1 + 6 omega variants) = 70 000 simulations per GPU per
+step; 365 d sampled hourly (8760 outputs); products per planet: transit times, linear ephemeris, O-C, maxavg, O-C
+periodogram, means of a/e/inc/omega.  A step is one pass of the whole path over that batch.  Weak scaling: every rank
+owns 70 000 systems.
 
-`value` is whole-job TTV sims/s with inputs resident in HBM (torch device tensors, kernels enqueued
-through the C ABI with NBT_F_DEVICE_PTRS); `e2e` is the same through nbt_run with HOST buffers
-(H2D of the parameter block and plan, D2H of every product inside the timed call);
-`system_steps_per_s` counts kick+drift stages.  The roofline is the FP64 vector pipe, measured
-live with a DFMA-chain kernel (MEASURED_PEAKS.json has no FP64 figure).
+`value` is whole-job TTV sims/s with inputs resident in HBM (torch device tensors, kernels enqueued through the C ABI
+with NBT_F_DEVICE_PTRS).  `e2e` is the same through the public host-buffer call a user makes: every step PLANS the
+batch anew (engine.Plan -> nbt_plan: sub-steps, launch order, CSR layout — a sampler's or the training-set
+generator's parameters change from call to call), copies the parameter block and plan H2D from pinned memory,
+runs the kernels and copies every product D2H into pinned buffers (nbt_run).
+
+`north_star` block (BASELINE.json's target: >= 1e11 system-steps/s on 8 GPUs for 3-planet systems at >= 50 % of the
+FP64 roofline; config 5 sharded over 1/2/4/8): three more device-timed workloads, each with system-steps/s, sims/s and
+the SURVEY §8(d) roofline fraction — (i) the README 3-planet system replicated, (ii) random 3-planet systems,
+(iii) C5 at full size, 1 M random 4-planet systems over 1095 d, sharded by system over the ranks (strong scaling).
+
+Roofline: the FP64 vector pipe.  achieved = SURVEY §8(d)'s algorithmic FLOPs — system-steps x (272 Np + 12.5 Np (Np+1)
+- 40) + output samples x 100 Np — / the CUDA-event duration of k_integrate; peak = a DFMA-chain kernel measured in the
+same run (MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s).
 """
 import argparse
 import ctypes as C
@@ -34,37 +43,37 @@ sys.path.insert(0, ROOT)
 
 N_DAYS, N_OUTPUTS = 365.0, 8760
 WORKLOAD = ("C2: random 2-planet systems (randomize() priors, generate_simulations.py omega sweep), "
-            "365 d @ 1 h, tt + ephemeris + O-C + maxavg + O-C periodogram + element means")
+            "365 d @ 1 h, tt + ephemeris + O-C + maxavg + O-C periodogram + element means "
+            "[north_star block: README 3-planet x 227 328 and random 3-planet systems, 365 d @ 1 h; "
+            "C5 = 1 M random 4-planet systems, 1095 d @ 1 h, sharded over the ranks]")
+FP64_NOMINAL = 37.2
 
 
-def f_step(np_, stages=3, forces=4, grad_kicks=1):
-    """Algorithmic FLOPs per system-step = one Kepler-drift stage of one system (FMA = 2,
-    div/sqrt = 1): drift 230 Np + kick 6 Np + the force evaluation (Jacobi<->inertial 21 Np, pairs
-    12.5 Np (Np+1) - 25, indirect term 15 (Np-1)).  SURVEY's figure has one force evaluation per stage
-    (272 Np + 12.5 Np (Np+1) - 40); the default SBABC3 scheme has `forces` = 4 evaluations and one
-    displaced-position set-up (6 Np + 7 (Np-1)) per `stages` = 3 drift stages."""
-    force = 21 * np_ + 12.5 * np_ * (np_ + 1) - 25 + 15 * (np_ - 1)
-    return 236 * np_ + (forces * force + grad_kicks * (6 * np_ + 7 * (np_ - 1))) / stages
+def base_config(args, world):
+    """The workload description, identical in both arms (`--impl ours` / `--impl reference`); arm-specific facts go
+    into `details` (ours) or `cpu_baseline.sample` (reference)."""
+    return {"workload": WORKLOAD, "systems_per_gpu": args.draws * (args.omegas + 1), "draws": args.draws,
+            "omega_variants": args.omegas, "n_planets": 2, "n_days": N_DAYS, "n_outputs": N_OUTPUTS,
+            "parallelism": "shard-by-system x%d" % world,
+            "l2": "256 MiB device fill between steps, outside the per-step event pairs"}
 
 
-F_OUT = 100  # per planet per output sample (Jacobi a, e, inc + crossing test)
-F_OMEGA = 75  # + argument of pericentre (eccentricity vector 20, node 7, acos 35, quadrant and sum 13), NBT_F_MEAN_OMEGA
+def f_step(np_):
+    """Algorithmic FLOPs per system-step (one Kepler-drift + kick stage of one system), SURVEY.md §8(d):
+    272 Np + 12.5 Np (Np + 1) - 40 = 579 / 926 / 1298 for Np = 2 / 3 / 4 (FMA = 2, div / sqrt = 1)."""
+    return 272 * np_ + 12.5 * np_ * (np_ + 1) - 40
 
-# (drift stages, force evaluations, displaced-position set-ups) per composition step of each NBT_SCHEME_*
-SCHEME_COST = {0: (1, 1, 0), 1: (3, 3, 0), 2: (4, 4, 0), 3: (4, 4, 0), 4: (2, 3, 1), 5: (3, 4, 1)}
+
+F_OUT = 100  # per planet per output sample (Jacobi a, e, inc + crossing test), SURVEY.md §8(d)
 
 
-def plan_flops(plan):
-    """Algorithmic FLOPs of the integration stages of one launch of `plan` (sampling not included)."""
-    per, np_, sch = plan.cfg.n_outputs - 1, plan.Np, plan.cfg.scheme
-    if plan.substeps is None:
-        k_main, k_alt = plan.cfg.substeps * plan.B, 0
-    else:
-        k_main, k_alt = int(plan.substeps[plan.substeps > 0].sum()), -int(plan.substeps[plan.substeps < 0].sum())
-    s, f, g = SCHEME_COST[5 if sch == 6 else sch]
-    fl = k_main * per * s * f_step(np_, s, f, g)
-    s, f, g = SCHEME_COST[4]   # NBT_SCHEME_AUTO: negative counts are C4 steps
-    return fl + k_alt * per * s * f_step(np_, s, f, g)
+def survey_flops(plan):
+    """§8(d) FLOPs of one k_integrate launch of `plan`: stages + per-sample work (the latter only when the element
+    means are on: without NBT_F_MEANS a sample is just the crossing test)."""
+    from nbody_ai_b200 import _abi
+    samples = int(plan.n_outputs_sys.sum()) if plan.n_outputs_sys is not None else plan.B * plan.cfg.n_outputs
+    out = F_OUT * plan.Np * samples if plan.cfg.flags & _abi.F_MEANS else 0
+    return plan.n_steps * f_step(plan.Np) + out
 
 
 class ClockSampler(threading.Thread):
@@ -111,14 +120,15 @@ class ClockSampler(threading.Thread):
 
 
 def ncu_traffic(np_, b):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_integrate launch on this workload, from the
-    committed `ncu --set full` capture (profiles/r1_traffic.json); None if no capture matches."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if t.get("n_planets") == np_ and t.get("systems") == b:
-            return t["dram_bytes_read"] + t["dram_bytes_write"]
-    except Exception:
-        pass
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_integrate launch on this workload, from the committed
+    `ncu --set full` capture (profiles/r2_traffic.json, else r1_traffic.json); None if no capture matches."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if t.get("n_planets") == np_ and t.get("systems") == b:
+                return t["dram_bytes_read"] + t["dram_bytes_write"]
+        except Exception:
+            pass
     return None
 
 
@@ -152,11 +162,46 @@ def env_int(name, default):
         return default
 
 
-def cpu_path(params, n_threads=0):
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on host cores (oracle port).  Plans with numpy only — this arm never loads
+# libnbt.so.
+# ---------------------------------------------------------------------------------------------
+class HostPlan:
+    """What engine.Buffers and oracle.run need of a plan, computed with numpy: CSR capacities of the transit products
+    min(ceil(1.05 Ndays / P) + 3, Noutputs) and of the O-C periodograms (astropy's autofrequency count on a baseline of
+    capacity - 1 epochs) — the layout include/nbt.h documents for nbt_plan_tt / nbt_plan_ls."""
+
+    def __init__(self, params, n_days, n_outputs, flags):
+        from nbody_ai_b200 import _abi
+        self.params = np.ascontiguousarray(params, dtype=np.float64)
+        B, N, _ = self.params.shape
+        self.B, self.N, self.Np = B, N, N - 1
+        self.cfg = _abi.make_config(B, N, n_days, n_outputs, substeps=1, scheme=_abi.SCHEME_SBABC3, flags=flags)
+        self.substeps = self.order = self.n_days_sys = self.n_outputs_sys = self.likelihood = None
+        self.rv_nfreq = 0
+        P = self.params[:, 1:, _abi.P_P]
+        ok = np.isfinite(P) & (P > 0)
+        cap = np.where(ok, np.minimum(np.ceil(1.05 * n_days / np.where(ok, P, 1.0)) + 3.0, float(n_outputs)), 3.0).astype(np.int64)
+        if flags & _abi.F_PLANET1_ONLY:
+            cap[:, 1:] = 1
+        self.tt_offsets = np.concatenate([[0], np.cumsum(cap.ravel())]).astype(np.int64)
+        self.cfg.tt_cap_max = int(cap.max()) if B else 1
+        self.ls_offsets = None
+        if flags & _abi.F_LS_OC:
+            c = cap.ravel().astype(np.float64)
+            df = 1.0 / np.maximum(c - 1.0, 1.0) / self.cfg.ls_samples_per_peak
+            nf = np.where(c >= 3, 1 + np.rint((self.cfg.ls_oc_maxfreq - self.cfg.ls_oc_minfreq) / df), 0).astype(np.int64)
+            self.ls_offsets = np.concatenate([[0], np.cumsum(nf)]).astype(np.int64)
+        self.n_steps = B * (n_outputs - 1)
+
+
+def cpu_path(params, n_days=N_DAYS, n_outputs=N_OUTPUTS, flags=None, n_threads=0):
     """The reference algorithm on host cores: oracle (IAS15 restatement + analyze semantics)."""
     import oracle
     from nbody_ai_b200 import _abi, engine
-    plan = engine.Plan(params, N_DAYS, N_OUTPUTS, substeps=1, flags=_abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC)
+    if flags is None:
+        flags = _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC
+    plan = HostPlan(params, n_days, n_outputs, flags)
     buf = engine.Buffers(plan)
     nt = n_threads or oracle.max_threads()
     t0 = time.perf_counter()
@@ -184,7 +229,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "ttv_sims_per_sec", "value": sims, "unit": "sims/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_systems_per_step": per_step, "n_days": N_DAYS, "n_outputs": N_OUTPUTS},
+        "config": base_config(args, world),
         "system_steps_per_s": sims * (N_OUTPUTS - 1),
         "cpu_baseline": {"value": sims, "unit": "sims/s", "cores": nt, "kind": "port", "cpu_model": cpu_model(),
                          "host_cpus": os.cpu_count(),
@@ -197,7 +242,7 @@ def run_reference(args, rank, world):
 
 def bind_to_gpu_numa_node(gpu_index):
     """One process per GPU: run on the CPUs next to this rank's GPU, so that the pinned staging buffers
-    (first touch) and the 340 MB of D2H per step stay on the GPU's own socket.  Returns the CPU count or None."""
+    (first touch) and the D2H traffic of every step stay on the GPU's own socket.  Returns the CPU count or None."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -205,6 +250,33 @@ def bind_to_gpu_numa_node(gpu_index):
         return len(os.sched_getaffinity(0))
     except Exception:
         return None
+
+
+class DeviceTimer:
+    """K device-timed passes of one plan (CUDA events on torch's current stream = the launch stream, L2 flushed
+    between passes outside the event pairs)."""
+
+    def __init__(self, torch, dev, flush, barrier):
+        self.torch, self.dev, self.flush, self.barrier = torch, dev, flush, barrier
+
+    def __call__(self, plan, dbuf, steps, warmup):
+        from nbody_ai_b200 import engine
+        torch = self.torch
+        for _ in range(warmup):
+            engine.run_device(plan, dbuf)
+        torch.cuda.synchronize(self.dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        stage_ms = np.zeros(4)
+        self.barrier()
+        for k in range(steps):
+            self.flush.fill_(k & 0xFF)                  # L2 flush, outside the event pair
+            ev[k][0].record()
+            engine.run_device(plan, dbuf, timing=True)
+            ev[k][1].record()
+            ev[k][1].synchronize()
+            stage_ms += engine.stage_timing()
+        self.barrier()
+        return float(sum(a.elapsed_time(b) for a, b in ev)), stage_ms
 
 
 def run_ours(args, rank, world, local_rank):
@@ -233,9 +305,7 @@ def run_ours(args, rank, world, local_rank):
     B, Np = params.shape[0], params.shape[1] - 1
     flags = _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC
     plan = engine.Plan(params, N_DAYS, N_OUTPUTS, flags=flags, device=local_rank)
-    plan.pin()
     dbuf = engine.DeviceBuffers(plan)
-    hbuf = engine.Buffers(plan, pinned=True)
 
     # FP64 roofline denominator, measured on this GPU right now
     tf, ms = C.c_double(0), C.c_double(0)
@@ -251,6 +321,16 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def reduce_max_sum(mx, sm):
+        """max over ranks of `mx`, sum over ranks of `sm` (lists of floats)."""
+        a = torch.tensor(mx, dtype=torch.float64, device=dev)
+        b = torch.tensor(sm, dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        return [float(x) for x in a.cpu()], [float(x) for x in b.cpu()]
+
+    timer = DeviceTimer(torch, dev, flush, barrier)
     for _ in range(args.warmup):
         engine.run_device(plan, dbuf)
     torch.cuda.synchronize(dev)
@@ -260,40 +340,45 @@ def run_ours(args, rank, world, local_rank):
     time.sleep(0.3)
 
     # ---- timed region: K steps, device-resident ------------------------------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage_ms = np.zeros(4)
-    barrier()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)                       # L2 flush, outside the event pair
-        ev[k][0].record()
-        engine.run_device(plan, dbuf, timing=True)
-        ev[k][1].record()
-        ev[k][1].synchronize()
-        stage_ms += engine.stage_timing()
-    barrier()
-    dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    dev_ms, stage_ms = timer(plan, dbuf, args.steps, 0)
     clocks = sampler.finish()
 
-    # ---- end to end through the host-pointer C ABI ---------------------------------------
-    for _ in range(min(args.warmup, 2)):
-        engine.run(plan, hbuf)
+    # ---- end to end through the host-pointer C ABI: plan + H2D + kernels + D2H every step --------------------
+    # N = 1: a fresh parameter block every step (other seeds of the same workload), so nothing of a plan can be reused;
+    # N > 1: the rank's shard is planned anew every step
+    pool = engine.BufferPool(pinned=True)
+    n_sets = 1 if world > 1 else min(max(args.steps, 1), 4)
+    param_sets = [params] + [workloads.c2_params(args.draws, args.omegas, seed=100 + i) for i in range(1, n_sets)]
+
+    def e2e_step(k):
+        p = engine.Plan(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=flags, device=local_rank, pool=pool)
+        return p, engine.run(p, pool.buffers_for(p))    # H2D + kernels + D2H + stream sync inside
+
+    for k in range(max(min(args.warmup, 2), n_sets)):        # every set once: the pool reaches its final size
+        e2e_step(k)
     barrier()
+    plan_s = 0.0
     t0 = time.perf_counter()
     for k in range(args.steps):
-        engine.run(plan, hbuf)                      # H2D + kernels + D2H + stream sync inside
+        tp = time.perf_counter()
+        p = engine.Plan(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=flags, device=local_rank, pool=pool)
+        plan_s += time.perf_counter() - tp
+        hbuf = engine.run(p, pool.buffers_for(p))
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    h2d = sum(a.nbytes for a in (plan.params, plan.substeps, plan.order, plan.tt_offsets, plan.ls_offsets) if a is not None)
+    h2d = sum(a.nbytes for a in (p.params, p.substeps, p.order, p.tt_offsets, p.ls_offsets) if a is not None)
     d2h = sum(getattr(hbuf, n).nbytes for n in ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e",
                                                "mean_inc", "mean_omega", "status", "ls_oc_power", "ls_oc_nfreq"))
 
     # sanity: the timed device path and the host path produced the same transits
     chk = dbuf.to_host()
-    assert np.array_equal(chk.n_tt, hbuf.n_tt), "device-resident and host-pointer paths disagree"
-    n_tt_total = int(np.minimum(hbuf.n_tt, np.diff(plan.tt_offsets)).sum())
+    ref_run = engine.run(plan)
+    assert np.array_equal(chk.n_tt, ref_run.n_tt), "device-resident and host-pointer paths disagree"
+    n_tt_total = int(np.minimum(ref_run.n_tt, np.diff(plan.tt_offsets)).sum())
+    del chk, ref_run
 
-    t = torch.tensor([dev_ms, e2e_ms, stage_ms[0]], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(B), float(plan.n_steps), float(n_tt_total)], dtype=torch.float64, device=dev)
+    (dev_ms, e2e_ms, integ_ms), (sims_all, steps_all, ntt_all) = reduce_max_sum(
+        [dev_ms, e2e_ms, stage_ms[0]], [float(B), float(plan.n_steps), float(n_tt_total)])
     # per-rank view (diagnosis of the max-over-ranks figure): step time, e2e time, SM clock, power-cap flag
     mine = torch.tensor([dev_ms / args.steps, e2e_ms / args.steps, clocks["sm_mhz"] or 0.0,
                          1.0 if "sw_power_cap" in clocks["reasons"] else 0.0], dtype=torch.float64, device=dev)
@@ -301,27 +386,83 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         per_rank = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(per_rank, mine)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     per_rank = [[round(float(x), 3) for x in r.cpu()] for r in per_rank]
-    dev_ms, e2e_ms, integ_ms = (float(x) for x in t.cpu())
-    sims_all, steps_all, ntt_all = (float(x) for x in tot.cpu())
+    main_flops, main_launch_ms = survey_flops(plan), stage_ms[0] / args.steps
+    substeps_hist = np.bincount(np.abs(plan.substeps)).tolist()
+    c4_systems = int((plan.substeps < 0).sum())
+    del dbuf, pool, param_sets
+    torch.cuda.empty_cache()
+
+    # ---- north-star block -------------------------------------------------------------------------------------
+    north = {}
+    launches_extra = 0
+    if not args.no_north_star:
+        def block(name, par, n_days, n_outputs, fl, note, scaling, steps=2, warmup=1, cpu_sample=0):
+            nonlocal launches_extra
+            t_plan = time.perf_counter()
+            pl = engine.Plan(par, n_days, n_outputs, flags=fl, device=local_rank)
+            t_plan = time.perf_counter() - t_plan
+            db = engine.DeviceBuffers(pl)
+            ms_tot, st = timer(pl, db, steps, warmup)
+            status = db.status.cpu().numpy()
+            bad = int(((status & (_abi.S_NONFINITE | _abi.S_UNBOUND | _abi.S_KEPLER | _abi.S_TT_OVERFLOW)) != 0).sum())
+            del db
+            torch.cuda.empty_cache()
+            (ms_tot, integ), (nsys, nsteps, flops, nbad) = reduce_max_sum(
+                [ms_tot, st[0]], [float(pl.B), float(pl.n_steps), float(survey_flops(pl)), float(bad)])
+            launches_extra += (2 + (1 if fl & _abi.F_LS_OC else 0)) * steps
+            ach = survey_flops(pl) / (st[0] / steps * 1e-3) * 1e-12       # this rank's kernel against this rank's peak
+            entry = {
+                "workload": note, "systems": nsys, "n_planets": pl.Np, "n_days": n_days, "n_outputs": n_outputs, "scaling": scaling,
+                "passes_timed": steps, "ms_per_pass": ms_tot / steps, "k_integrate_ms_per_pass_max_rank": integ / steps,
+                "system_steps_per_pass": nsteps, "system_steps_per_s": nsteps * steps / (ms_tot * 1e-3),
+                "sims_per_s": nsys * steps / (ms_tot * 1e-3),
+                "roofline": {"bound": "fp64", "kernel": "k_integrate<%d>" % pl.Np, "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": ach / fp64_peak, "frac_of_nominal_37.2": ach / FP64_NOMINAL, "flops_per_launch_rank0": survey_flops(pl),
+                             "flops_per_system_step": f_step(pl.Np), "launch_ms_rank0": st[0] / steps},
+                "systems_broken_or_overflowing": nbad, "host_plan_s_rank0": t_plan,
+            }
+            if cpu_sample and rank == 0 and world == 1 and not args.no_cpu:
+                dt, nt, _ = cpu_path(par[:cpu_sample], n_days, n_outputs, fl)
+                entry["cpu_port"] = {"sims_per_s": cpu_sample / dt, "system_steps_per_s": cpu_sample * (n_outputs - 1) / dt, "cores": nt,
+                                     "sample": "first %d systems, oracle on %d host threads, %.1f s" % (cpu_sample, nt, dt)}
+            north[name] = entry
+
+        full = _abi.F_MEANS | _abi.F_MEAN_OMEGA
+        block("three_planet_readme", workloads.c1_params(args.np3_systems), N_DAYS, N_OUTPUTS, full,
+              "README.md:23-38 system (1.12 Msun + 3 planets, P = 3.29 / 7 / 12 d) x %d per GPU, tt + ephemeris + O-C + maxavg + element means" % args.np3_systems,
+              "weak", cpu_sample=64)
+        block("three_planet_random", workloads.random_systems(args.np3_random, 3, seed=300 + rank), N_DAYS, N_OUTPUTS, full | _abi.F_LS_OC,
+              "random 3-planet systems (randomize() priors extended outward), %d per GPU, all analyze products incl. O-C periodogram" % args.np3_random,
+              "weak", cpu_sample=256)
+        if args.c5_systems > 0:
+            lo, hi = engine.shard_range(args.c5_systems, rank, world)
+            # every rank draws the whole-job stream in 125 000-system chunks (seeded per chunk) and keeps its own range
+            chunk = 125000
+            parts = []
+            for c0 in range(0, args.c5_systems, chunk):
+                c1 = min(c0 + chunk, args.c5_systems)
+                if c1 <= lo or c0 >= hi:
+                    continue
+                blk = workloads.c5_params(c1 - c0, seed=2 + c0 // chunk)
+                parts.append(blk[max(lo - c0, 0):min(hi, c1) - c0])
+            block("c5_full", np.concatenate(parts), 1095.0, 26280, _abi.F_MEANS,
+                  "BASELINE config 5: %d random 4-planet systems in total, 1095 d @ 1 h, tt + ephemeris + O-C + maxavg + mean a/e/inc, sharded by system over %d rank(s)" % (args.c5_systems, world),
+                  "strong", steps=args.c5_passes, warmup=0, cpu_sample=128)
 
     if rank == 0:
         sims_per_s = sims_all * args.steps / (dev_ms * 1e-3)
         steps_per_s = steps_all * args.steps / (dev_ms * 1e-3)
-        # roofline of the dominant kernel (k_integrate), per launch on this rank
-        flops = plan_flops(plan) + B * N_OUTPUTS * (F_OUT + F_OMEGA) * Np   # the bench sets NBT_F_MEAN_OMEGA
-        integ_launch_ms = stage_ms[0] / args.steps
-        achieved = flops / (integ_launch_ms * 1e-3) * 1e-12
+        achieved = main_flops / (main_launch_ms * 1e-3) * 1e-12
         line = {
             "metric": "ttv_sims_per_sec", "value": sims_per_s, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "systems_per_gpu": B, "draws": args.draws, "omega_variants": args.omegas,
-                       "n_planets": Np, "n_days": N_DAYS, "n_outputs": N_OUTPUTS, "scheme": "auto: sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks); c4 (2-stage force-gradient) where P_min >= 250 output steps",
-                       "substeps_hist": np.bincount(np.abs(plan.substeps)).tolist(), "c4_systems": int((plan.substeps < 0).sum()), "parallelism": "shard-by-system x%d%s" % (world, ", cost-balanced (engine.shard_balanced)" if world > 1 else ""), "cpu_affinity": affinity,
-                       "l2": "256 MiB device fill between steps, outside the per-step event pairs"},
+            "config": base_config(args, world),
+            "details": {"scheme": "auto: sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks); c4 (2-stage force-gradient) where P_min >= 250 output steps",
+                        "substeps_hist": substeps_hist, "c4_systems": c4_systems,
+                        "shards": "cost-balanced (engine.shard_balanced) of one global batch" if world > 1 else "one batch", "cpu_affinity": affinity,
+                        "e2e": "every step: engine.Plan (nbt_plan host planner) on %s + nbt_run with pinned host buffers" % ("a fresh parameter block (%d seeds in rotation)" % n_sets if n_sets > 1 else "the rank's shard")},
             "system_steps_per_s": steps_per_s,
             "system_steps_per_step": steps_all,
             "transits_per_step": ntt_all,
@@ -329,15 +470,18 @@ def run_ours(args, rank, world, local_rank):
                                   "k_ls_oc": stage_ms[2] / args.steps},
             "roofline": {"bound": "fp64", "kernel": "k_integrate<%d>" % Np, "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None,
+                         "frac_of_nominal_37.2": achieved / FP64_NOMINAL,
+                         "model": "SURVEY 8(d): system-steps x (272 Np + 12.5 Np (Np+1) - 40) + output samples x 100 Np",
                          "peak_source": "nbt_fp64_peak DFMA-chain kernel measured in this run (nominal 37.2 at 1965 MHz)",
                          "peak_three_register_operands": fp64_peak_3reg,
-                         "flops_per_launch": flops, "launch_ms": integ_launch_ms, "traffic": ncu_traffic(Np, B),
-                         "hbm": hbm_side(ncu_traffic(Np, B), integ_launch_ms)},
+                         "flops_per_launch": main_flops, "launch_ms": main_launch_ms, "traffic": ncu_traffic(Np, B),
+                         "hbm": hbm_side(ncu_traffic(Np, B), main_launch_ms)},
             "e2e": {"value": sims_all * args.steps / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": 3 * args.steps,   # k_integrate, k_fit, k_ls_oc
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps, "host_plan_ms_per_step_rank0": 1e3 * plan_s / args.steps},
+            "gpu_launches": 3 * args.steps + launches_extra,   # k_integrate, k_fit, k_ls_oc per timed device step (+ the north-star passes)
             "clocks": clocks,
             "ranks": {"columns": ["ms_per_step", "e2e_ms_per_step", "sm_mhz", "sw_power_cap"], "rows": per_rank},
+            "north_star": north,
         }
         if world == 1 and not args.no_cpu:
             n_s = min(args.cpu_sample, B)
@@ -382,11 +526,11 @@ def emit(line):
         print(text, flush=True)
 
 
-def ensure_built():
+def ensure_built(need_cuda_lib=True):
     """The in-tree libraries normally travel with the repo snapshot; compile them if they did not
     (local rank 0 builds, the other ranks of a torchrun job wait for the file)."""
     from nbody_ai_b200 import _abi
-    if os.path.exists(_abi.lib_path()):
+    if not need_cuda_lib or os.path.exists(_abi.lib_path()):
         return
     if env_int("LOCAL_RANK", 0) == 0:
         import __graft_entry__
@@ -410,10 +554,15 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--ref-sample", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true")
+    ap.add_argument("--np3-systems", type=int, default=227328, help="README 3-planet replicas per GPU (148 SMs x 1536)")
+    ap.add_argument("--np3-random", type=int, default=75776, help="random 3-planet systems per GPU (148 x 512)")
+    ap.add_argument("--c5-systems", type=int, default=1000000, help="C5 systems in total (sharded over the ranks); 0 = skip")
+    ap.add_argument("--c5-passes", type=int, default=2)
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     with StdoutToStderr() as OUT:
-        ensure_built()
+        ensure_built(need_cuda_lib=args.impl != "reference")
         if args.impl == "reference":
             run_reference(args, rank, world)
         else:

@@ -231,6 +231,20 @@ int nbt_plan_substeps(const nbt_config* cfg, const nbt_inputs* in, int32_t* subs
 /* Number of system-steps (kick+drift stages) nbt_run will execute for this plan (in->substeps, grids). */
 int64_t nbt_count_steps(const nbt_config* cfg, const nbt_inputs* in);
 
+/* The whole plan in one call, on n_threads host threads (0 = all): what nbt_plan_substeps + nbt_plan_order +
+ * nbt_plan_lanes + nbt_plan_tt + nbt_plan_ls + nbt_count_steps produce, bit for bit, in one pass over params.  Callers
+ * whose parameters change from call to call (samplers: nbody/nested.py:85, ttv_fit.py:47; the training-set loop,
+ * simulations/generate_simulations.py:41-110) plan every call anew, so planning time is end-to-end time.
+ *   sub-steps: cfg->substeps > 0 = uniform; else in->substeps if set; else computed into substeps_out[B].
+ *   sort_mode 1: order[B] = nbt_plan_order's launch order (when B > 32 or C4-marked systems exist); 0: index order,
+ *   except that C4-marked systems (NBT_SCHEME_AUTO) still move to the end.  order may be NULL with sort_mode 0 only if
+ *   the caller accepts index order (then marked systems run SBABC3 steps).
+ *   ls_offsets: NULL unless NBT_F_LS_OC.
+ *   summary[5] = { system-steps of the plan, largest CSR capacity (cfg.tt_cap_max), cfg.alt_systems,
+ *                  1 if order[] is the identity (the caller may pass inputs.order = NULL), cfg.lanes_systems }. */
+int nbt_plan(const nbt_config* cfg, const nbt_inputs* in, int32_t sort_mode, int32_t* substeps_out, int32_t* order,
+             int64_t* tt_offsets, int64_t* ls_offsets, int64_t* summary, int32_t n_threads);
+
 /* 1 if the system described by one parameter row block [n_bodies][NBT_NPAR] is outside the envelope the sub-step
  * rule was calibrated on (what nbt_run reports as NBT_S_UNCALIBRATED), else 0. */
 int nbt_uncalibrated(const double* params_one, int n_bodies);

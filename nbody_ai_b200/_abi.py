@@ -149,6 +149,7 @@ def load():
     lib.nbt_count_steps.restype = C.c_int64
     lib.nbt_count_steps.argtypes = [C.POINTER(nbt_config), C.POINTER(nbt_inputs)]
     lib.nbt_uncalibrated.argtypes = [_dp, C.c_int]
+    lib.nbt_plan.argtypes = [C.POINTER(nbt_config), C.POINTER(nbt_inputs), C.c_int32, _ip, _ip, _lp, _lp, _lp, C.c_int32]
     lib.nbt_run.argtypes = [C.POINTER(nbt_config), C.POINTER(nbt_inputs), C.POINTER(nbt_outputs), C.c_void_p]
     lib.nbt_lomb_scargle.argtypes = [_dp, _dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int64,
                                      _dp, C.c_int, C.c_int, C.c_void_p]

@@ -10,6 +10,7 @@
 //                     (nbody/simulation.py:213 -> nbody/tools.py:97-104)           FP64-pipe bound
 //   k_transpose / k_rv_max / k_ls_series   RV products (nbody/simulation.py:186-188)
 //   k_chi2            nested-sampling log-likelihood (nbody/nested.py:85-95)
+//   k_integrate_whfast the reference's integrator='whfast' preset (WHFast, corrector 5; nbody/simulation.py:39-42)
 //   k_integrate_ias15 the reference's own integrator (REBOUND's default IAS15) for the few systems no fixed step
 //                     resolves (engine.run_verified)                                latency-bound, rare
 //   k_ls_peaks        on-device reduction of the O-C periodograms to their highest peaks
@@ -26,11 +27,13 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nbt_core.cuh"
 #include "nbt_ias15.cuh"
 #include "nbt_lanes.cuh"
+#include "nbt_whfast.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing
@@ -1016,9 +1019,31 @@ static const nbt_ias15_tables& ias15_tables() {
     return T;
 }
 
+// NBT_SCHEME_WHFAST: the reference's integrator='whfast' preset (nbody/simulation.py:39-42), one system per thread
+template <int NP>
+__global__ void __launch_bounds__(32) k_integrate_whfast(const nbt_run_args A) {
+    const int sys = (int)(blockIdx.x * 32u + threadIdx.x);
+    if (sys >= A.B) return;
+    nbt_simulate_system_whfast<NP>(A, sys);
+}
+
 static cudaError_t launch_special_np(int np, int scheme, const nbt_run_args& A, cudaStream_t st) {
-    if (scheme != NBT_SCHEME_IAS15) return cudaErrorNotSupported;
     const int grid = (A.B + 31) / 32;
+    if (scheme == NBT_SCHEME_WHFAST) {
+        switch (np) {
+        case 1: k_integrate_whfast<1><<<grid, 32, 0, st>>>(A); break;
+        case 2: k_integrate_whfast<2><<<grid, 32, 0, st>>>(A); break;
+        case 3: k_integrate_whfast<3><<<grid, 32, 0, st>>>(A); break;
+        case 4: k_integrate_whfast<4><<<grid, 32, 0, st>>>(A); break;
+        case 5: k_integrate_whfast<5><<<grid, 32, 0, st>>>(A); break;
+        case 6: k_integrate_whfast<6><<<grid, 32, 0, st>>>(A); break;
+        case 7: k_integrate_whfast<7><<<grid, 32, 0, st>>>(A); break;
+        case 8: k_integrate_whfast<8><<<grid, 32, 0, st>>>(A); break;
+        default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
+    if (scheme != NBT_SCHEME_IAS15) return cudaErrorNotSupported;
     const nbt_ias15_tables& T = ias15_tables();
     switch (np) {
     case 1: k_integrate_ias15<1><<<grid, 32, 0, st>>>(A, T); break;
@@ -1486,6 +1511,174 @@ int64_t nbt_count_steps(const nbt_config* cfg, const nbt_inputs* in) {
     return tot;
 }
 
+/* nbt_plan: everything a caller plans before nbt_run, in one pass over the parameter block on n_threads host threads
+ * (the separate nbt_plan_* helpers above, same results bit for bit — tests/test_host_logic.py).  A sampler or the
+ * training-set generator plans every call anew (parameters change from call to call), so this sits on the end-to-end
+ * path: 70 000 two-planet systems take ~1.5 ms here against ~10 ms through the five helpers. */
+}  // extern "C" (a template cannot have C linkage)
+template <class F>
+static void plan_parallel(int B, int n_threads, F&& body) {
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min(T, std::min(32, (B + 4095) / 4096)));
+    if (T == 1) { body(0, 0, B); return; }
+    std::vector<std::thread> th;
+    th.reserve(T);
+    for (int t = 0; t < T; t++) {
+        const int lo = (int)((int64_t)B * t / T), hi = (int)((int64_t)B * (t + 1) / T);
+        th.emplace_back([&body, t, lo, hi] { body(t, lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+extern "C" {
+
+int nbt_plan(const nbt_config* cfg, const nbt_inputs* in, int32_t sort_mode, int32_t* substeps_out, int32_t* order,
+             int64_t* tt_offsets, int64_t* ls_offsets, int64_t* summary, int32_t n_threads) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!in || !in->params || !tt_offsets || !summary) return nbt_fail(-10, "nbt_plan: NULL argument");
+    if ((rc = check_grids(cfg, in)) != 0) return rc;
+    const int B = cfg->n_systems, N = cfg->n_bodies, Np = N - 1;
+    const double* params = in->params;
+    const bool uniform = cfg->substeps > 0;
+    const int32_t* sub_in = uniform ? nullptr : in->substeps;
+    if (!uniform && !sub_in && !substeps_out) return nbt_fail(-10, "nbt_plan: substeps_out is required when neither cfg.substeps nor inputs.substeps is set");
+    if (sort_mode && !order) return nbt_fail(-10, "nbt_plan: order is required when sort_mode != 0");
+    for (int b = 0; b < B; b++) {
+        if (!(grid_days(cfg, in, b) > 0.0) || grid_outputs(cfg, in, b) < 2)
+            return nbt_fail(-14, "system %d: n_days must be > 0 and n_outputs >= 2", b);
+        if (!in->n_days_sys) break;
+    }
+    // pass 1 (parallel): sub-step counts, Hill flags, CSR capacities (stored as counts at [i + 1]), step totals
+    if (!uniform && !sub_in) {
+        nbt_inputs tmp = *in;
+        tmp.substeps = nullptr;
+        std::vector<int> rcs(64, 0);
+        plan_parallel(B, n_threads, [&](int t, int lo, int hi) {
+            nbt_config c = *cfg;
+            nbt_inputs i2 = tmp;
+            c.n_systems = hi - lo;
+            i2.params = params + (size_t)lo * N * NBT_NPAR;
+            if (tmp.n_days_sys) { i2.n_days_sys = tmp.n_days_sys + lo; i2.n_outputs_sys = tmp.n_outputs_sys + lo; }
+            rcs[t] = nbt_plan_substeps(&c, &i2, substeps_out + lo);
+        });
+        for (int r : rcs) if (r) return r;
+        sub_in = substeps_out;
+    }
+    const bool want_ls = ls_offsets != nullptr;
+    const bool need_hill = order != nullptr && sort_mode == 1;
+    std::vector<uint8_t> unstable(need_hill ? B : 0);
+    const int64_t S = scheme_stages(cfg->scheme);
+    const int64_t S_alt = cfg->scheme == NBT_SCHEME_AUTO ? scheme_stages(NBT_SCHEME_C4) : S;
+    std::vector<int64_t> steps_part(64, 0), nalt_part(64, 0), capmax_part(64, 1);
+    tt_offsets[0] = 0;
+    if (want_ls) ls_offsets[0] = 0;
+    plan_parallel(B, n_threads, [&](int t, int lo, int hi) {
+        int64_t steps = 0, nalt = 0, capmax = 1;
+        for (int b = lo; b < hi; b++) {
+            const double* par = params + (size_t)b * N * NBT_NPAR;
+            const double nd = grid_days(cfg, in, b);
+            const int no = grid_outputs(cfg, in, b);
+            for (int j = 0; j < Np; j++) {
+                const double P = par[(j + 1) * NBT_NPAR + NBT_P_P];
+                int64_t cap = 3;
+                if (P > 0.0 && std::isfinite(P)) {
+                    double c = ceil(1.05 * nd / P) + 3.0;
+                    if (c > (double)no) c = (double)no;
+                    cap = (int64_t)c;
+                }
+                if ((cfg->flags & NBT_F_PLANET1_ONLY) && j > 0) cap = 1;
+                tt_offsets[(size_t)b * Np + j + 1] = cap;
+                capmax = std::max(capmax, cap);
+                if (want_ls)
+                    ls_offsets[(size_t)b * Np + j + 1] =
+                        (cap >= 3) ? nbt_ls_nfreq((double)(cap - 1), cfg->ls_oc_minfreq, cfg->ls_oc_maxfreq, cfg->ls_samples_per_peak) : 0;
+            }
+            const int64_t k = sub_in ? sub_in[b] : std::max(cfg->substeps, 1);
+            steps += ((int64_t)no - 1) * (k < 0 ? -k * S_alt : k * S);
+            nalt += k < 0 ? 1 : 0;
+            if (need_hill) unstable[b] = hill_separation(par, N) < 4.0 ? 1 : 0;
+        }
+        steps_part[t] = steps; nalt_part[t] = nalt; capmax_part[t] = capmax;
+    });
+    int64_t n_steps = 0, nalt = 0, capmax = 1;
+    for (int t = 0; t < 64; t++) { n_steps += steps_part[t]; nalt += nalt_part[t]; capmax = std::max(capmax, capmax_part[t]); }
+    if (capmax > INT32_MAX) return nbt_fail(-11, "tt capacity overflow");
+    // pass 2: capacities -> offsets
+    const int64_t nsp = (int64_t)B * Np;
+    for (int64_t i = 0; i < nsp; i++) tt_offsets[i + 1] += tt_offsets[i];
+    if (want_ls)
+        for (int64_t i = 0; i < nsp; i++) ls_offsets[i + 1] += ls_offsets[i];
+    // pass 3: launch order — the stable sort of nbt_plan_order as a counting sort over (sub-steps descending, unstable first)
+    const bool marked = cfg->scheme == NBT_SCHEME_AUTO && nalt > 0;
+    const bool adaptive = cfg->scheme == NBT_SCHEME_IAS15 || cfg->scheme == NBT_SCHEME_WHFAST;
+    bool identity = true;
+    if (order) {
+        if (sort_mode == 1 && (B > 32 || marked) && !adaptive) {
+            int kmin = INT32_MAX, kmax = INT32_MIN;
+            for (int b = 0; b < B; b++) { const int k = sub_in ? sub_in[b] : 1; kmin = std::min(kmin, k); kmax = std::max(kmax, k); }
+            if (B == 0) { kmin = kmax = 1; }
+            const int64_t nb = ((int64_t)kmax - kmin + 1) * 2;
+            const int32_t* nos = in->n_outputs_sys;
+            if (nb <= (1 << 22)) {
+                std::vector<int32_t> start((size_t)nb + 1, 0);
+                auto bucket = [&](int b) { const int k = sub_in ? sub_in[b] : 1; return (size_t)(kmax - k) * 2 + (1 - unstable[b]); };
+                for (int b = 0; b < B; b++) start[bucket(b) + 1]++;
+                for (int64_t i = 0; i < nb; i++) start[i + 1] += start[i];
+                std::vector<int32_t> pos(start.begin(), start.end() - 1);
+                for (int b = 0; b < B; b++) order[pos[bucket(b)]++] = b;
+                if (nos)
+                    for (int64_t i = 0; i < nb; i++)
+                        if (start[i + 1] - start[i] > 1)
+                            std::stable_sort(order + start[i], order + start[i + 1], [&](int32_t a, int32_t c) { return nos[a] > nos[c]; });
+            } else {   // pathological range of counts: the comparison sort
+                std::iota(order, order + B, 0);
+                std::stable_sort(order, order + B, [&](int32_t a, int32_t c) {
+                    const int ka = sub_in ? sub_in[a] : 1, kc = sub_in ? sub_in[c] : 1;
+                    if (ka != kc) return ka > kc;
+                    if (unstable[a] != unstable[c]) return unstable[a] > unstable[c];
+                    if (nos && nos[a] != nos[c]) return nos[a] > nos[c];
+                    return false;
+                });
+            }
+            if (sub_in && !nos) {   // spread the unstable systems of the multi-step groups over the group's warps (see nbt_plan_order)
+                std::vector<int32_t> tmp;
+                for (int g0 = 0; g0 < B;) {
+                    const int k = sub_in[order[g0]];
+                    int g1 = g0;
+                    while (g1 < B && sub_in[order[g1]] == k) g1++;
+                    int u = 0;
+                    while (g0 + u < g1 && unstable[order[g0 + u]]) u++;
+                    const int n = g1 - g0, s = n - u;
+                    if (k >= 2 && u > 0 && s > 0) {
+                        tmp.assign(order + g0, order + g1);
+                        int iu = 0, is = 0;
+                        for (int p = 0; p < n; p++) {
+                            const bool take_u = (long long)(p + 1) * u / n > (long long)p * u / n;
+                            order[g0 + p] = take_u ? tmp[iu++] : tmp[u + is++];
+                        }
+                    }
+                    g0 = g1;
+                }
+            }
+        } else if (marked) {   // unsorted: the C4 systems still go last (scheme uniform per block)
+            int w = 0;
+            for (int b = 0; b < B; b++) if (sub_in[b] >= 0) order[w++] = b;
+            for (int b = 0; b < B; b++) if (sub_in[b] < 0) order[w++] = b;
+        } else {
+            std::iota(order, order + B, 0);
+        }
+        for (int b = 0; b < B && identity; b++) identity = order[b] == b;
+    }
+    nbt_config c2 = *cfg;
+    const int lanes = nbt_plan_lanes(&c2, in);
+    summary[0] = n_steps;
+    summary[1] = capmax;
+    summary[2] = cfg->scheme == NBT_SCHEME_AUTO ? nalt : 0;
+    summary[3] = identity ? 1 : 0;
+    summary[4] = lanes;
+    return 0;
+}
+
 int nbt_uncalibrated(const double* params_one, int n_bodies) {
     if (!params_one || n_bodies < 2 || n_bodies > NBT_MAX_BODIES) return 0;
     return ::nbt_uncalibrated_impl(params_one, n_bodies) ? 1 : 0;
@@ -1520,7 +1713,6 @@ static int run_impl(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         return nbt_fail(-16, "nbt_run: NBT_F_LS_PEAKS needs NBT_F_LS_OC, inputs.ls_offsets and outputs.ls_oc_peaks");
     if ((cfg->flags & NBT_F_LS_PEAKS) && (cfg->flags & NBT_F_DEVICE_PTRS) && (!out->ls_oc_power || !out->ls_oc_nfreq))
         return nbt_fail(-16, "nbt_run: with device pointers NBT_F_LS_PEAKS needs ls_oc_power and ls_oc_nfreq as scratch");
-    if (!scan && cfg->scheme == NBT_SCHEME_WHFAST) return nbt_fail(-7, "NBT_SCHEME_WHFAST is not available in this build");
     if ((cfg->flags & NBT_F_MEANS) && (!out->mean_a || !out->mean_e || !out->mean_inc))
         return nbt_fail(-10, "nbt_run: NBT_F_MEANS needs mean_a, mean_e, mean_inc");
     if (!scan && cfg->substeps <= 0 && !in->substeps) return nbt_fail(-12, "nbt_run: cfg.substeps <= 0 needs inputs.substeps");

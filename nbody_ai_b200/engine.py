@@ -73,13 +73,20 @@ class Plan:
     """Configuration + CSR layout of one nbt_run call (host planning through libnbt's helpers).
 
     n_days / n_outputs: scalars (one output grid for the whole batch) or arrays [B] — every system on its own grid
-    np.linspace(0, n_days[b], n_outputs[b]) (simulations/generate_simulations.py:45-50), still one launch."""
+    np.linspace(0, n_days[b], n_outputs[b]) (simulations/generate_simulations.py:45-50), still one launch.
+    pool: a BufferPool whose page-locked storage holds the plan's arrays (params copied in), for callers that plan every
+    call anew — the plan is then valid until the pool serves the next one.  threads: host threads of nbt_plan (0 = all)."""
 
     def __init__(self, params, n_days, n_outputs, substeps=None, scheme=SCHEME_AUTO,
-                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True, lanes=None, likelihood=None):
+                 tt_mode=TT_GRID_LINEAR, flags=F_MEANS, device=0, sort=True, lanes=None, likelihood=None, threads=0, pool=None):
         lib = _abi.load()
         self.params = _as_params(params)
         B, N, _ = self.params.shape
+        new = (lambda name, n, dt: np.zeros(n, dtype=dt)) if pool is None else (lambda name, n, dt: pool._take("plan/" + name, (n,), dt))
+        if pool is not None:
+            pinned = pool._take("plan/params", self.params.shape, np.float64)
+            np.copyto(pinned, self.params)
+            self.params = pinned
         if isinstance(scheme, str):
             scheme = SCHEMES[scheme]
         self.n_days_sys = self.n_outputs_sys = None
@@ -98,50 +105,37 @@ class Plan:
         self.cfg = _abi.make_config(B, N, n_days, n_outputs, substeps=0, scheme=scheme,
                                     tt_mode=tt_mode, flags=flags, device=device)
         self.B, self.N, self.Np = B, N, N - 1
-        # composition steps per output interval
+        # the whole plan in one call of the library's threaded host planner (nbt_plan): composition steps per output
+        # interval; launch order (heavy systems first, equal trip counts within a warp, unstable ones grouped or spread;
+        # NBT_SCHEME_AUTO: the systems marked for C4 steps last — sorted or not, scheme uniform per block); which
+        # systems run one planet per lane; CSR capacities of the transit products and of the O-C periodograms
+        sub_out = None
         if substeps is None:
-            self.substeps = np.zeros(B, dtype=np.int32)
-            _abi.check(lib.nbt_plan_substeps(C.byref(self.cfg), C.byref(self._inputs()), _abi.ptr(self.substeps, C.c_int32)), lib)
+            self.substeps = None
+            sub_out = new("substeps", B, np.int32)
         elif np.isscalar(substeps):
             self.cfg.substeps = int(substeps)
             self.substeps = None
         else:
             self.substeps = np.ascontiguousarray(substeps, dtype=np.int32)
             assert self.substeps.shape == (B,)
-        # launch order: heavy systems first, equal trip counts within a warp, unstable ones grouped
-        # (NBT_SCHEME_AUTO: the systems marked for C4 steps go last — sorted or not, the two schemes are two launches)
-        self.order = None
-        marked = self.cfg.scheme == SCHEME_AUTO and self.substeps is not None and bool((self.substeps < 0).any())
-        if marked and not sort:
-            self.order = np.concatenate([np.flatnonzero(self.substeps >= 0), np.flatnonzero(self.substeps < 0)]).astype(np.int32)
-            self.cfg.alt_systems = int((self.substeps < 0).sum())
-            if np.array_equal(self.order, np.arange(B, dtype=np.int32)):
-                self.order = None
-        if sort and (B > 32 or marked) and scheme not in (_abi.SCHEME_IAS15, _abi.SCHEME_WHFAST):
-            self.order = np.zeros(B, dtype=np.int32)
-            nalt = lib.nbt_plan_order(C.byref(self.cfg), C.byref(self._inputs()), _abi.ptr(self.order, C.c_int32))
-            if nalt < 0:
-                _abi.check(nalt, lib)
-            self.cfg.alt_systems = int(nalt) if self.cfg.scheme == SCHEME_AUTO else 0
-            if np.array_equal(self.order, np.arange(B, dtype=np.int32)):
-                self.order = None
-        # which systems run one planet per lane (long ones / small batches), see nbt_plan_lanes
+        self.order = new("order", B, np.int32)
+        self.tt_offsets = new("tt_offsets", B * self.Np + 1, np.int64)
+        self.ls_offsets = new("ls_offsets", B * self.Np + 1, np.int64) if flags & F_LS_OC else None
+        summary = np.zeros(5, dtype=np.int64)
+        _abi.check(lib.nbt_plan(C.byref(self.cfg), C.byref(self._inputs()), 1 if sort else 0, _abi.ptr(sub_out, C.c_int32),
+                                _abi.ptr(self.order, C.c_int32), _abi.ptr(self.tt_offsets, C.c_int64),
+                                _abi.ptr(self.ls_offsets, C.c_int64), _abi.ptr(summary, C.c_int64), int(threads)), lib)
+        if sub_out is not None:
+            self.substeps = sub_out
+        self.n_steps = int(summary[0])
+        self.cfg.tt_cap_max = int(summary[1])
+        self.cfg.alt_systems = int(summary[2])
+        if summary[3]:
+            self.order = None
         if lanes is None:
-            lanes = lib.nbt_plan_lanes(C.byref(self.cfg), C.byref(self._inputs()))
-            if lanes < 0:
-                _abi.check(lanes, lib)
+            lanes = int(summary[4])
         self.cfg.lanes_systems = int(min(max(int(lanes), 0), B))
-        # CSR capacities of the transit products
-        self.tt_offsets = np.zeros(B * self.Np + 1, dtype=np.int64)
-        cap = lib.nbt_plan_tt(C.byref(self.cfg), C.byref(self._inputs()), _abi.ptr(self.tt_offsets, C.c_int64))
-        if cap < 0:
-            _abi.check(cap, lib)
-        self.cfg.tt_cap_max = cap
-        self.ls_offsets = None
-        if flags & F_LS_OC:
-            self.ls_offsets = np.zeros(B * self.Np + 1, dtype=np.int64)
-            _abi.check(lib.nbt_plan_ls(C.byref(self.cfg), _abi.ptr(self.tt_offsets, C.c_int64), _abi.ptr(self.ls_offsets, C.c_int64)), lib)
-        self.n_steps = int(lib.nbt_count_steps(C.byref(self.cfg), C.byref(self._inputs())))
         self.rv_nfreq = 0
         if flags & F_LS_RV:
             step = float(n_days) / (int(n_outputs) - 1)
@@ -313,7 +307,8 @@ class BufferPool:
             m = max(int(n * self.headroom), 1)
             if self.pinned:
                 import torch
-                t = torch.zeros(m, dtype=torch.float64 if dtype == np.float64 else torch.int32, pin_memory=True)
+                t = torch.zeros(m, dtype={"float64": torch.float64, "int32": torch.int32, "int64": torch.int64}[np.dtype(dtype).name],
+                                pin_memory=True)
                 self.store[name + "/t"] = t
                 cur = t.numpy()
             else:

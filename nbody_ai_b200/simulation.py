@@ -45,13 +45,12 @@ class Simulation:
 
 def _integrator_kw(integrator, Ndays, Noutputs):
     """integrator=None: REBOUND's default (IAS15) is matched within the parity tolerances by the planned
-    SBABC3 / C4 compositions (NBT_SCHEME_AUTO).  'whfast' (simulation.py:39-42): Wisdom-Holman leapfrog at REBOUND's
-    default dt = 1e-3 d — far inside the tolerances of either form of REBOUND's WHFast (the 5th-order corrector of
-    :41 moves transit times by < 1e-3 s at this step; NBT_SCHEME_WHFAST, the corrector-exact form, is reserved in the
-    ABI but not built).  'tes' (:34-38) is a high-accuracy scheme: same as None."""
+    SBABC3 / C4 compositions (NBT_SCHEME_AUTO).  'whfast' (simulation.py:39-42): NBT_SCHEME_WHFAST — REBOUND's WHFast
+    at its default dt = 1e-3 d with the 5th-order symplectic corrector and safe_mode = 0 semantics (corrector applied
+    and undone around every sim.integrate(t), last step of an output interval shortened to land on it).  'tes'
+    (:34-38) is a high-accuracy scheme: same as None."""
     if integrator == 'whfast':
-        step = float(Ndays) / (int(Noutputs) - 1)
-        return dict(scheme=_abi.SCHEME_WH2, substeps=max(1, int(np.ceil(step / 1e-3))))
+        return dict(scheme=_abi.SCHEME_WHFAST, substeps=None)
     return dict(scheme=_abi.SCHEME_AUTO, substeps=None)
 
 

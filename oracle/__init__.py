@@ -35,6 +35,8 @@ def lib():
         L.nbo_initial_state.argtypes = [_dp, C.c_int, _dp]
         L.nbo_integrate_series.restype = C.c_long
         L.nbo_integrate_series.argtypes = [_dp, C.c_int, C.c_double, C.c_int, _dp, _dp]
+        L.nbo_integrate_series_whfast.restype = C.c_long
+        L.nbo_integrate_series_whfast.argtypes = [_dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, _dp]
         L.nbo_transit_times.restype = C.c_int
         L.nbo_transit_times.argtypes = [_dp, _dp, _dp, C.c_int, _dp, C.c_int]
         L.nbo_ttv_fit.argtypes = [_dp, C.c_int, _dp, _dp, _dp]
@@ -75,6 +77,16 @@ def integrate_series(params, n_days, n_outputs):
     ns = lib().nbo_integrate_series(_abi.ptr(params), n, float(n_days), int(n_outputs), _abi.ptr(series), _abi.ptr(final))
     times = np.linspace(0.0, n_days, n_outputs)
     return times, series, final, ns
+
+
+def integrate_series_whfast(params, n_days, n_outputs, dt=0.0, corrector=5):
+    """Oracle of generate(..., integrator='whfast') + integrate() (nbody/simulation.py:39-42): WHFast at REBOUND's
+    default dt = 1e-3 d (or `dt`), symplectic corrector of order 5 (0 = off).  Returns (times, series, n_steps)."""
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    n = params.shape[0]
+    series = np.zeros((n_outputs, 3 + 10 * (n - 1)))
+    ns = lib().nbo_integrate_series_whfast(_abi.ptr(params), n, float(n_days), int(n_outputs), float(dt), int(corrector), _abi.ptr(series))
+    return np.linspace(0.0, n_days, n_outputs), series, ns
 
 
 def transit_times(xp, xs, times):

@@ -21,6 +21,7 @@
  * What is restated, in reference order:
  *   nbody/simulation.py:27-52    generate(): units day/AU/Msun, rebound.add(**obj) per body
  *                                (Jacobi primaries, a from P), move_to_com()
+ *   nbody/simulation.py:33-42    integrator='whfast' preset: WHFast, corrector 5, safe_mode 0, dt = 1e-3 d
  *   nbody/simulation.py:131-160  integrate(): default REBOUND integrator (IAS15, adaptive
  *                                Gauss-Radau 15, Rein & Spiegel 2015) landing on
  *                                np.linspace(0, Ndays, Noutputs); star x,y,z; planet x,y,z and
@@ -344,6 +345,234 @@ static void ias15_integrate_to(ias15_t* I, double t_end) {
             }
         }
     }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* integrator='whfast' (nbody/simulation.py:39-42): sim.integrator = "whfast",                  */
+/* ri_whfast.corrector = 5, ri_whfast.safe_mode = 0, dt left at REBOUND's default 1e-3 (days).  */
+/* [3P] REBOUND's WHFast (Rein & Tamayo 2015), restated from the paper and the documented       */
+/* behaviour of the settings: Wisdom-Holman drift-kick-drift in Jacobi coordinates — Kepler     */
+/* drift of Jacobi coordinate i with mu = G (m_0 + ... + m_i), interaction kick from the         */
+/* direct-sum accelerations without the star-planet-1 pair, transformed to Jacobi               */
+/* accelerations, plus G eta_i r'_i / r'_i^3 for i >= 2 —; with safe_mode = 0 consecutive half  */
+/* drifts are merged and the state is only "synchronised" (half drift + inverse corrector) at   */
+/* the end of every sim.integrate(t); the symplectic corrector of order 5 (Wisdom, Holman &     */
+/* Touma 1996: a_k = k sqrt(7/40), b_51 = -beta/6, b_52 = 5 beta/6, beta = 1/(48 sqrt(7/40)))   */
+/* is applied when a synchronised state starts stepping and inverted at synchronisation;        */
+/* exact_finish_time = 1: the step that would overshoot the requested time is replaced by one   */
+/* of the remaining length (after a synchronisation), and dt returns to 1e-3 afterwards.        */
+/* corrector_order = 0 switches the corrector off (tests: its effect on the error).             */
+/* ------------------------------------------------------------------------------------------ */
+static void sample_row(const sys_t* s, double* row);
+
+typedef struct {
+    int n, corrector, synced;
+    double m[MAXN], eta[MAXN];          /* eta_i = m_0 + ... + m_i */
+    double xj[3 * MAXN], vj[3 * MAXN];  /* Jacobi coordinates; index 0 = centre of mass */
+    double t, dt, dt_last_done;
+    long n_steps, max_steps;   /* budget: REBOUND's dt bookkeeping can collapse dt when an output interval is shorter than dt */
+    int gave_up;
+} whfast_t;
+
+static void stumpff_cs(double z, double* c0, double* c1, double* c2, double* c3) {
+    int n = 0;
+    while (fabs(z) > 0.1) { z *= 0.25; n++; }
+    /* c3 = sum (-z)^k / (2k+3)!, c2 = sum (-z)^k / (2k+2)! */
+    double a3 = 1.0 / 6.0, a2 = 0.5, s3 = a3, s2 = a2;
+    for (int k = 1; k < 12; k++) {
+        a3 *= -z / ((2.0 * k + 2.0) * (2.0 * k + 3.0));
+        a2 *= -z / ((2.0 * k + 1.0) * (2.0 * k + 2.0));
+        s3 += a3; s2 += a2;
+    }
+    double C3 = s3, C2 = s2, C1 = 1.0 - z * C3, C0 = 1.0 - z * C2;
+    for (; n > 0; n--) {
+        C3 = (C2 + C0 * C3) * 0.25;
+        C2 = C1 * C1 * 0.5;
+        C1 = C0 * C1;
+        C0 = 2.0 * C0 * C0 - 1.0;
+    }
+    *c0 = C0; *c1 = C1; *c2 = C2; *c3 = C3;
+}
+
+/* two-body advance by h (either sign) in universal variables: solve r0 G1 + eta G2 + mu G3 = h for X,
+ * G_k = X^k c_k(beta X^2), beta = 2 mu / r0 - v0^2; Newton with a bisection safeguard, to round-off */
+static int kepler_advance(double mu, double h, double* x, double* v) {
+    const double r0 = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    const double v2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double eta = x[0] * v[0] + x[1] * v[1] + x[2] * v[2];
+    const double beta = 2.0 * mu / r0 - v2;
+    double X = h / r0, lo = -INFINITY, hi = INFINITY;
+    double G1 = 0, G2 = 0, G3 = 0, c0, c1, c2, c3, r = r0;
+    int ok = 0;
+    for (int it = 0; it < 60; it++) {
+        stumpff_cs(beta * X * X, &c0, &c1, &c2, &c3);
+        G1 = X * c1; G2 = X * X * c2; G3 = X * X * X * c3;
+        const double F = r0 * G1 + eta * G2 + mu * G3 - h;
+        r = r0 * c0 + eta * G1 + mu * G2;          /* dF/dX = new radius > 0: F is monotonic */
+        if (F > 0) hi = X; else lo = X;
+        double Xn = X - F / r;
+        if (!(Xn > lo && Xn < hi)) Xn = (isfinite(lo) && isfinite(hi)) ? 0.5 * (lo + hi) : (F > 0 ? X - fabs(X) - 1e-3 : X + fabs(X) + 1e-3);
+        if (fabs(Xn - X) <= 1e-16 * fabs(Xn) || Xn == X) { X = Xn; ok = 1; break; }
+        X = Xn;
+    }
+    stumpff_cs(beta * X * X, &c0, &c1, &c2, &c3);
+    G1 = X * c1; G2 = X * X * c2; G3 = X * X * X * c3;
+    r = r0 * c0 + eta * G1 + mu * G2;
+    const double f = 1.0 - mu * G2 / r0, g = h - mu * G3, fd = -mu * G1 / (r * r0), gd = 1.0 - mu * G2 / r;
+    for (int k = 0; k < 3; k++) {
+        const double xn = f * x[k] + g * v[k], vn = fd * x[k] + gd * v[k];
+        x[k] = xn; v[k] = vn;
+    }
+    return ok;
+}
+
+static void wh_from_inertial(whfast_t* W, const sys_t* s, int corrector) {
+    W->n = s->n; W->corrector = corrector; W->synced = 1; W->t = 0.0; W->dt = 1e-3; W->dt_last_done = 0.0; W->n_steps = 0; W->max_steps = 0; W->gave_up = 0;
+    double M = 0.0, cx[3] = {0, 0, 0}, cv[3] = {0, 0, 0};     /* mass-weighted sums of bodies 0..i-1 */
+    for (int i = 0; i < s->n; i++) {
+        W->m[i] = s->m[i];
+        if (i > 0)
+            for (int k = 0; k < 3; k++) { W->xj[3 * i + k] = s->x[3 * i + k] - cx[k] / M; W->vj[3 * i + k] = s->v[3 * i + k] - cv[k] / M; }
+        for (int k = 0; k < 3; k++) { cx[k] += s->m[i] * s->x[3 * i + k]; cv[k] += s->m[i] * s->v[3 * i + k]; }
+        M += s->m[i];
+        W->eta[i] = M;
+    }
+    for (int k = 0; k < 3; k++) { W->xj[k] = cx[k] / M; W->vj[k] = cv[k] / M; }
+}
+
+/* Jacobi -> inertial (positions and velocities): from the outermost body inwards */
+static void wh_to_inertial(const whfast_t* W, sys_t* s) {
+    s->n = W->n;
+    double cx[3], cv[3];      /* centre of mass of bodies 0..i */
+    for (int k = 0; k < 3; k++) { cx[k] = W->xj[k]; cv[k] = W->vj[k]; }
+    for (int i = W->n - 1; i > 0; i--) {
+        const double fr = W->m[i] / W->eta[i];
+        for (int k = 0; k < 3; k++) {
+            /* r_i = R_{i-1} + r'_i and R_i = R_{i-1} + fr r'_i  =>  R_{i-1} = R_i - fr r'_i */
+            const double Rx = cx[k] - fr * W->xj[3 * i + k], Rv = cv[k] - fr * W->vj[3 * i + k];
+            s->x[3 * i + k] = Rx + W->xj[3 * i + k]; s->v[3 * i + k] = Rv + W->vj[3 * i + k];
+            cx[k] = Rx; cv[k] = Rv;
+        }
+        s->m[i] = W->m[i];
+    }
+    s->m[0] = W->m[0];
+    for (int k = 0; k < 3; k++) { s->x[k] = cx[k]; s->v[k] = cv[k]; }
+}
+
+static void wh_drift(whfast_t* W, double h) {
+    for (int i = 1; i < W->n; i++) kepler_advance(NBT_G * W->eta[i], h, W->xj + 3 * i, W->vj + 3 * i);
+    for (int k = 0; k < 3; k++) W->xj[k] += h * W->vj[k];      /* centre of mass */
+}
+
+static void wh_kick(whfast_t* W, double h) {
+    sys_t s;
+    wh_to_inertial(W, &s);
+    const int n = W->n;
+    double a[3 * MAXN];
+    for (int i = 0; i < 3 * n; i++) a[i] = 0.0;
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) {
+            if (i == 0 && j == 1) continue;                   /* in the Kepler part of the splitting */
+            double d[3], r2 = 0.0;
+            for (int k = 0; k < 3; k++) { d[k] = s.x[3 * j + k] - s.x[3 * i + k]; r2 += d[k] * d[k]; }
+            const double pre = NBT_G / (r2 * sqrt(r2));
+            for (int k = 0; k < 3; k++) { a[3 * i + k] += pre * s.m[j] * d[k]; a[3 * j + k] -= pre * s.m[i] * d[k]; }
+        }
+    /* inertial -> Jacobi accelerations: a'_i = a_i - (sum_{k<i} m_k a_k) / eta_{i-1} */
+    double sa[3] = {W->m[0] * a[0], W->m[0] * a[1], W->m[0] * a[2]};
+    for (int i = 1; i < n; i++) {
+        double r2 = 0.0;
+        for (int k = 0; k < 3; k++) r2 += W->xj[3 * i + k] * W->xj[3 * i + k];
+        const double pre = (i > 1) ? NBT_G * W->eta[i] / (r2 * sqrt(r2)) : 0.0;
+        for (int k = 0; k < 3; k++) {
+            const double aj = a[3 * i + k] - sa[k] / W->eta[i - 1];
+            W->vj[3 * i + k] += h * (aj + pre * W->xj[3 * i + k]);
+            sa[k] += W->m[i] * a[3 * i + k];
+        }
+    }
+}
+
+static void wh_Z(whfast_t* W, double a, double b) {
+    wh_drift(W, a); wh_kick(W, -b); wh_drift(W, -2.0 * a); wh_kick(W, b); wh_drift(W, a);
+}
+
+static void wh_corrector(whfast_t* W, double inv) {
+    if (W->corrector != 5) return;
+    const double a1 = 0.41833001326703777398908601289259374469640768464934, a2 = 2.0 * a1;
+    const double b51 = -0.0083001986759332891664501193034244790614369381874871;
+    const double b52 = 0.041500993379666445832250596517122395307184690937435;
+    const double dt = W->dt;
+    wh_Z(W, -a2 * dt, -inv * b51 * dt);
+    wh_Z(W, -a1 * dt, -inv * b52 * dt);
+    wh_Z(W, a1 * dt, inv * b52 * dt);
+    wh_Z(W, a2 * dt, inv * b51 * dt);
+}
+
+static void wh_synchronize(whfast_t* W) {
+    if (W->synced) return;
+    wh_drift(W, 0.5 * W->dt);
+    wh_corrector(W, -1.0);
+    W->synced = 1;
+}
+
+static void wh_step(whfast_t* W) {
+    if (W->synced) { wh_corrector(W, 1.0); wh_drift(W, 0.5 * W->dt); }
+    else wh_drift(W, W->dt);
+    W->t += 0.5 * W->dt;
+    wh_kick(W, W->dt);
+    W->synced = 0;
+    W->t += 0.5 * W->dt;
+    W->dt_last_done = W->dt;
+    W->n_steps++;
+}
+
+/* sim.integrate(tmax), exact_finish_time = 1 */
+static void wh_integrate_to(whfast_t* W, double tmax) {
+    double last_full_dt = W->dt;
+    int last_step = 0;
+    for (;;) {
+        if (W->t + W->dt >= tmax) {           /* the next step would overshoot */
+            if (W->t == tmax) break;
+            if (last_step) {
+                double tscale = 1e-12 * fabs(tmax);
+                if (tscale < 1e-200) tscale = 1e-12;
+                if (fabs(W->t - tmax) < tscale) break;
+                wh_synchronize(W);
+                W->dt = tmax - W->t;
+            } else {
+                last_step = 1;
+                wh_synchronize(W);
+                if (W->dt_last_done != 0.0) last_full_dt = W->dt_last_done;
+                W->dt = tmax - W->t;
+            }
+        }
+        if (W->max_steps > 0 && W->n_steps >= W->max_steps) { W->gave_up = 1; break; }
+        wh_step(W);
+    }
+    wh_synchronize(W);
+    W->dt = last_full_dt;
+}
+
+/* integrate() with integrator='whfast': series[n_outputs][3 + 10*Np]; dt0 = REBOUND's default 1e-3 unless > 0;
+ * returns the number of steps taken */
+long nbo_integrate_series_whfast(const double* params, int n_bodies, double n_days, int n_outputs, double dt0,
+                                 int corrector, double* series) {
+    sys_t s;
+    build_system(params, n_bodies, &s);
+    whfast_t W;
+    wh_from_inertial(&W, &s, corrector);
+    if (dt0 > 0.0) W.dt = dt0;
+    const int Wd = 3 + 10 * (n_bodies - 1);
+    const double step = n_days / (double)(n_outputs - 1);
+    W.max_steps = (long)(4.0 * (n_days / W.dt + n_outputs)) + 1000;
+    for (int o = 0; o < n_outputs; o++) {
+        const double t = (o == n_outputs - 1) ? n_days : o * step;
+        if (!W.gave_up) wh_integrate_to(&W, t);
+        if (W.gave_up) { for (int k = 0; k < Wd; k++) series[(size_t)o * Wd + k] = NAN; continue; }
+        wh_to_inertial(&W, &s);
+        sample_row(&s, series + (size_t)o * Wd);
+    }
+    return W.n_steps;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -688,7 +917,10 @@ static void run_one(const nbt_config* cfg, const nbt_inputs* in, nbt_outputs* ou
         double* times = (double*)malloc(sizeof(double) * NO);
         double* col_p = (double*)malloc(sizeof(double) * NO);
         double* col_s = (double*)malloc(sizeof(double) * NO);
-        total_steps += nbo_integrate_series(par, N, n_days, NO, series, NULL);
+        if (cfg->scheme == NBT_SCHEME_WHFAST)      /* generate(..., integrator='whfast'), nbody/simulation.py:39-42 */
+            total_steps += nbo_integrate_series_whfast(par, N, n_days, NO, 0.0, 5, series);
+        else
+            total_steps += nbo_integrate_series(par, N, n_days, NO, series, NULL);
         double step = n_days / (double)(NO - 1);
         for (int o = 0; o < NO; o++) times[o] = (o == NO - 1) ? n_days : o * step;
         int status = 0;

@@ -7,6 +7,7 @@
 
 #include "../../nbody_ai_b200/csrc/nbt_core.cuh"
 #include "../../nbody_ai_b200/csrc/nbt_ias15.cuh"
+#include "../../nbody_ai_b200/csrc/nbt_whfast.cuh"
 
 template <int NP>
 static void run_np(const nbt_run_args& A, int first, int count) {
@@ -40,6 +41,17 @@ extern "C" int hostsim_run(const nbt_config* cfg, const nbt_inputs* in, nbt_outp
             case 2: nbt_simulate_system_ias15<2>(A, T, b); break;
             case 3: nbt_simulate_system_ias15<3>(A, T, b); break;
             case 4: nbt_simulate_system_ias15<4>(A, T, b); break;
+            default: return -1;
+            }
+        return 0;
+    }
+    if (cfg->scheme == NBT_SCHEME_WHFAST) {   // the reference's 'whfast' preset (k_integrate_whfast)
+        for (int b = 0; b < A.B; b++)
+            switch (cfg->n_bodies - 1) {
+            case 1: nbt_simulate_system_whfast<1>(A, b); break;
+            case 2: nbt_simulate_system_whfast<2>(A, b); break;
+            case 3: nbt_simulate_system_whfast<3>(A, b); break;
+            case 4: nbt_simulate_system_whfast<4>(A, b); break;
             default: return -1;
             }
         return 0;

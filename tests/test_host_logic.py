@@ -91,3 +91,82 @@ def test_randomize_draws_match_reference_rng():
         o = simulation.randomize()
         got = [o[0]['m'], o[1]['m'], o[1]['P'], o[2]['m'], o[2]['P'], o[2]['e'], o[2]['omega'], o[1]['inc'], o[2]['inc']]
         assert np.allclose(got, row, rtol=1e-12, atol=0)
+
+
+def _plan_by_helpers(lib, par, n_days, n_outputs, flags, scheme, sort, nds=None, nos=None, substeps=None):
+    """The plan assembled from the separate nbt_plan_* helpers (what engine.Plan did before nbt_plan existed)."""
+    import ctypes as C
+    B, N = par.shape[:2]
+    Np = N - 1
+    cfg = _abi.make_config(B, N, n_days, n_outputs, substeps=0, scheme=scheme, flags=flags)
+    inp = _abi.nbt_inputs()
+    inp.params = _abi.ptr(par)
+    inp.n_days_sys, inp.n_outputs_sys = _abi.ptr(nds), _abi.ptr(nos, C.c_int32)
+    if substeps is None:
+        sub = np.zeros(B, dtype=np.int32)
+        assert lib.nbt_plan_substeps(C.byref(cfg), C.byref(inp), _abi.ptr(sub, C.c_int32)) == 0
+    else:
+        sub = np.ascontiguousarray(substeps, dtype=np.int32)
+    inp.substeps = _abi.ptr(sub, C.c_int32)
+    marked = scheme == _abi.SCHEME_AUTO and bool((sub < 0).any())
+    order = np.arange(B, dtype=np.int32)
+    if sort and (B > 32 or marked):
+        assert lib.nbt_plan_order(C.byref(cfg), C.byref(inp), _abi.ptr(order, C.c_int32)) >= 0
+    elif marked:
+        order = np.concatenate([np.flatnonzero(sub >= 0), np.flatnonzero(sub < 0)]).astype(np.int32)
+    tto, lso = np.zeros(B * Np + 1, dtype=np.int64), np.zeros(B * Np + 1, dtype=np.int64)
+    cap = lib.nbt_plan_tt(C.byref(cfg), C.byref(inp), _abi.ptr(tto, C.c_int64))
+    assert lib.nbt_plan_ls(C.byref(cfg), _abi.ptr(tto, C.c_int64), _abi.ptr(lso, C.c_int64)) == 0
+    return dict(substeps=sub, order=order, tt_offsets=tto, ls_offsets=lso, cap=cap, n_steps=lib.nbt_count_steps(C.byref(cfg), C.byref(inp)),
+                alt=int((sub < 0).sum()) if scheme == _abi.SCHEME_AUTO else 0)
+
+
+@pytest.mark.parametrize("threads", [1, 0])
+def test_one_call_planner_matches_the_helpers(nbt, threads):
+    """nbt_plan (one threaded pass, counting sort) == nbt_plan_substeps + _order + _tt + _ls + nbt_count_steps, bit for
+    bit: uniform and per-system grids, every scheme family, sorted and unsorted, given sub-steps, tiny batches."""
+    cases = [
+        (workloads.c2_params(3000, 6, seed=3), 365.0, 8760, _abi.F_MEANS | _abi.F_LS_OC, _abi.SCHEME_AUTO, True),
+        (workloads.c2_params(3000, 6, seed=3), 365.0, 8760, _abi.F_MEANS | _abi.F_LS_OC, _abi.SCHEME_AUTO, False),
+        (workloads.c5_params(6000, seed=5), 1095.0, 26280, _abi.F_MEANS, _abi.SCHEME_AUTO, True),
+        (workloads.random_systems(5000, 3, seed=6), 200.0, 1201, _abi.F_PLANET1_ONLY | _abi.F_LS_OC, _abi.SCHEME_SBABC3, True),
+        (workloads.random_systems(20, 2, seed=7), 365.0, 8760, _abi.F_MEANS, _abi.SCHEME_AUTO, True),
+        (workloads.random_systems(20, 2, seed=7), 100.0, 201, _abi.F_MEANS, _abi.SCHEME_M64, True),
+    ]
+    for par, nd, no, fl, sch, sort in cases:
+        want = _plan_by_helpers(nbt, par, nd, no, fl, sch, sort)
+        plan = engine.Plan(par, nd, no, flags=fl, scheme=sch, sort=sort, threads=threads)
+        assert np.array_equal(plan.substeps, want["substeps"]) and np.array_equal(plan.tt_offsets, want["tt_offsets"])
+        if fl & _abi.F_LS_OC:
+            assert np.array_equal(plan.ls_offsets, want["ls_offsets"])
+        got_order = np.arange(plan.B, dtype=np.int32) if plan.order is None else plan.order
+        assert np.array_equal(got_order, want["order"])
+        assert plan.n_steps == want["n_steps"] and plan.cfg.tt_cap_max == want["cap"] and plan.cfg.alt_systems == want["alt"]
+    # per-system grids (generate_simulations.py:45-50) and caller-given sub-steps
+    par = workloads.random_systems(4000, 2, seed=8)
+    nds = par[:, 1, 1] * 60
+    nos = np.rint(par[:, 1, 1] * 60 * 24).astype(np.int32)
+    want = _plan_by_helpers(nbt, par, float(nds.max()), int(nos.max()), _abi.F_PLANET1_ONLY, _abi.SCHEME_AUTO, True, nds=nds, nos=nos)
+    plan = engine.Plan(par, nds, nos, flags=_abi.F_PLANET1_ONLY, threads=threads)
+    assert np.array_equal(plan.substeps, want["substeps"]) and np.array_equal(plan.order, want["order"])
+    assert np.array_equal(plan.tt_offsets, want["tt_offsets"]) and plan.n_steps == want["n_steps"]
+    given = np.where(np.arange(4000) % 3 == 0, 2, 1).astype(np.int32)
+    want = _plan_by_helpers(nbt, par, 365.0, 8760, _abi.F_MEANS, _abi.SCHEME_SBABC3, True, substeps=given)
+    plan = engine.Plan(par, 365.0, 8760, substeps=given, scheme="sbabc3", threads=threads)
+    assert np.array_equal(plan.order, want["order"]) and plan.n_steps == want["n_steps"]
+    uni = engine.Plan(par, 365.0, 8760, substeps=2, scheme="sbabc3", threads=threads)
+    assert uni.substeps is None and uni.n_steps == 4000 * 8759 * 2 * 3
+
+
+def test_bench_cpu_arm_plans_without_the_cuda_library(nbt):
+    """bench.py --impl reference sizes its CSR buffers with numpy (HostPlan) so that the CPU arm never loads libnbt.so;
+    the layout must be the library's."""
+    import bench
+    for par, nd, no, fl in ((workloads.c2_params(300, 6, seed=0), 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC),
+                            (workloads.c5_params(200), 1095.0, 26280, _abi.F_MEANS),
+                            (workloads.c3_params(100)[0], 79, 3792, _abi.F_PLANET1_ONLY | _abi.F_LS_OC)):
+        hp, lp = bench.HostPlan(par, nd, no, fl), engine.Plan(par, nd, no, flags=fl)
+        assert np.array_equal(hp.tt_offsets, lp.tt_offsets) and hp.cfg.tt_cap_max == lp.cfg.tt_cap_max
+        if fl & _abi.F_LS_OC:
+            assert np.array_equal(hp.ls_offsets, lp.ls_offsets)
+    assert bench.f_step(2) == 579 and bench.f_step(3) == 926 and bench.f_step(4) == 1298      # SURVEY.md 8(d)

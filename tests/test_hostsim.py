@@ -186,3 +186,27 @@ def test_branch_free_acos(hostsim):
     y = np.zeros_like(x)
     hostsim.hostsim_acos(x.ctypes.data_as(C.POINTER(C.c_double)), y.ctypes.data_as(C.POINTER(C.c_double)), len(x))
     assert np.abs(y - np.arccos(x)).max() < 1e-15
+
+
+def test_whfast_preset_device_arithmetic_vs_oracle(hostsim):
+    """NBT_SCHEME_WHFAST (nbt_whfast.cuh: integrator='whfast', corrector 5, safe_mode 0, dt = 1e-3 d) in the product's
+    arithmetic against the oracle's independent restatement of the same algorithm: positions to 1e-12 AU, transit
+    times to 1e-5 s, elements to 1e-10 — and against IAS15 inside the parity tolerances."""
+    par = np.concatenate([workloads.c1_params(1), workloads.random_systems(3, 3, seed=5)])
+    plan = engine.Plan(par, 20.0, 481, scheme="whfast", flags=_abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_SERIES, lanes=0)
+    assert list(plan.substeps) == [41] * 4
+    got, want = host_run(hostsim, plan), oracle_run(plan)
+    assert np.abs(got.series[:, :, :3] - want.series[:, :, :3]).max() < 1e-13
+    for j in range(3):
+        c = 3 + 10 * j
+        assert np.abs(got.series[:, :, c:c + 3] - want.series[:, :, c:c + 3]).max() < 1e-12
+        assert np.abs(got.series[:, :, c + 5] - want.series[:, :, c + 5]).max() < 1e-10
+    assert np.array_equal(got.n_tt, want.n_tt)
+    ias = oracle_run(engine.Plan(par, 20.0, 481, scheme="ias15", flags=_abi.F_MEANS | _abi.F_MEAN_OMEGA, lanes=0))
+    for b in range(4):
+        for j in range(3):
+            if got.n_transits(b, j):
+                assert np.abs(got.tt_of(b, j) - want.tt_of(b, j)).max() * 86400 < 1e-5
+                assert np.abs(got.tt_of(b, j) - ias.tt_of(b, j)).max() * 86400 < 1e-3
+    assert np.all(np.abs(got.mean_e - want.mean_e) / np.maximum(want.mean_e, 1e-4) < 1e-9)
+    assert np.all(np.abs(got.mean_e - ias.mean_e) / np.maximum(ias.mean_e, 1e-4) < 1e-8)

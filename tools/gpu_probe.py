@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from nbody_ai_b200 import _abi, engine, workloads  # noqa: E402
-from bench import plan_flops  # noqa: E402
+from bench import survey_flops as plan_flops  # noqa: E402  (SURVEY 8(d) FLOP model)
 
 
 def timed(params, nd, no, flags, reps=2, **kw):
