@@ -176,12 +176,20 @@ class HostPlan:
         self.params = np.ascontiguousarray(params, dtype=np.float64)
         B, N, _ = self.params.shape
         self.B, self.N, self.Np = B, N, N - 1
-        self.cfg = _abi.make_config(B, N, n_days, n_outputs, substeps=1, scheme=_abi.SCHEME_SBABC3, flags=flags)
         self.substeps = self.order = self.n_days_sys = self.n_outputs_sys = self.likelihood = None
+        nd, no = np.asarray(n_days, dtype=np.float64), np.asarray(n_outputs)
+        if nd.ndim or no.ndim:     # per-system grids (generate_simulations.py:45-50)
+            self.n_days_sys = np.ascontiguousarray(np.broadcast_to(nd, (B,)), dtype=np.float64)
+            self.n_outputs_sys = np.ascontiguousarray(np.broadcast_to(no, (B,)), dtype=np.int32)
+            nd, no = self.n_days_sys[:, None], self.n_outputs_sys[:, None].astype(np.float64)
+            n_days, n_outputs = float(self.n_days_sys.max()), int(self.n_outputs_sys.max())
+        else:
+            nd, no = float(n_days), float(n_outputs)
+        self.cfg = _abi.make_config(B, N, n_days, n_outputs, substeps=1, scheme=_abi.SCHEME_SBABC3, flags=flags)
         self.rv_nfreq = 0
         P = self.params[:, 1:, _abi.P_P]
         ok = np.isfinite(P) & (P > 0)
-        cap = np.where(ok, np.minimum(np.ceil(1.05 * n_days / np.where(ok, P, 1.0)) + 3.0, float(n_outputs)), 3.0).astype(np.int64)
+        cap = np.where(ok, np.minimum(np.ceil(1.05 * nd / np.where(ok, P, 1.0)) + 3.0, no), 3.0).astype(np.int64)
         if flags & _abi.F_PLANET1_ONLY:
             cap[:, 1:] = 1
         self.tt_offsets = np.concatenate([[0], np.cumsum(cap.ravel())]).astype(np.int64)
@@ -192,7 +200,7 @@ class HostPlan:
             df = 1.0 / np.maximum(c - 1.0, 1.0) / self.cfg.ls_samples_per_peak
             nf = np.where(c >= 3, 1 + np.rint((self.cfg.ls_oc_maxfreq - self.cfg.ls_oc_minfreq) / df), 0).astype(np.int64)
             self.ls_offsets = np.concatenate([[0], np.cumsum(nf)]).astype(np.int64)
-        self.n_steps = B * (n_outputs - 1)
+        self.n_steps = int(self.n_outputs_sys.sum() - B) if self.n_outputs_sys is not None else B * (n_outputs - 1)
 
 
 def cpu_path(params, n_days=N_DAYS, n_outputs=N_OUTPUTS, flags=None, n_threads=0):
@@ -346,13 +354,55 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the host-pointer C ABI: plan + H2D + kernels + D2H every step --------------------
     # N = 1: a fresh parameter block every step (other seeds of the same workload), so nothing of a plan can be reused;
     # N > 1: the rank's shard is planned anew every step
-    pool = engine.BufferPool(pinned=True)
+    # N > 1 also times the final host gather: every rank's buffers live in a page-locked shared-memory segment
+    # (engine.SharedHostPool) that rank 0 maps, so the gather is a barrier after which rank 0 reads all shards in place
+    # (it sums every shard's transit counts as proof)
     n_sets = 1 if world > 1 else min(max(args.steps, 1), 4)
     param_sets = [params] + [workloads.c2_params(args.draws, args.omegas, seed=100 + i) for i in range(1, n_sets)]
+    gather_note, seg = None, None
+    pool = None
+    if world > 1:
+        seg = "nbt_bench_%s_%%d" % os.environ.get("MASTER_PORT", "0")
+        try:
+            need = sum(a.nbytes for a in (plan.params, plan.substeps, plan.tt_offsets, plan.ls_offsets) if a is not None) * 2
+            need += 8 * (2 * int(plan.tt_offsets[-1]) + int(plan.ls_offsets[-1]) + 16 * B * Np) + (4 << 20)
+            try:
+                os.unlink(os.path.join(engine.SharedHostPool.DIR, seg % rank))
+            except OSError:
+                pass
+            pool = engine.SharedHostPool(seg % rank, int(1.2 * need))
+            gather_note = "zero-copy: per-rank page-locked shared-memory segments (engine.SharedHostPool), barrier, rank 0 reads every shard in place"
+        except Exception as exc:      # no /dev/shm or registration refused: per-rank pinned buffers, gather not timed
+            pool, gather_note = None, "unavailable (%s): per-rank pinned buffers only" % exc
+        ok = torch.tensor([1.0 if pool is not None else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0 and pool is not None:
+            pool.close()
+            pool, gather_note = None, "unavailable on another rank: per-rank pinned buffers only"
+    shared = pool is not None
+    if pool is None:
+        pool = engine.BufferPool(pinned=True)
+    gathered = [0]
 
     def e2e_step(k):
+        if shared:
+            pool.reset()
+        tp = time.perf_counter()
         p = engine.Plan(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=flags, device=local_rank, pool=pool)
-        return p, engine.run(p, pool.buffers_for(p))    # H2D + kernels + D2H + stream sync inside
+        tp = time.perf_counter() - tp
+        buf = engine.run(p, pool.buffers_for(p))        # H2D + kernels + D2H + stream sync inside
+        if shared:
+            pool.publish(p, buf, extra={"index": mine.astype(np.int64)})
+            dist.barrier()                              # the final host gather
+            if rank == 0:
+                tot = 0
+                for r in range(world):
+                    sh = engine.SharedHostPool.attach(seg % r)
+                    tot += int(sh["n_tt"].sum()) + int(sh["status"].shape[0]) + int(sh["ls_oc_power"].shape[0] > 0)
+                    del sh
+                gathered[0] = tot
+            dist.barrier()                              # the segments are free for the next step
+        return p, buf, tp
 
     for k in range(max(min(args.warmup, 2), n_sets)):        # every set once: the pool reaches its final size
         e2e_step(k)
@@ -360,15 +410,36 @@ def run_ours(args, rank, world, local_rank):
     plan_s = 0.0
     t0 = time.perf_counter()
     for k in range(args.steps):
-        tp = time.perf_counter()
-        p = engine.Plan(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=flags, device=local_rank, pool=pool)
-        plan_s += time.perf_counter() - tp
-        hbuf = engine.run(p, pool.buffers_for(p))
+        p, hbuf, tp = e2e_step(k)
+        plan_s += tp
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3
     h2d = sum(a.nbytes for a in (p.params, p.substeps, p.order, p.tt_offsets, p.ls_offsets) if a is not None)
-    d2h = sum(getattr(hbuf, n).nbytes for n in ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e",
-                                               "mean_inc", "mean_omega", "status", "ls_oc_power", "ls_oc_nfreq"))
+    names = ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega", "status",
+             "ls_oc_power", "ls_oc_nfreq", "ls_oc_peaks")
+    d2h = sum(getattr(hbuf, n).nbytes for n in names if getattr(hbuf, n) is not None)
+    # the same with the periodograms reduced to their three highest peaks on the device (NBT_F_LS_PEAKS; what a caller
+    # like simulation_grid.py needs of them): the power arrays — two thirds of the D2H bytes — never leave the GPU
+    pool2 = engine.BufferPool(pinned=True)
+    lean = ("ls_oc_power", "ls_oc_nfreq")
+
+    def peaks_step(k):
+        q = engine.Plan(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=flags | _abi.F_LS_PEAKS, device=local_rank, pool=pool2)
+        return engine.run(q, pool2.buffers_for(q, skip=lean))
+
+    for k in range(n_sets):
+        peaks_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        pbuf = peaks_step(k)
+    torch.cuda.synchronize(dev)
+    e2e_peaks_ms = (time.perf_counter() - t0) * 1e3
+    d2h_peaks = sum(getattr(pbuf, n).nbytes for n in names if getattr(pbuf, n) is not None)
+    del pool2, pbuf
+    if shared:
+        del p, hbuf
+        pool.close()
 
     # sanity: the timed device path and the host path produced the same transits
     chk = dbuf.to_host()
@@ -377,8 +448,8 @@ def run_ours(args, rank, world, local_rank):
     n_tt_total = int(np.minimum(ref_run.n_tt, np.diff(plan.tt_offsets)).sum())
     del chk, ref_run
 
-    (dev_ms, e2e_ms, integ_ms), (sims_all, steps_all, ntt_all) = reduce_max_sum(
-        [dev_ms, e2e_ms, stage_ms[0]], [float(B), float(plan.n_steps), float(n_tt_total)])
+    (dev_ms, e2e_ms, integ_ms, e2e_peaks_ms), (sims_all, steps_all, ntt_all) = reduce_max_sum(
+        [dev_ms, e2e_ms, stage_ms[0], e2e_peaks_ms], [float(B), float(plan.n_steps), float(n_tt_total)])
     # per-rank view (diagnosis of the max-over-ranks figure): step time, e2e time, SM clock, power-cap flag
     mine = torch.tensor([dev_ms / args.steps, e2e_ms / args.steps, clocks["sm_mhz"] or 0.0,
                          1.0 if "sw_power_cap" in clocks["reasons"] else 0.0], dtype=torch.float64, device=dev)
@@ -477,7 +548,11 @@ def run_ours(args, rank, world, local_rank):
                          "flops_per_launch": main_flops, "launch_ms": main_launch_ms, "traffic": ncu_traffic(Np, B),
                          "hbm": hbm_side(ncu_traffic(Np, B), main_launch_ms)},
             "e2e": {"value": sims_all * args.steps / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps, "host_plan_ms_per_step_rank0": 1e3 * plan_s / args.steps},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps, "host_plan_ms_per_step_rank0": 1e3 * plan_s / args.steps,
+                    "final_host_gather": gather_note if world > 1 else "single rank: results are in the caller's buffers"},
+            "e2e_peaks": {"value": sims_all * args.steps / (e2e_peaks_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
+                          "d2h_bytes_per_step": int(d2h_peaks), "ms_per_step": e2e_peaks_ms / args.steps,
+                          "note": "as e2e, with NBT_F_LS_PEAKS: each O-C periodogram reduced to its 3 highest peaks on the device, power arrays not copied back"},
             "gpu_launches": 3 * args.steps + launches_extra,   # k_integrate, k_fit, k_ls_oc per timed device step (+ the north-star passes)
             "clocks": clocks,
             "ranks": {"columns": ["ms_per_step", "e2e_ms_per_step", "sm_mhz", "sw_power_cap"], "rows": per_rank},
@@ -489,10 +564,89 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": n_s / dt, "unit": "sims/s", "cores": nt, "kind": "port", "cpu_model": cpu_model(),
                                     "host_cpus": os.cpu_count(),
                                     "sample": "first %d systems of the same batch, oracle (IAS15 + analyze) on %d host threads, %.1f s" % (n_s, nt, dt)}
+        if world == 1 and not args.no_blocks:
+            line["blocks"] = extra_blocks(args, local_rank)
         emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def extra_blocks(args, local_rank):
+    """Two more end-to-end figures of BASELINE configs on the public API, beside the CPU port (N = 1 only):
+    C3 — the nested-sampling likelihood batch (nbody/nested.py:85-95): loglike/s through nested.NestedLikelihood
+         .loglike_batch, i.e. planning + H2D + forward model at 30-min cadence + ephemeris + chi^2 on the device +
+         D2H of loglike[B] per call;
+    C2 generator — simulations/generate_simulations.py:41-110 at its own settings (periods = 1000, 6 omega variants,
+         every draw on its own grid of P1 x 1000 days at 1 h): accepted draws/s through dataset.generate_training_set."""
+    import oracle
+    from nbody_ai_b200 import _abi, dataset, nested, workloads
+    out = {}
+    # ---- C3 ----------------------------------------------------------------------------------------------
+    n3 = args.c3_batch
+    objects = [{'m': 1.22}, {'m': 10.4 * 0.000954588, 'P': 0.94145, 'inc': np.pi / 2, 'e': 0, 'omega': 0},
+               {'m': 3e-4, 'P': 2.1, 'inc': np.pi / 2, 'e': 0.02, 'omega': 1.0}]
+    bounds = [[0.0, 1.0], {'P': [0.94135, 0.94155]}, {'P': [1.9, 2.4], 'm': [1.5e-5, 4.2e-4], 'e': [0, 0.1], 'omega': [0, 2 * np.pi]}]
+    rng = np.random.default_rng(1)
+    xx = np.arange(56, dtype=float)
+    _, _, tt0 = nested.get_ttv(objects, ndays=79)
+    yy = tt0[:56] + rng.normal(0, 0.5 / 1440, 56)
+    yerr = np.full(56, 0.5 / 1440)
+    L = nested.NestedLikelihood(xx, yy, yerr, objects, bounds, device=local_rank)
+    def cubes(n):
+        return np.column_stack([rng.normal(tt0[0], 1e-4, n), rng.normal(0.94145, 1e-6, n), rng.uniform(0.94135, 0.94155, n),
+                                rng.uniform(1.9, 2.4, n), rng.uniform(1.5e-5, 4.2e-4, n), rng.uniform(0, 0.1, n), rng.uniform(0, 2 * np.pi, n)])
+    sets = [cubes(n3) for _ in range(4)]
+    for c in sets[:2]:
+        L.loglike_batch(c)
+    t0 = time.perf_counter()
+    for k in range(args.c3_calls):
+        ll = L.loglike_batch(sets[k % 4])
+    dt3 = time.perf_counter() - t0
+    entry = {"workload": "BASELINE config 3: %d parameter vectors per call (WASP-18-like star + hot Jupiter + perturber), %d d @ 30 min, 56 observed epochs" % (n3, L.ndays),
+             "api": "nested.NestedLikelihood.loglike_batch (nbt_plan + nbt_run with NBT_F_LOGLIKE: only loglike[B], status[B] come back)",
+             "calls_timed": args.c3_calls, "ms_per_call": 1e3 * dt3 / args.c3_calls, "loglike_per_s": n3 * args.c3_calls / dt3,
+             "finite_frac": float(np.isfinite(ll).mean())}
+    if not args.no_cpu:
+        ns = min(256, n3)
+        par = L.params_for(sets[0][:ns])
+        plan = HostPlan(par, L.ndays, int(L.ndays * 48), _abi.F_PLANET1_ONLY)
+        from nbody_ai_b200 import engine
+        buf = engine.Buffers(plan)
+        nt = oracle.max_threads()
+        t0 = time.perf_counter()
+        oracle.run(plan.cfg, plan.params, buf, n_threads=nt)
+        for b in range(ns):
+            oracle.loglike(buf.ttv_of(b, 0), sets[0][b, 0], sets[0][b, 1], xx, yy, yerr)
+        dtc = time.perf_counter() - t0
+        entry["cpu_port"] = {"loglike_per_s": ns / dtc, "cores": nt, "sample": "%d of the vectors, oracle (IAS15 + analyze + chi^2) on %d host threads, %.1f s" % (ns, nt, dtc)}
+    out["c3_likelihood"] = entry
+    # ---- training-set generator -----------------------------------------------------------------------------
+    st = {}
+    dataset.generate_training_set(samples=8, omegas=6, periods=1000, rng=np.random.default_rng(5), device=local_rank)      # warm-up
+    t0 = time.perf_counter()
+    X, y = dataset.generate_training_set(samples=args.gen_draws, omegas=6, periods=1000, rng=np.random.default_rng(6), device=local_rank, stats=st)
+    dtg = time.perf_counter() - t0
+    entry = {"workload": "simulations/generate_simulations.py:41-110 at its defaults: periods = 1000, 6 omega variants per accepted draw, every simulation on its own grid (P1 x 1000 d @ 1 h)",
+             "api": "dataset.generate_training_set (candidate draws + variants in one nbt_run with per-system grids, rejection on the host)",
+             "accepted_draws": args.gen_draws, "rows": len(X), "seconds": dtg, "draws_per_s": args.gen_draws / dtg, "simulations_per_s": st["simulations"] / dtg,
+             "launches": st["launches"], "candidates": st["candidates"], "acceptance": st["accepted"] / max(st["candidates"], 1)}
+    if not args.no_cpu:
+        blk = dataset.draw_block(4, 6, np.random.default_rng(7))
+        par = blk.reshape(-1, 3, _abi.NBT_NPAR)
+        nd, no = dataset.grids(par, 1000)
+        plan = HostPlan(par, nd, no, _abi.F_PLANET1_ONLY)
+        from nbody_ai_b200 import engine
+        buf = engine.Buffers(plan)
+        nt = oracle.max_threads()
+        t0 = time.perf_counter()
+        oracle.run(plan.cfg, plan.params, buf, n_threads=nt)
+        dtc = time.perf_counter() - t0
+        acc = st["accepted"] / max(st["candidates"], 1)
+        entry["cpu_port"] = {"simulations_per_s": len(par) / dtc, "draws_per_s": len(par) / dtc / (1.0 / max(acc, 1e-9) + 6.0), "cores": nt,
+                             "sample": "4 candidate draws x 7 simulations, oracle on %d host threads, %.1f s; draws/s = simulations/s / (1 / acceptance + 6)" % (nt, dtc)}
+    out["training_set_generator"] = entry
+    return out
 
 
 class StdoutToStderr:
@@ -559,6 +713,10 @@ def main():
     ap.add_argument("--np3-random", type=int, default=75776, help="random 3-planet systems per GPU (148 x 512)")
     ap.add_argument("--c5-systems", type=int, default=1000000, help="C5 systems in total (sharded over the ranks); 0 = skip")
     ap.add_argument("--c5-passes", type=int, default=2)
+    ap.add_argument("--no-blocks", action="store_true", help="skip the C3 likelihood and training-set generator blocks (N = 1)")
+    ap.add_argument("--c3-batch", type=int, default=5000)
+    ap.add_argument("--c3-calls", type=int, default=10)
+    ap.add_argument("--gen-draws", type=int, default=512)
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     with StdoutToStderr() as OUT:

@@ -134,6 +134,9 @@ __device__ double warp_maxavg(const double* x, int n, int lane) {
 #endif
 #ifndef NBT_MINBLOCKS
 #define NBT_MINBLOCKS 1
+#ifndef NBT_LAT_MINB
+#define NBT_LAT_MINB 1   /* resident CTAs per SM the latency variant (Np = 2) is compiled for: 1 = no register cap (216) */
+#endif
 #endif
 #ifndef NBT_LAT_MAX_SYSTEMS
 #define NBT_LAT_MAX_SYSTEMS (4 * 56832)   /* launches below this many systems take the latency variant (Np <= 2) */
@@ -145,7 +148,7 @@ __device__ double warp_maxavg(const double* x, int n, int lane) {
 // race for the SMs: the light one getting ahead cost 12 ms of the 72 ms bench launch).
 // (the throughput variant for two planets sits at 6 resident CTAs per SM, 168 registers: keep it there)
 template <int NP, bool SERIES, bool LAT>
-__global__ void __launch_bounds__(NBT_BLOCK, (NP == 2 && !SERIES && !LAT) ? 6 : NBT_MINBLOCKS)
+__global__ void __launch_bounds__(NBT_BLOCK, (NP == 2 && !SERIES) ? (LAT ? NBT_LAT_MINB : 6) : NBT_MINBLOCKS)
 k_integrate(const nbt_run_args A, int first, int count, int main_count) {
     const int main_blocks = (main_count + NBT_BLOCK - 1) / NBT_BLOCK;
     const bool alt = (int)blockIdx.x >= main_blocks;

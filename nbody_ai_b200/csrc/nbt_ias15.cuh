@@ -376,7 +376,15 @@ NBT_HD void nbt_simulate_system_ias15(const nbt_run_args& A, const nbt_ias15_tab
     const int NO = (A.n_outputs_sys != nullptr) ? A.n_outputs_sys[sys] : A.n_outputs;
     const double n_days = (A.n_days_sys != nullptr) ? A.n_days_sys[sys] : A.n_days;
     const double step = n_days / (double)(NO - 1);
-    I.max_steps = 200LL * NO + 100000LL;
+    {   // step budget: one step per output plus ~25 per innermost orbit is what a regular system needs; a pair on a collision
+        // course drives the adaptive step towards zero — the run is given up (NBT_S_NONFINITE) at 16x that
+        double pmin = INFINITY;
+        for (int i = 1; i <= NP; i++) {
+            const double P = par[i * NBT_NPAR + NBT_P_P];
+            if (P > 0.0 && P < pmin) pmin = P;
+        }
+        I.max_steps = 2LL * NO + 10000LL + (isfinite(pmin) ? (long long)(400.0 * n_days / pmin) : 0LL);
+    }
     nbt_sampler<NP> Q;
     nbt_sampler_init<NP>(Q);
     for (int o = 0; o < NO; o++) {

@@ -24,14 +24,15 @@ struct nbt_whfast {
     int status;
 };
 
+// (out of line: a step of the corrector is 20 drifts and 8 kicks; inlined, the NP = 8 kernel was 240 000 SASS lines)
 template <int NP>
-NBT_HD void nbt_wh_drift(nbt_whfast<NP>& W, double h) {
+NBT_HD_COLD void nbt_wh_drift(nbt_whfast<NP>& W, double h) {
     for (int i = 0; i < NP; i++)
         nbt_kepler_drift<true>(W.c.GM[i], h, W.s.x[i], W.s.y[i], W.s.z[i], W.s.vx[i], W.s.vy[i], W.s.vz[i], W.s.r[i], W.s.ir[i], W.status);
 }
 
 template <int NP>
-NBT_HD void nbt_wh_kick(nbt_whfast<NP>& W, double h) {
+NBT_HD_COLD void nbt_wh_kick(nbt_whfast<NP>& W, double h) {
     double ax[NP], ay[NP], az[NP];
     nbt_accel<NP>(W.s, W.c, ax, ay, az);
     for (int i = 0; i < NP; i++) {
@@ -45,7 +46,7 @@ NBT_HD void nbt_wh_Z(nbt_whfast<NP>& W, double a, double b) {
 }
 
 template <int NP>
-NBT_HD void nbt_wh_corrector(nbt_whfast<NP>& W, double inv) {
+NBT_HD_COLD void nbt_wh_corrector(nbt_whfast<NP>& W, double inv) {
     const double a1 = 0.41833001326703777398908601289259374469640768464934, a2 = 2.0 * a1;
     const double b51 = -0.0083001986759332891664501193034244790614369381874871;
     const double b52 = 0.041500993379666445832250596517122395307184690937435;

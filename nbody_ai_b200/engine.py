@@ -323,6 +323,116 @@ class BufferPool:
         return buf
 
 
+class SharedHostPool(BufferPool):
+    """The final host gather of a sharded batch on one node, without a copy.
+
+    One process per GPU: each rank's results land in its own host buffers.  Here those buffers live in a
+    POSIX shared-memory segment per rank, page-locked for CUDA (cudaHostRegister), so that the D2H copies of nbt_run are
+    DMA straight into memory that every other process of the job can map: after a barrier rank 0 (or any rank) reads
+    every shard in place through `SharedHostPool.attach(name)`.  The "gather" is the barrier.
+
+    A pool serves one plan at a time: call reset(), then Plan(..., pool=pool) and pool.buffers_for(plan), run, and
+    publish(plan, buffers) — which writes the array directory into the segment's header for the readers."""
+
+    HEADER = 1 << 16
+    DIR = "/dev/shm"      # tmpfs: the segment is ordinary shared memory, named so that the other ranks can map it
+
+    def __init__(self, name, capacity_bytes, register=True):
+        import mmap
+        import os
+        self.name, self.capacity = name, int(capacity_bytes)
+        self.path = os.path.join(self.DIR, name)
+        fd = os.open(self.path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+        try:
+            os.ftruncate(fd, self.HEADER + self.capacity)
+            self.map = mmap.mmap(fd, self.HEADER + self.capacity)
+        finally:
+            os.close(fd)
+        self.base = np.frombuffer(self.map, dtype=np.uint8)
+        self.base[:] = 0                                   # first touch by the owner: pages on this rank's NUMA node
+        self.registered = False
+        if register:
+            import torch
+            rc = torch.cuda.cudart().cudaHostRegister(self.base.ctypes.data, self.base.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister of the shared segment failed (%s)" % rc)
+            self.registered = True
+        self.pinned, self.headroom, self.store = False, 1.0, {}
+        self.used = 0
+
+    def reset(self):
+        self.used = 0
+
+    def _take(self, name, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        off = (self.used + 255) & ~255
+        if off + n > self.capacity:
+            raise MemoryError("SharedHostPool %s: %d bytes needed, capacity %d" % (self.name, off + n, self.capacity))
+        self.used = off + n
+        return self.base[self.HEADER + off:self.HEADER + off + n].view(dtype).reshape(shape)
+
+    def buffers_for(self, plan, skip=()):
+        buf = Buffers.__new__(Buffers)
+        buf._pool_alloc = self._take
+        Buffers.__init__(buf, plan, pinned=False, skip=skip)
+        return buf
+
+    def publish(self, plan, buffers, extra=None):
+        """Write the directory of this step's arrays (results, the CSR offsets they are indexed by, the global system
+        indices of the shard if given in `extra`) into the header."""
+        import pickle
+        entries = {}
+        arrays = {n: getattr(buffers, n) for n, _ in OUTPUT_NAMES}
+        arrays.update(tt_offsets=plan.tt_offsets, ls_offsets=plan.ls_offsets)
+        arrays.update(extra or {})
+        lo = self.base.ctypes.data + self.HEADER
+        for n, a in arrays.items():
+            if a is None:
+                continue
+            if not (lo <= a.ctypes.data and a.ctypes.data + a.nbytes <= lo + self.capacity):   # not from the pool: copy in
+                b = self._take("pub/" + n, a.shape, a.dtype)
+                np.copyto(b, a)
+                a = b
+            entries[n] = (a.ctypes.data - lo, a.shape, a.dtype.str)
+        blob = pickle.dumps(dict(B=plan.B, Np=plan.Np, flags=int(plan.cfg.flags), arrays=entries))
+        assert len(blob) + 8 <= self.HEADER
+        self.base[8:8 + len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+        self.base[:8].view(np.int64)[0] = len(blob)
+
+    def close(self):
+        """Unregister and unlink the segment (the mapping itself goes with the last view of it)."""
+        import os
+        if self.registered:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self.base.ctypes.data)
+            self.registered = False
+        self.base = self.map = None
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+    @staticmethod
+    def attach(name):
+        """Read-only view of another rank's published step: dict of arrays (views into the shared segment) + B, Np."""
+        import mmap
+        import os
+        import pickle
+        fd = os.open(os.path.join(SharedHostPool.DIR, name), os.O_RDONLY)
+        try:
+            shm = mmap.mmap(fd, 0, prot=mmap.PROT_READ)
+        finally:
+            os.close(fd)
+        base = np.frombuffer(shm, dtype=np.uint8)
+        n = int(base[:8].view(np.int64)[0])
+        meta = pickle.loads(base[8:8 + n].tobytes())
+        out = dict(B=meta["B"], Np=meta["Np"], flags=meta["flags"], _shm=shm)
+        for k, (off, shape, dt) in meta["arrays"].items():
+            cnt = int(np.prod(shape)) * np.dtype(dt).itemsize
+            out[k] = base[SharedHostPool.HEADER + off:SharedHostPool.HEADER + off + cnt].view(np.dtype(dt)).reshape(shape)
+        return out
+
+
 def run(plan, buffers=None, stream=None):
     """One nbt_run over host buffers (H2D + kernels + D2H inside the call).  Raises without CUDA."""
     lib = _abi.load()

@@ -684,6 +684,9 @@ long nbo_integrate_series(const double* params, int n_bodies, double n_days, int
     build_system(params, n_bodies, &s);
     ias15_t* I = (ias15_t*)malloc(sizeof(ias15_t));
     ias15_init(I, &s);
+    /* step budget: a pair on a collision course drives the adaptive step towards zero; REBOUND crawls through it (it has
+     * no budget), so the allowance is generous — 200 steps per output where a regular system takes one or two — before
+     * the run is given up and marked non-finite.  (The product's IAS15 kernel gives up much earlier, nbt_ias15.cuh.) */
     I->max_steps = 200L * n_outputs + 100000L;
     int W = 3 + 10 * (n_bodies - 1);
     double step = n_days / (double)(n_outputs - 1); /* np.linspace(0, Ndays, Noutputs) */

@@ -261,3 +261,31 @@ def test_whfast_preset_vs_oracle(gpu_lib):
         assert np.abs(sim_data['pdata'][j]['x'] - ser[:, 3 + 10 * j]).max() < 1e-11
         assert np.abs(sim_data['pdata'][j]['e'] - ser[:, 8 + 10 * j]).max() < 1e-9
     assert np.abs(sim_data['star']['x'] - ser[:, 0]).max() < 1e-13
+
+
+def test_solar_system_amplitude_ranges(gpu_lib):
+    """solarsystem_nbody.py: the eight planets for 1000 years at 1-hour cadence, one planet per lane
+    (k_integrate_lanes<8>) — the TTV amplitudes the script's comment quotes (:32-38: Mercury 0-1, Venus 3-5, Earth 4-6,
+    Mars 20-40, Jupiter 500-1000, Saturn 1000-1500 min; read off a plot, every planet started at f = omega = 0, so an
+    order-of-magnitude known answer only: the inner four within ~30 %, the giants — a few dozen transits of a 900-year
+    term — within a factor of a few)."""
+    from nbody_ai_b200.tools import mearth, msun
+    objects = [{'m': 1.},
+               {'m': 0.0553 * mearth / msun, 'P': 87.969, 'inc': 3.14159 / 2, 'e': 0.205},
+               {'m': 0.815 * mearth / msun, 'P': 224.701, 'inc': 3.14159 / 2, 'e': 0.007},
+               {'m': mearth / msun, 'P': 365.24, 'inc': 3.14159 / 2, 'e': 0.017},
+               {'m': 0.107 * mearth / msun, 'P': 686.980, 'inc': 3.14159 / 2, 'e': 0.094},
+               {'m': 317.83 * mearth / msun, 'P': 4332.589, 'inc': 3.14159 / 2, 'e': 0.049},
+               {'m': 95.16 * mearth / msun, 'P': 10759.22, 'inc': 3.14159 / 2, 'e': 0.056},
+               {'m': 14.54 * mearth / msun, 'P': 30588.740, 'inc': 3.14159 / 2, 'e': 0.0457},
+               {'m': 17.15 * mearth / msun, 'P': 59799.9, 'inc': 3.14159 / 2, 'e': 0.0113}]
+    par = _abi.objects_to_params(objects)[None]
+    plan = engine.Plan(par, 1000 * 365, 1000 * 365 * 24, flags=0)          # solarsystem_nbody.py:24
+    assert plan.cfg.lanes_systems == 1
+    got = engine.run(plan)
+    assert not got.status[0] & (_abi.S_NONFINITE | _abi.S_UNBOUND | _abi.S_TT_OVERFLOW)
+    amp = got.ttv_max[:8] * 1440
+    print("solar-system TTV max-avg [min]:", np.round(amp, 2), "transits", got.n_tt[:8])
+    assert list(got.n_tt[:4]) == [4149, 1625, 1000, 532] or np.all(np.abs(got.n_tt[:4] - [4149, 1625, 1000, 532]) <= 1)
+    for j, (lo, hi) in enumerate([(0.5, 2.0), (3.0, 6.0), (4.0, 8.0), (20.0, 55.0), (300.0, 3000.0), (800.0, 8000.0)]):
+        assert lo < amp[j] < hi, (j, amp[j])

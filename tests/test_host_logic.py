@@ -169,4 +169,9 @@ def test_bench_cpu_arm_plans_without_the_cuda_library(nbt):
         assert np.array_equal(hp.tt_offsets, lp.tt_offsets) and hp.cfg.tt_cap_max == lp.cfg.tt_cap_max
         if fl & _abi.F_LS_OC:
             assert np.array_equal(hp.ls_offsets, lp.ls_offsets)
+    from nbody_ai_b200 import dataset
+    par = dataset.draw_block(20, 2, np.random.default_rng(2)).reshape(-1, 3, 7)
+    nd, no = dataset.grids(par, 50)
+    hp, lp = bench.HostPlan(par, nd, no, _abi.F_PLANET1_ONLY), engine.Plan(par, nd, no, flags=_abi.F_PLANET1_ONLY)
+    assert np.array_equal(hp.tt_offsets, lp.tt_offsets) and np.array_equal(hp.n_outputs_sys, lp.n_outputs_sys)
     assert bench.f_step(2) == 579 and bench.f_step(3) == 926 and bench.f_step(4) == 1298

@@ -1,5 +1,5 @@
 """Pins the CPU oracle (test infrastructure) against every known answer the reference offers:
-G1 (figures/report_simulation.png table), G2 (sim_data.txt), the reference's own pure-numpy
+G1 (figures/report_simulation.png table), G3 (figures/report.png table), G2 (sim_data.txt), G4 (solarsystem_nbody.py amplitude ranges), the reference's own pure-numpy
 functions run on the oracle's series (tests/golden/ref_functions.npz, tests/golden/make_golden.py),
 an independent scipy DOP853 integration, scipy's Lomb-Scargle, numpy lstsq/percentile."""
 import json
@@ -46,6 +46,43 @@ def test_g1_report_table(readme_run):
     assert abs(1 / f[k] - 7.0) < 0.05 and abs(p[k] - 0.79) < 0.01
     masses = README[1:, 0] * 1.989e30 / 5.972e24
     assert np.allclose(masses, [88.99, 314.0, 137.3], rtol=2e-4)
+
+
+def test_g3_report_table(built):
+    """figures/report.png — the second report() table the reference ships: 1.12 Msun, 0.25 and 0.1 Mjup at
+    3.2888 / 7 d, run with example.py's recipe (Ndays = 30 P1, hourly): every number of the table to its printed
+    precision, the transit counts of the O-C panel (30 / 14 epochs) and the peaks of the three periodograms as read
+    off the figure (O-C: ~16.5 epochs at 0.93 and ~8 epochs at 0.93; RV: 3.29 d at 0.91, the 7 d bump at 0.09; RV
+    trace within +-42 m/s).  (The third table, simulations/report.png, gives its inputs only to table precision —
+    a randomize() draw with unknown omega_2 — and pins nothing beyond orders of magnitude.)"""
+    from nbody_ai_b200.tools import mearth, mjup, msun
+    objs = [{'m': 1.12}, {'m': 0.25 * mjup / msun, 'P': 3.2888, 'inc': 3.14159 / 2, 'e': 0, 'omega': 0},
+            {'m': 0.1 * mjup / msun, 'P': 7, 'inc': 3.14159 / 2, 'e': 0, 'omega': 0}]
+    P = _abi.objects_to_params(objs)
+    ndays, nout = 30 * 3.2888, int(30 * 3.2888 * 24)
+    times, series, _, _ = oracle.integrate_series(P, ndays, nout)
+    xs = series[:, 0]
+    want = dict(mass=[79.45, 31.78], a=[0.045, 0.074], P=[3.29, 7.0], e=[0.001, 0.001], ttvmax=[1.2, 1.3], n=[30, 14],
+                peak=[(16.5, 0.93), (8.0, 0.93)])
+    for j in range(2):
+        col = series[:, 3 + 10 * j: 13 + 10 * j]
+        tt = oracle.transit_times(col[:, 0], xs, times)
+        ttv, m, b = oracle.ttv_fit(tt)
+        assert len(tt) == want['n'][j]
+        assert round(P[j + 1, 0] * msun / mearth, 2) == want['mass'][j]
+        assert round(col[:, 4].mean(), 3) == want['a'][j] and round(m, 2) == want['P'][j]
+        assert round(col[:, 5].mean(), 3) == want['e'][j]
+        assert round(oracle.maxavg(ttv) * 1440, 1) == want['ttvmax'][j]
+        f, p = oracle.lomb_scargle(np.arange(len(ttv)), ttv, 1. / 180, 0.5)
+        k = np.argmax(p)
+        assert abs(1 / f[k] - want['peak'][j][0]) < 0.5 and abs(p[k] - want['peak'][j][1]) < 0.01
+    rv = np.diff(xs) * 1.496e11 * (nout / (ndays * 86400.))
+    f, p = oracle.lomb_scargle(times[1:], rv)
+    k = np.argmax(p)
+    assert abs(1 / f[k] - 3.29) < 0.01 and abs(p[k] - 0.91) < 0.01
+    near7 = (1 / f > 6) & (1 / f < 8)
+    assert abs(p[near7].max() - 0.09) < 0.01
+    assert 38 < rv.max() < 43 and -43 < rv.min() < -38
 
 
 def test_g2_sim_data(built):

@@ -88,3 +88,60 @@ def test_two_rank_shard_and_gather(built):
     for k in want:
         assert np.array_equal(got[k], want[k], equal_nan=True), k
         assert np.array_equal(got_balanced[k], want[k], equal_nan=True), k
+
+
+def _shared_worker(rank, world, port, q, tag):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    hs = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
+    par = workloads.c2_params(3, 2, seed=21)
+    mine = engine.shard_balanced(engine.system_cost(par, 40.0, 961), rank, world)
+    pool = engine.SharedHostPool("%s_%d" % (tag, rank), 8 << 20, register=False)       # no CUDA here: plain shared memory
+    for step in range(2):                         # the pool is reused from step to step
+        pool.reset()
+        plan = engine.Plan(par[mine], 40.0, 961, substeps=1, flags=_abi.F_MEANS, pool=pool)
+        buf = pool.buffers_for(plan)
+        inp, out = buf.as_structs()
+        assert hs.hostsim_run(C.byref(plan.cfg), C.byref(inp), C.byref(out)) == 0
+        pool.publish(plan, buf, extra={"index": mine.astype(np.int64)})
+        dist.barrier()                            # the final host gather: every shard is now readable in place
+        if rank == 0:
+            n_tt = np.zeros((len(par), 2), dtype=np.int32)
+            mean_a, first_tt = np.zeros((len(par), 2)), np.full((len(par), 2), np.nan)
+            for r in range(world):
+                sh = engine.SharedHostPool.attach("%s_%d" % (tag, r))
+                idx = sh["index"]
+                n_tt[idx] = sh["n_tt"].reshape(-1, 2)
+                mean_a[idx] = sh["mean_a"].reshape(-1, 2)
+                for q_, b in enumerate(idx):
+                    for j in range(2):
+                        if sh["n_tt"][q_ * 2 + j]:
+                            first_tt[b, j] = sh["tt"][sh["tt_offsets"][q_ * 2 + j]]
+                del sh
+        dist.barrier()
+    if rank == 0:
+        q.put({"n_tt": n_tt, "mean_a": mean_a, "first_tt": first_tt})
+    dist.barrier()
+    pool.close()
+    dist.destroy_process_group()
+
+
+def test_shared_memory_gather(built):
+    """engine.SharedHostPool: each rank's results in its own shared segment, read in place by rank 0 after a barrier —
+    the zero-copy final host gather of a one-node job; bit-identical to the unsharded run."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    tag = "nbt_test_%d" % os.getpid()
+    procs = [ctx.Process(target=_shared_worker, args=(r, 2, port, q, tag)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _host_products(workloads.c2_params(3, 2, seed=21))
+    for k in got:
+        assert np.array_equal(got[k], want[k], equal_nan=True), k
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith(tag)]
