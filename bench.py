@@ -448,15 +448,16 @@ def run_ours(args, rank, world, local_rank):
     n_tt_total = int(np.minimum(ref_run.n_tt, np.diff(plan.tt_offsets)).sum())
     del chk, ref_run
 
+    my_dev_ms, my_e2e_ms = dev_ms, e2e_ms          # this rank's own times (the `ranks` table), before the max over ranks
     (dev_ms, e2e_ms, integ_ms, e2e_peaks_ms), (sims_all, steps_all, ntt_all) = reduce_max_sum(
         [dev_ms, e2e_ms, stage_ms[0], e2e_peaks_ms], [float(B), float(plan.n_steps), float(n_tt_total)])
     # per-rank view (diagnosis of the max-over-ranks figure): step time, e2e time, SM clock, power-cap flag
-    mine = torch.tensor([dev_ms / args.steps, e2e_ms / args.steps, clocks["sm_mhz"] or 0.0,
+    mine_t = torch.tensor([my_dev_ms / args.steps, my_e2e_ms / args.steps, clocks["sm_mhz"] or 0.0,
                          1.0 if "sw_power_cap" in clocks["reasons"] else 0.0], dtype=torch.float64, device=dev)
-    per_rank = [mine]
+    per_rank = [mine_t]
     if dist is not None:
-        per_rank = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(per_rank, mine)
+        per_rank = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(per_rank, mine_t)
     per_rank = [[round(float(x), 3) for x in r.cpu()] for r in per_rank]
     main_flops, main_launch_ms = survey_flops(plan), stage_ms[0] / args.steps
     substeps_hist = np.bincount(np.abs(plan.substeps)).tolist()

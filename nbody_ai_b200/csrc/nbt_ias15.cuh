@@ -58,6 +58,7 @@ struct nbt_ias15 {
     double t, dt, dt_last;
     int have_b;
     long long n_steps, n_reject, max_steps;
+    double dt_floor;   // give up below this adaptive step (0 = never): see nbt_simulate_system_ias15
     bool gave_up;
 };
 
@@ -124,6 +125,7 @@ NBT_HD void nbt_ias15_setup(const double* par, nbt_ias15<NB>& I) {
     I.t = 0.0; I.dt = 1e-3; I.dt_last = 0.0;   // REBOUND's default initial dt
     I.have_b = 0; I.n_steps = 0; I.n_reject = 0; I.gave_up = false;
     I.max_steps = 2000000000LL;
+    I.dt_floor = 0.0;
 }
 
 // one step of size dt; true if accepted (state advanced), false if rejected (I.dt shrunk)
@@ -245,7 +247,7 @@ NBT_HD void nbt_ias15_integrate_to(nbt_ias15<NB>& I, const nbt_ias15_tables& T, 
         const double keep = I.dt;
         bool shortened = false;
         if (dt >= remaining) { dt = remaining; shortened = true; }
-        if (!(dt > 0.0) || !isfinite(dt)) { I.gave_up = true; return; }
+        if (!(dt > 0.0) || !isfinite(dt) || (!shortened && dt < I.dt_floor)) { I.gave_up = true; return; }
         if (nbt_ias15_step<NB>(I, T, dt) && shortened) { I.t = t_end; I.dt = keep; }
     }
 }
@@ -376,14 +378,18 @@ NBT_HD void nbt_simulate_system_ias15(const nbt_run_args& A, const nbt_ias15_tab
     const int NO = (A.n_outputs_sys != nullptr) ? A.n_outputs_sys[sys] : A.n_outputs;
     const double n_days = (A.n_days_sys != nullptr) ? A.n_days_sys[sys] : A.n_days;
     const double step = n_days / (double)(NO - 1);
-    {   // step budget: one step per output plus ~25 per innermost orbit is what a regular system needs; a pair on a collision
-        // course drives the adaptive step towards zero — the run is given up (NBT_S_NONFINITE) at 16x that
+    {   // step budget: one step per output plus ~25 per innermost orbit is what a regular system needs, and a scattering
+        // event a few hundred more; a captured pair (two planets orbiting each other) keeps the adaptive step small for
+        // good — the run is given up (NBT_S_NONFINITE) at 2 per output + 100 per innermost orbit.  (REBOUND has no budget
+        // and would crawl on; such a system is chaotic and excluded from any comparison.)  The step floor only guards
+        // against a collapse to zero: 1e-9 P_min is two point masses a few km apart.
         double pmin = INFINITY;
         for (int i = 1; i <= NP; i++) {
             const double P = par[i * NBT_NPAR + NBT_P_P];
             if (P > 0.0 && P < pmin) pmin = P;
         }
-        I.max_steps = 2LL * NO + 10000LL + (isfinite(pmin) ? (long long)(400.0 * n_days / pmin) : 0LL);
+        I.max_steps = 2LL * NO + 10000LL + (isfinite(pmin) ? (long long)(100.0 * n_days / pmin) : 0LL);
+        I.dt_floor = isfinite(pmin) ? 1e-9 * pmin : 0.0;
     }
     nbt_sampler<NP> Q;
     nbt_sampler_init<NP>(Q);
