@@ -15,8 +15,12 @@ owns 70 000 systems.
 `value` is whole-job TTV sims/s with inputs resident in HBM (torch device tensors, kernels enqueued through the C ABI
 with NBT_F_DEVICE_PTRS).  `e2e` is the same through the public host-buffer call a user makes: every step PLANS the
 batch anew (engine.Plan -> nbt_plan: sub-steps, launch order, CSR layout — a sampler's or the training-set
-generator's parameters change from call to call), copies the parameter block and plan H2D from pinned memory,
-runs the kernels and copies every product D2H into pinned buffers (nbt_run).
+generator's parameters change from call to call), copies the parameter block and plan H2D from page-locked memory,
+runs the kernels and copies every product D2H into page-locked buffers (nbt_run) — with two steps in flight
+(engine.Pipeline: two host threads, one stream and one buffer pool each), so that one step's planning and copies
+overlap the next one's kernels; for N > 1 the buffers are shared-memory segments and a reader on rank 0 consumes every
+rank's every step in place (the final host gather, inside the timed region).  `e2e_sequential` is the same one step at
+a time, `e2e_peaks` with the periodograms reduced to their peaks on the device.
 
 `north_star` block (BASELINE.json's target: >= 1e11 system-steps/s on 8 GPUs for 3-planet systems at >= 50 % of the
 FP64 roofline; config 5 sharded over 1/2/4/8): three more device-timed workloads, each with system-steps/s, sims/s and
@@ -353,93 +357,137 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the host-pointer C ABI: plan + H2D + kernels + D2H every step --------------------
     # N = 1: a fresh parameter block every step (other seeds of the same workload), so nothing of a plan can be reused;
-    # N > 1: the rank's shard is planned anew every step
-    # N > 1 also times the final host gather: every rank's buffers live in a page-locked shared-memory segment
-    # (engine.SharedHostPool) that rank 0 maps, so the gather is a barrier after which rank 0 reads all shards in place
-    # (it sums every shard's transit counts as proof)
+    # N > 1: the rank's shard is planned anew every step.
+    #   e2e            the throughput form: engine.Pipeline keeps 2 steps in flight (2 host threads, each with its own
+    #                  stream and page-locked pool), so one step's planning and copies overlap the next one's kernels.
+    #                  N > 1 also times the final host gather: the pools are shared-memory segments that rank 0 maps
+    #                  (engine.SharedHostPool); a reader thread on rank 0 consumes every rank's every step in place (it
+    #                  sums the transit counts as proof) and acknowledges it before the segment is reused
+    #   e2e_sequential one step at a time (plan, nbt_run, next), per-rank pinned pool, no gather — a sampler's view
+    #   e2e_peaks      sequential, periodograms reduced to their peaks on the device (NBT_F_LS_PEAKS)
     n_sets = 1 if world > 1 else min(max(args.steps, 1), 4)
     param_sets = [params] + [workloads.c2_params(args.draws, args.omegas, seed=100 + i) for i in range(1, n_sets)]
-    gather_note, seg = None, None
-    pool = None
-    if world > 1:
-        seg = "nbt_bench_%s_%%d" % os.environ.get("MASTER_PORT", "0")
-        try:
-            need = sum(a.nbytes for a in (plan.params, plan.substeps, plan.tt_offsets, plan.ls_offsets) if a is not None) * 2
-            need += 8 * (2 * int(plan.tt_offsets[-1]) + int(plan.ls_offsets[-1]) + 16 * B * Np) + (4 << 20)
-            try:
-                os.unlink(os.path.join(engine.SharedHostPool.DIR, seg % rank))
-            except OSError:
-                pass
-            pool = engine.SharedHostPool(seg % rank, int(1.2 * need))
-            gather_note = "zero-copy: per-rank page-locked shared-memory segments (engine.SharedHostPool), barrier, rank 0 reads every shard in place"
-        except Exception as exc:      # no /dev/shm or registration refused: per-rank pinned buffers, gather not timed
-            pool, gather_note = None, "unavailable (%s): per-rank pinned buffers only" % exc
-        ok = torch.tensor([1.0 if pool is not None else 0.0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok.item()) == 0.0 and pool is not None:
-            pool.close()
-            pool, gather_note = None, "unavailable on another rank: per-rank pinned buffers only"
-    shared = pool is not None
-    if pool is None:
-        pool = engine.BufferPool(pinned=True)
-    gathered = [0]
+    plan_threads = max(1, min(8, (os.cpu_count() or 8) // world))
+    depth = 2
+    names = ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega", "status",
+             "ls_oc_power", "ls_oc_nfreq", "ls_oc_peaks")
 
-    def e2e_step(k):
-        if shared:
-            pool.reset()
+    # -- sequential
+    pool = engine.BufferPool(pinned=True)
+
+    def seq_step(k, fl, skip=()):
         tp = time.perf_counter()
-        p = engine.Plan(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=flags, device=local_rank, pool=pool)
+        p = engine.Plan(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=fl, device=local_rank, pool=pool, threads=plan_threads)
         tp = time.perf_counter() - tp
-        buf = engine.run(p, pool.buffers_for(p))        # H2D + kernels + D2H + stream sync inside
-        if shared:
-            pool.publish(p, buf, extra={"index": mine.astype(np.int64)})
-            dist.barrier()                              # the final host gather
-            if rank == 0:
-                tot = 0
-                for r in range(world):
-                    sh = engine.SharedHostPool.attach(seg % r)
-                    tot += int(sh["n_tt"].sum()) + int(sh["status"].shape[0]) + int(sh["ls_oc_power"].shape[0] > 0)
-                    del sh
-                gathered[0] = tot
-            dist.barrier()                              # the segments are free for the next step
-        return p, buf, tp
+        return p, engine.run(p, pool.buffers_for(p, skip=skip)), tp     # H2D + kernels + D2H + stream sync inside
 
     for k in range(max(min(args.warmup, 2), n_sets)):        # every set once: the pool reaches its final size
-        e2e_step(k)
+        seq_step(k, flags)
     barrier()
     plan_s = 0.0
     t0 = time.perf_counter()
     for k in range(args.steps):
-        p, hbuf, tp = e2e_step(k)
+        p, hbuf, tp = seq_step(k, flags)
         plan_s += tp
     torch.cuda.synchronize(dev)
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_seq_ms = (time.perf_counter() - t0) * 1e3
     h2d = sum(a.nbytes for a in (p.params, p.substeps, p.order, p.tt_offsets, p.ls_offsets) if a is not None)
-    names = ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega", "status",
-             "ls_oc_power", "ls_oc_nfreq", "ls_oc_peaks")
     d2h = sum(getattr(hbuf, n).nbytes for n in names if getattr(hbuf, n) is not None)
-    # the same with the periodograms reduced to their three highest peaks on the device (NBT_F_LS_PEAKS; what a caller
-    # like simulation_grid.py needs of them): the power arrays — two thirds of the D2H bytes — never leave the GPU
-    pool2 = engine.BufferPool(pinned=True)
+    # -- sequential, periodograms reduced to peaks on the device: the power arrays (two thirds of the D2H bytes) stay there
     lean = ("ls_oc_power", "ls_oc_nfreq")
-
-    def peaks_step(k):
-        q = engine.Plan(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=flags | _abi.F_LS_PEAKS, device=local_rank, pool=pool2)
-        return engine.run(q, pool2.buffers_for(q, skip=lean))
-
     for k in range(n_sets):
-        peaks_step(k)
+        seq_step(k, flags | _abi.F_LS_PEAKS, lean)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        pbuf = peaks_step(k)
+        _, pbuf, _ = seq_step(k, flags | _abi.F_LS_PEAKS, lean)
     torch.cuda.synchronize(dev)
     e2e_peaks_ms = (time.perf_counter() - t0) * 1e3
     d2h_peaks = sum(getattr(pbuf, n).nbytes for n in names if getattr(pbuf, n) is not None)
-    del pool2, pbuf
+    del p, hbuf, pbuf, pool
+
+    # -- pipelined (+ shared-memory gather for N > 1)
+    gather_note, pools, seg = "single rank: results are in the caller's buffers", None, None
+    if world > 1:
+        seg = "nbt_bench_%s_%%d_%%d" % os.environ.get("MASTER_PORT", "0")
+        try:
+            need = sum(a.nbytes for a in (plan.params, plan.substeps, plan.tt_offsets, plan.ls_offsets) if a is not None) * 2
+            need += 8 * (2 * int(plan.tt_offsets[-1]) + int(plan.ls_offsets[-1]) + 16 * B * Np) + (4 << 20)
+            pools = []
+            for w in range(depth):
+                try:
+                    os.unlink(os.path.join(engine.SharedHostPool.DIR, seg % (rank, w)))
+                except OSError:
+                    pass
+                pools.append(engine.SharedHostPool(seg % (rank, w), int(1.2 * need)))
+            gather_note = ("zero-copy: every rank's buffers are page-locked shared-memory segments (engine.SharedHostPool, %d per rank); a reader "
+                           "thread on rank 0 consumes every step of every rank in place and acknowledges it" % depth)
+        except Exception as exc:      # no /dev/shm or registration refused: per-rank pinned buffers, gather not timed
+            for q in pools or []:
+                q.close()
+            pools, gather_note = None, "unavailable (%s): per-rank pinned buffers only" % exc
+        ok = torch.tensor([1.0 if pools is not None else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0 and pools is not None:
+            for q in pools:
+                q.close()
+            pools, gather_note = None, "unavailable on another rank: per-rank pinned buffers only"
+    shared = pools is not None
+    consumed, stop_reader, reader = [0, 0], [False], None
     if shared:
-        del p, hbuf
-        pool.close()
+        dist.barrier()                                  # every segment exists
+        if rank == 0:
+            def read_all():
+                views = {}
+                while not stop_reader[0]:
+                    idle = True
+                    for r in range(world):
+                        for w in range(depth):
+                            v = views.get((r, w))
+                            if v is None or v["_hdr"][1] > v["_hdr"][2]:
+                                v = engine.SharedHostPool.attach(seg % (r, w), ack=True)
+                                views[(r, w)] = v
+                            if v["seq"] > int(v["_hdr"][2]):
+                                consumed[1] += int(v["n_tt"].sum()) + int(v["status"].shape[0]) + int(v["ls_oc_power"][-1] == v["ls_oc_power"][-1])
+                                engine.SharedHostPool.acknowledge(v)
+                                consumed[0] += 1
+                                idle = False
+                    if idle:
+                        time.sleep(2e-4)
+            reader = threading.Thread(target=read_all, daemon=True)
+            reader.start()
+
+    def publish(pl, bf, pl_pool):
+        pl_pool.publish(pl, bf, extra={"index": mine.astype(np.int64)})
+
+    pipe = engine.Pipeline(depth=depth, device=local_rank, pools=pools, threads=plan_threads)
+
+    def pipelined(n):
+        futs = [pipe.submit(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=flags, on_done=publish if shared else None) for k in range(n)]
+        for f in futs:
+            f.result()
+
+    n_warm = max(2 * depth, n_sets)
+    pipelined(n_warm)
+    barrier()
+    t0 = time.perf_counter()
+    pipelined(args.steps)
+    if shared:
+        if rank == 0:                                   # the gather is complete when rank 0 has read every step of every rank
+            while consumed[0] < world * (n_warm + args.steps):
+                time.sleep(2e-4)
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    pipe.close()
+    stop_reader[0] = True
+    if reader is not None:
+        reader.join()
+    if shared:
+        dist.barrier()
+        for q in pools:
+            q.close()
+    del pipe, pools
 
     # sanity: the timed device path and the host path produced the same transits
     chk = dbuf.to_host()
@@ -448,9 +496,9 @@ def run_ours(args, rank, world, local_rank):
     n_tt_total = int(np.minimum(ref_run.n_tt, np.diff(plan.tt_offsets)).sum())
     del chk, ref_run
 
-    my_dev_ms, my_e2e_ms = dev_ms, e2e_ms          # this rank's own times (the `ranks` table), before the max over ranks
-    (dev_ms, e2e_ms, integ_ms, e2e_peaks_ms), (sims_all, steps_all, ntt_all) = reduce_max_sum(
-        [dev_ms, e2e_ms, stage_ms[0], e2e_peaks_ms], [float(B), float(plan.n_steps), float(n_tt_total)])
+    my_dev_ms, my_e2e_ms = dev_ms, e2e_seq_ms      # this rank's own times (the `ranks` table), before the max over ranks
+    (dev_ms, e2e_ms, integ_ms, e2e_peaks_ms, e2e_seq_ms), (sims_all, steps_all, ntt_all) = reduce_max_sum(
+        [dev_ms, e2e_ms, stage_ms[0], e2e_peaks_ms, e2e_seq_ms], [float(B), float(plan.n_steps), float(n_tt_total)])
     # per-rank view (diagnosis of the max-over-ranks figure): step time, e2e time, SM clock, power-cap flag
     mine_t = torch.tensor([my_dev_ms / args.steps, my_e2e_ms / args.steps, clocks["sm_mhz"] or 0.0,
                          1.0 if "sw_power_cap" in clocks["reasons"] else 0.0], dtype=torch.float64, device=dev)
@@ -462,7 +510,7 @@ def run_ours(args, rank, world, local_rank):
     main_flops, main_launch_ms = survey_flops(plan), stage_ms[0] / args.steps
     substeps_hist = np.bincount(np.abs(plan.substeps)).tolist()
     c4_systems = int((plan.substeps < 0).sum())
-    del dbuf, pool, param_sets
+    del dbuf, param_sets
     torch.cuda.empty_cache()
 
     # ---- north-star block -------------------------------------------------------------------------------------
@@ -534,7 +582,7 @@ def run_ours(args, rank, world, local_rank):
             "details": {"scheme": "auto: sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks); c4 (2-stage force-gradient) where P_min >= 250 output steps",
                         "substeps_hist": substeps_hist, "c4_systems": c4_systems,
                         "shards": "cost-balanced (engine.shard_balanced) of one global batch" if world > 1 else "one batch", "cpu_affinity": affinity,
-                        "e2e": "every step: engine.Plan (nbt_plan host planner) on %s + nbt_run with pinned host buffers" % ("a fresh parameter block (%d seeds in rotation)" % n_sets if n_sets > 1 else "the rank's shard")},
+                        "e2e": "every step: engine.Plan (nbt_plan host planner, %d threads) on %s + nbt_run with page-locked host buffers; e2e = engine.Pipeline, %d steps in flight; e2e_sequential = one at a time" % (plan_threads, "a fresh parameter block (%d seeds in rotation)" % n_sets if n_sets > 1 else "the rank's shard", depth)},
             "system_steps_per_s": steps_per_s,
             "system_steps_per_step": steps_all,
             "transits_per_step": ntt_all,
@@ -549,14 +597,18 @@ def run_ours(args, rank, world, local_rank):
                          "flops_per_launch": main_flops, "launch_ms": main_launch_ms, "traffic": ncu_traffic(Np, B),
                          "hbm": hbm_side(ncu_traffic(Np, B), main_launch_ms)},
             "e2e": {"value": sims_all * args.steps / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps, "host_plan_ms_per_step_rank0": 1e3 * plan_s / args.steps,
-                    "final_host_gather": gather_note if world > 1 else "single rank: results are in the caller's buffers"},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps, "steps_in_flight": depth,
+                    "final_host_gather": gather_note},
+            "e2e_sequential": {"value": sims_all * args.steps / (e2e_seq_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
+                               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_seq_ms / args.steps,
+                               "host_plan_ms_per_step_rank0": 1e3 * plan_s / args.steps,
+                               "note": "one step at a time: plan, nbt_run (H2D + kernels + D2H + sync), next; per-rank pinned buffers, no gather"},
             "e2e_peaks": {"value": sims_all * args.steps / (e2e_peaks_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                           "d2h_bytes_per_step": int(d2h_peaks), "ms_per_step": e2e_peaks_ms / args.steps,
-                          "note": "as e2e, with NBT_F_LS_PEAKS: each O-C periodogram reduced to its 3 highest peaks on the device, power arrays not copied back"},
+                          "note": "as e2e_sequential, with NBT_F_LS_PEAKS: each O-C periodogram reduced to its 3 highest peaks on the device, power arrays not copied back"},
             "gpu_launches": 3 * args.steps + launches_extra,   # k_integrate, k_fit, k_ls_oc per timed device step (+ the north-star passes)
             "clocks": clocks,
-            "ranks": {"columns": ["ms_per_step", "e2e_ms_per_step", "sm_mhz", "sw_power_cap"], "rows": per_rank},
+            "ranks": {"columns": ["ms_per_step", "e2e_sequential_ms_per_step", "sm_mhz", "sw_power_cap"], "rows": per_rank},
             "north_star": north,
         }
         if world == 1 and not args.no_cpu:

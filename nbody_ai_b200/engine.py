@@ -395,9 +395,21 @@ class SharedHostPool(BufferPool):
                 a = b
             entries[n] = (a.ctypes.data - lo, a.shape, a.dtype.str)
         blob = pickle.dumps(dict(B=plan.B, Np=plan.Np, flags=int(plan.cfg.flags), arrays=entries))
-        assert len(blob) + 8 <= self.HEADER
-        self.base[8:8 + len(blob)] = np.frombuffer(blob, dtype=np.uint8)
-        self.base[:8].view(np.int64)[0] = len(blob)
+        assert len(blob) + 64 <= self.HEADER
+        self.base[64:64 + len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+        hdr = self.base[:24].view(np.int64)          # [0] directory bytes, [1] steps published, [2] steps consumed (reader's ack)
+        hdr[0] = len(blob)
+        hdr[1] += 1                                  # after the directory and the data: a reader that sees it sees them
+
+    def wait_consumed(self, timeout=60.0):
+        """Block until the reader has acknowledged everything published so far (before the segment is reused)."""
+        import time
+        hdr = self.base[:24].view(np.int64)
+        t0 = time.perf_counter()
+        while hdr[2] < hdr[1]:
+            if time.perf_counter() - t0 > timeout:
+                raise TimeoutError("SharedHostPool %s: reader did not acknowledge step %d" % (self.name, int(hdr[1])))
+            time.sleep(2e-4)
 
     def close(self):
         """Unregister and unlink the segment (the mapping itself goes with the last view of it)."""
@@ -413,24 +425,35 @@ class SharedHostPool(BufferPool):
             pass
 
     @staticmethod
-    def attach(name):
-        """Read-only view of another rank's published step: dict of arrays (views into the shared segment) + B, Np."""
+    def attach(name, ack=False):
+        """View of another rank's published step: dict of arrays (views into the shared segment) + B, Np, and `seq`, the
+        number of steps published so far.  ack=True maps the segment writable so that acknowledge() can tell the owner
+        that the step has been consumed (see wait_consumed)."""
         import mmap
         import os
         import pickle
-        fd = os.open(os.path.join(SharedHostPool.DIR, name), os.O_RDONLY)
+        fd = os.open(os.path.join(SharedHostPool.DIR, name), os.O_RDWR if ack else os.O_RDONLY)
         try:
-            shm = mmap.mmap(fd, 0, prot=mmap.PROT_READ)
+            shm = mmap.mmap(fd, 0, prot=(mmap.PROT_READ | mmap.PROT_WRITE) if ack else mmap.PROT_READ)
         finally:
             os.close(fd)
         base = np.frombuffer(shm, dtype=np.uint8)
-        n = int(base[:8].view(np.int64)[0])
-        meta = pickle.loads(base[8:8 + n].tobytes())
-        out = dict(B=meta["B"], Np=meta["Np"], flags=meta["flags"], _shm=shm)
+        hdr = base[:24].view(np.int64)
+        out = dict(seq=int(hdr[1]), _shm=shm, _hdr=hdr)
+        if out["seq"] == 0:
+            return out
+        n = int(hdr[0])
+        meta = pickle.loads(base[64:64 + n].tobytes())
+        out.update(B=meta["B"], Np=meta["Np"], flags=meta["flags"])
         for k, (off, shape, dt) in meta["arrays"].items():
             cnt = int(np.prod(shape)) * np.dtype(dt).itemsize
             out[k] = base[SharedHostPool.HEADER + off:SharedHostPool.HEADER + off + cnt].view(np.dtype(dt)).reshape(shape)
         return out
+
+    @staticmethod
+    def acknowledge(view):
+        """Reader side: everything published up to view['seq'] has been consumed (needs attach(..., ack=True))."""
+        view["_hdr"][2] = view["seq"]
 
 
 def run(plan, buffers=None, stream=None):
@@ -444,6 +467,67 @@ def run(plan, buffers=None, stream=None):
     rc = lib.nbt_run(C.byref(cfg), C.byref(inp), C.byref(out), C.c_void_p(stream or 0))
     _abi.check(rc, lib)
     return buffers
+
+
+class Pipeline:
+    """`depth` nbt_run calls in flight from `depth` host threads: ctypes releases the GIL inside libnbt (nbt_plan and
+    nbt_run alike), every worker has its own CUDA stream and its own page-locked pool, so the planning and the H2D / D2H
+    copies of one batch overlap the kernels of the next — the throughput form of the host-buffer path for callers whose
+    batches do not depend on each other (the training-set generator, grids, a sampler's independent walkers).
+
+        pipe = Pipeline(depth=2, device=0)
+        futures = [pipe.submit(params_k, n_days, n_outputs, flags=...) for params_k in batches]
+        plan, buffers = futures[0].result()
+
+    A result stays valid until its worker serves another batch, i.e. until `depth` more submissions; `on_done(plan,
+    buffers, worker_pool)` runs in the worker right after nbt_run (e.g. SharedHostPool.publish).  pools: one pool per
+    worker (default: pinned BufferPools)."""
+
+    def __init__(self, depth=2, device=0, pools=None, threads=0):
+        import queue
+        import threading
+        import torch
+        self.depth, self.device, self.threads = depth, device, threads
+        self.pools = pools if pools is not None else [BufferPool(pinned=True) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
+        self.jobs = [queue.Queue() for _ in range(depth)]
+        self.next = 0
+        self.workers = [threading.Thread(target=self._work, args=(w,), daemon=True) for w in range(depth)]
+        for t in self.workers:
+            t.start()
+
+    def _work(self, w):
+        pool, stream = self.pools[w], self.streams[w].cuda_stream
+        while True:
+            job = self.jobs[w].get()
+            if job is None:
+                return
+            fut, params, n_days, n_outputs, kw, skip, on_done = job
+            try:
+                if hasattr(pool, "wait_consumed"):
+                    pool.wait_consumed()
+                    pool.reset()
+                plan = Plan(params, n_days, n_outputs, device=self.device, pool=pool, threads=self.threads, **kw)
+                buf = run(plan, pool.buffers_for(plan, skip=skip), stream=stream)
+                if on_done is not None:
+                    on_done(plan, buf, pool)
+                fut.set_result((plan, buf))
+            except BaseException as exc:      # surfaced by Future.result() in the caller's thread
+                fut.set_exception(exc)
+
+    def submit(self, params, n_days, n_outputs, skip=(), on_done=None, **plan_kw):
+        """Queue one batch (round-robin over the workers); returns a concurrent.futures.Future of (plan, buffers)."""
+        from concurrent.futures import Future
+        fut = Future()
+        self.jobs[self.next].put((fut, params, n_days, n_outputs, plan_kw, skip, on_done))
+        self.next = (self.next + 1) % self.depth
+        return fut
+
+    def close(self):
+        for q in self.jobs:
+            q.put(None)
+        for t in self.workers:
+            t.join()
 
 
 def run_batch(params, n_days, n_outputs, **kw):

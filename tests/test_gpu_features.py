@@ -289,3 +289,23 @@ def test_solar_system_amplitude_ranges(gpu_lib):
     assert list(got.n_tt[:4]) == [4149, 1625, 1000, 532] or np.all(np.abs(got.n_tt[:4] - [4149, 1625, 1000, 532]) <= 1)
     for j, (lo, hi) in enumerate([(0.5, 2.0), (3.0, 6.0), (4.0, 8.0), (20.0, 55.0), (300.0, 3000.0), (800.0, 8000.0)]):
         assert lo < amp[j] < hi, (j, amp[j])
+
+
+def test_pipeline_matches_sequential_runs(gpu_lib):
+    """engine.Pipeline (two nbt_run calls in flight from two host threads, own streams and pinned pools): every batch's
+    products are bit-identical to a plain engine.run of the same batch, also for ragged sizes and mixed flags."""
+    batches = [workloads.c2_params(30 + 7 * k, 2, seed=40 + k) for k in range(5)]
+    pipe = engine.Pipeline(depth=2)
+    try:
+        for start in (0, 2):                      # results stay valid for `depth` submissions: check them pairwise
+            futs = [pipe.submit(batches[k], 120.0, 2881, flags=FULL) for k in range(start, min(start + 2, 5))]
+            for k, f in zip(range(start, start + 2), futs):
+                plan, buf = f.result()
+                want = engine.run(engine.Plan(batches[k], 120.0, 2881, flags=FULL))
+                for name in ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_omega", "status", "ls_oc_power"):
+                    assert np.array_equal(getattr(buf, name), getattr(want, name), equal_nan=True), (k, name)
+        plan, buf = pipe.submit(batches[4], 60.0, 1441, flags=_abi.F_PLANET1_ONLY).result()
+        want = engine.run(engine.Plan(batches[4], 60.0, 1441, flags=_abi.F_PLANET1_ONLY))
+        assert np.array_equal(buf.tt, want.tt, equal_nan=True) and np.array_equal(buf.n_tt, want.n_tt)
+    finally:
+        pipe.close()

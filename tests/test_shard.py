@@ -110,7 +110,8 @@ def _shared_worker(rank, world, port, q, tag):
             n_tt = np.zeros((len(par), 2), dtype=np.int32)
             mean_a, first_tt = np.zeros((len(par), 2)), np.full((len(par), 2), np.nan)
             for r in range(world):
-                sh = engine.SharedHostPool.attach("%s_%d" % (tag, r))
+                sh = engine.SharedHostPool.attach("%s_%d" % (tag, r), ack=True)
+                assert sh["seq"] == step + 1
                 idx = sh["index"]
                 n_tt[idx] = sh["n_tt"].reshape(-1, 2)
                 mean_a[idx] = sh["mean_a"].reshape(-1, 2)
@@ -118,7 +119,9 @@ def _shared_worker(rank, world, port, q, tag):
                     for j in range(2):
                         if sh["n_tt"][q_ * 2 + j]:
                             first_tt[b, j] = sh["tt"][sh["tt_offsets"][q_ * 2 + j]]
+                engine.SharedHostPool.acknowledge(sh)
                 del sh
+        pool.wait_consumed()                      # the owner may reuse its segment once the reader has acknowledged
         dist.barrier()
     if rank == 0:
         q.put({"n_tt": n_tt, "mean_a": mean_a, "first_tt": first_tt})
