@@ -13,11 +13,14 @@ periodogram, means of a/e/inc/omega.  A step is one pass of the whole path over 
 owns 70 000 systems.
 
 `value` is whole-job TTV sims/s with inputs resident in HBM (torch device tensors, kernels enqueued through the C ABI
-with NBT_F_DEVICE_PTRS).  `e2e` is the same through the public host-buffer call a user makes: every step PLANS the
+with NBT_F_DEVICE_PTRS), K steps with two in flight: two CUDA streams and two buffer sets alternate, so that the tail of
+one heterogeneous launch — its few long systems — is filled by the blocks of the next step.  `value_single_stream`
+times the same steps one at a time; that region also gives the per-kernel CUDA-event times of `stage_ms_per_step` and
+the roofline's launch duration.  `e2e` is the same through the public host-buffer call a user makes: every step PLANS the
 batch anew (engine.Plan -> nbt_plan: sub-steps, launch order, CSR layout — a sampler's or the training-set
 generator's parameters change from call to call), copies the parameter block and plan H2D from page-locked memory,
-runs the kernels and copies every product D2H into page-locked buffers (nbt_run) — with two steps in flight
-(engine.Pipeline: two host threads, one stream and one buffer pool each), so that one step's planning and copies
+runs the kernels and copies every product D2H into page-locked buffers (nbt_run) — with several steps in flight
+(engine.Pipeline: 4 host threads for N <= 2, else 3, one stream and one buffer pool each), so that one step's planning and copies
 overlap the next one's kernels; for N > 1 the buffers are shared-memory segments and a reader on rank 0 consumes every
 rank's every step in place (the final host gather, inside the timed region).  `e2e_sequential` is the same one step at
 a time, `e2e_peaks` with the periodograms reduced to their peaks on the device.
@@ -59,7 +62,7 @@ def base_config(args, world):
     return {"workload": WORKLOAD, "systems_per_gpu": args.draws * (args.omegas + 1), "draws": args.draws,
             "omega_variants": args.omegas, "n_planets": 2, "n_days": N_DAYS, "n_outputs": N_OUTPUTS,
             "parallelism": "shard-by-system x%d" % world,
-            "l2": "256 MiB device fill between steps, outside the per-step event pairs"}
+            "l2": "256 MiB device fill (> 126 MB L2) in front of every timed step; every step also writes 340 MB of products"}
 
 
 def f_step(np_):
@@ -351,14 +354,45 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     time.sleep(0.3)
 
-    # ---- timed region: K steps, device-resident ------------------------------------------
-    dev_ms, stage_ms = timer(plan, dbuf, args.steps, 0)
+    # ---- timed region 1: K steps one at a time on one stream (per-kernel CUDA events: the roofline's launch time) ------
+    seq_ms, stage_ms = timer(plan, dbuf, args.steps, 0)
+
+    # ---- timed region 2 (`value`): the same K steps with TWO in flight — two streams, two buffer sets alternating — so
+    # that the tail of one heterogeneous launch (its few long systems) is filled by the next step's blocks.  N = 1: the
+    # second set is another seed of the workload; N > 1: the rank's shard again.  One event pair around the region.
+    plan_b = plan if world > 1 else engine.Plan(workloads.c2_params(args.draws, args.omegas, seed=1), N_DAYS, N_OUTPUTS,
+                                                flags=flags, device=local_rank)
+    sets = [(plan, dbuf), (plan_b, engine.DeviceBuffers(plan_b))]
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+
+    def overlapped(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream(dev)
+        e0.record(cur)
+        for st_ in streams:
+            st_.wait_event(e0)
+        for k in range(n):
+            with torch.cuda.stream(streams[k % 2]):
+                flush.fill_(k & 0xFF)                  # L2 flush in front of every step, on the step's own stream
+                engine.run_device(*sets[k % 2])
+        for st_ in streams:
+            cur.wait_stream(st_)
+        e1.record(cur)
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    overlapped(4)
+    barrier()
+    dev_ms = overlapped(args.steps)
+    barrier()
+    steps_timed = sum(sets[k % 2][0].n_steps for k in range(args.steps))
     clocks = sampler.finish()
+    del sets, streams
 
     # ---- end to end through the host-pointer C ABI: plan + H2D + kernels + D2H every step --------------------
     # N = 1: a fresh parameter block every step (other seeds of the same workload), so nothing of a plan can be reused;
     # N > 1: the rank's shard is planned anew every step.
-    #   e2e            the throughput form: engine.Pipeline keeps 2 steps in flight (2 host threads, each with its own
+    #   e2e            the throughput form: engine.Pipeline keeps --e2e-depth steps in flight (host threads, each with its own
     #                  stream and page-locked pool), so one step's planning and copies overlap the next one's kernels.
     #                  N > 1 also times the final host gather: the pools are shared-memory segments that rank 0 maps
     #                  (engine.SharedHostPool); a reader thread on rank 0 consumes every rank's every step in place (it
@@ -368,7 +402,7 @@ def run_ours(args, rank, world, local_rank):
     n_sets = 1 if world > 1 else min(max(args.steps, 1), 4)
     param_sets = [params] + [workloads.c2_params(args.draws, args.omegas, seed=100 + i) for i in range(1, n_sets)]
     plan_threads = max(1, min(8, (os.cpu_count() or 8) // world))
-    depth = 2
+    depth = max(1, args.e2e_depth if args.e2e_depth > 0 else (4 if world <= 2 else 3))
     names = ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega", "status",
              "ls_oc_power", "ls_oc_nfreq", "ls_oc_peaks")
 
@@ -497,8 +531,8 @@ def run_ours(args, rank, world, local_rank):
     del chk, ref_run
 
     my_dev_ms, my_e2e_ms = dev_ms, e2e_seq_ms      # this rank's own times (the `ranks` table), before the max over ranks
-    (dev_ms, e2e_ms, integ_ms, e2e_peaks_ms, e2e_seq_ms), (sims_all, steps_all, ntt_all) = reduce_max_sum(
-        [dev_ms, e2e_ms, stage_ms[0], e2e_peaks_ms, e2e_seq_ms], [float(B), float(plan.n_steps), float(n_tt_total)])
+    (dev_ms, e2e_ms, integ_ms, e2e_peaks_ms, e2e_seq_ms, seq_ms), (sims_all, steps_all, ntt_all, steps_one) = reduce_max_sum(
+        [dev_ms, e2e_ms, stage_ms[0], e2e_peaks_ms, e2e_seq_ms, seq_ms], [float(B), float(steps_timed), float(n_tt_total), float(plan.n_steps)])
     # per-rank view (diagnosis of the max-over-ranks figure): step time, e2e time, SM clock, power-cap flag
     mine_t = torch.tensor([my_dev_ms / args.steps, my_e2e_ms / args.steps, clocks["sm_mhz"] or 0.0,
                          1.0 if "sw_power_cap" in clocks["reasons"] else 0.0], dtype=torch.float64, device=dev)
@@ -572,7 +606,7 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         sims_per_s = sims_all * args.steps / (dev_ms * 1e-3)
-        steps_per_s = steps_all * args.steps / (dev_ms * 1e-3)
+        steps_per_s = steps_all / (dev_ms * 1e-3)          # steps_all: system-steps of all K timed steps, all ranks
         achieved = main_flops / (main_launch_ms * 1e-3) * 1e-12
         line = {
             "metric": "ttv_sims_per_sec", "value": sims_per_s, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
@@ -581,10 +615,15 @@ def run_ours(args, rank, world, local_rank):
             "config": base_config(args, world),
             "details": {"scheme": "auto: sbabc3 (3-stage order (6,4) Wisdom-Holman composition with force-gradient end kicks); c4 (2-stage force-gradient) where P_min >= 250 output steps",
                         "substeps_hist": substeps_hist, "c4_systems": c4_systems,
+                        "value": "K steps with two in flight: two CUDA streams and two buffer sets alternate (the next step's blocks fill the tail of the current launch); a 256 MiB fill precedes every step on its stream; one event pair around the region.  value_single_stream: one at a time",
                         "shards": "cost-balanced (engine.shard_balanced) of one global batch" if world > 1 else "one batch", "cpu_affinity": affinity,
                         "e2e": "every step: engine.Plan (nbt_plan host planner, %d threads) on %s + nbt_run with page-locked host buffers; e2e = engine.Pipeline, %d steps in flight; e2e_sequential = one at a time" % (plan_threads, "a fresh parameter block (%d seeds in rotation)" % n_sets if n_sets > 1 else "the rank's shard", depth)},
+            "steps_in_flight": 2,
+            "value_single_stream": {"value": sims_all * args.steps / (seq_ms * 1e-3), "unit": "sims/s", "ms_per_step": seq_ms / args.steps,
+                                    "system_steps_per_s": steps_one * args.steps / (seq_ms * 1e-3),
+                                    "note": "the same K steps one at a time on one stream (what `stage_ms_per_step` and `roofline` time)"},
             "system_steps_per_s": steps_per_s,
-            "system_steps_per_step": steps_all,
+            "system_steps_per_step": steps_one,
             "transits_per_step": ntt_all,
             "stage_ms_per_step": {"k_integrate": stage_ms[0] / args.steps, "k_fit": stage_ms[1] / args.steps,
                                   "k_ls_oc": stage_ms[2] / args.steps},
@@ -595,6 +634,10 @@ def run_ours(args, rank, world, local_rank):
                          "peak_source": "nbt_fp64_peak DFMA-chain kernel measured in this run (nominal 37.2 at 1965 MHz)",
                          "peak_three_register_operands": fp64_peak_3reg,
                          "flops_per_launch": main_flops, "launch_ms": main_launch_ms, "traffic": ncu_traffic(Np, B),
+                         "launch_timing": "CUDA events around k_integrate on its launch stream (NBT_F_TIMING) in the single-stream region: one launch at a time",
+                         "two_steps_in_flight": {"achieved": main_flops * args.steps / (my_dev_ms * 1e-3) * 1e-12,
+                                                 "frac": main_flops * args.steps / (my_dev_ms * 1e-3) * 1e-12 / fp64_peak,
+                                                 "note": "k_integrate's FLOPs of the K steps / the elapsed time of the overlapped region (which also holds k_fit and k_ls_oc): the rate the FP64 pipe sustains once the tail of a launch is filled by the next"},
                          "hbm": hbm_side(ncu_traffic(Np, B), main_launch_ms)},
             "e2e": {"value": sims_all * args.steps / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps, "steps_in_flight": depth,
@@ -766,6 +809,7 @@ def main():
     ap.add_argument("--np3-random", type=int, default=75776, help="random 3-planet systems per GPU (148 x 512)")
     ap.add_argument("--c5-systems", type=int, default=1000000, help="C5 systems in total (sharded over the ranks); 0 = skip")
     ap.add_argument("--c5-passes", type=int, default=2)
+    ap.add_argument("--e2e-depth", type=int, default=0, help="steps the pipelined e2e keeps in flight (host threads / streams / buffer pools); 0 = 4 for N <= 2, else 3")
     ap.add_argument("--no-blocks", action="store_true", help="skip the C3 likelihood and training-set generator blocks (N = 1)")
     ap.add_argument("--c3-batch", type=int, default=5000)
     ap.add_argument("--c3-calls", type=int, default=10)

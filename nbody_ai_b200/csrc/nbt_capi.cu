@@ -1064,12 +1064,12 @@ static cudaError_t launch_special_np(int np, int scheme, const nbt_run_args& A, 
 
 // side streams per device: the lanes-kernel launches of a call (the long systems) run concurrently with
 // the one-thread-per-system launch; high priority, because the long systems should get their SMs first
+// (per calling thread: concurrent nbt_run calls from several host threads — engine.Pipeline — must not queue their
+// copies behind each other's events, nor wait for each other in cudaStreamSynchronize)
 struct SideStream { cudaStream_t st[2] = {nullptr, nullptr}; };
-static std::mutex g_side_mu;
-static SideStream g_side[64];
+static thread_local SideStream g_side[64];
 
 static cudaError_t get_side(int dev, SideStream** out) {
-    std::lock_guard<std::mutex> lk(g_side_mu);
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     SideStream& s = g_side[dev];
     for (int i = 0; i < 2; i++)

@@ -76,7 +76,7 @@ def summarise(w, units, keep):
     return out
 
 
-def sweep(par, n_days, n_outputs, label, flags=_abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, **plan_kw):
+def sweep(par, n_days, n_outputs, label, flags=_abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, dump=None, **plan_kw):
     plan = engine.Plan(par, n_days, n_outputs, flags=flags, **plan_kw)
     B, Np = plan.B, plan.Np
     t0 = time.time(); fast = engine.run(plan); t_fast = time.time() - t0
@@ -111,6 +111,10 @@ def sweep(par, n_days, n_outputs, label, flags=_abi.F_MEANS | _abi.F_MEAN_OMEGA 
                     mass_ratio=(par[b, 1:, 0] / par[b, 0, 0]).tolist(), e=par[b, 1:, 2].tolist(),
                     **{k: float(v[b]) for k, v in w.items()})
 
+    if dump is not None:
+        np.savez_compressed(dump, flagged=flagged, chaotic=chaotic, units_fast=uf, units_verified=uv, substeps=plan.substeps,
+                            status_fast=fast_copy.status, status_verified=ver.status, status_oracle=want.status,
+                            P=par[:, 1:, 1], m=par[:, 1:, 0], mstar=par[:, 0, 0], e=par[:, 1:, 2])
     return dict(
         label=label, n_systems=int(B), n_planets=int(Np), n_days=float(n_days), n_outputs=int(n_outputs),
         exclusion_rule="oracle self-sensitivity only (periods x (1 +- 1e-13): > 0.01 s in a transit time, > 1e-9 in a mean e, or the oracle run breaks)",
@@ -147,9 +151,9 @@ def main():
               r["fast"]["outside_tolerance_unflagged"], flush=True)
 
     if n:
-        add(sweep(workloads.random_systems(n, 2, seed=1001), 365.0, 8760, "C2 priors (randomize()), 2 planets, 365 d @ 1 h"))
+        add(sweep(workloads.random_systems(n, 2, seed=1001), 365.0, 8760, "C2 priors (randomize()), 2 planets, 365 d @ 1 h", dump=out[:-5] + "_c2.npz"))
     if n5:
-        add(sweep(workloads.random_systems(n5, 4, seed=1002), 1095.0, 26280, "C5 priors, 4 planets, 1095 d @ 1 h"))
+        add(sweep(workloads.random_systems(n5, 4, seed=1002), 1095.0, 26280, "C5 priors, 4 planets, 1095 d @ 1 h", dump=out[:-5] + "_c5.npz"))
     if npts:
         par, meta = workloads.c4_params(npts)
         add(sweep(par, meta["ndays"], meta["noutputs"], "C4 reference grid %d x %d (1 Msun, 10 Mearth, ratio 1.41-2.41), %d epochs @ 30 min" % (npts, npts, meta["epochs"]),
