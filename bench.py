@@ -649,7 +649,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e_peaks": {"value": sims_all * args.steps / (e2e_peaks_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                           "d2h_bytes_per_step": int(d2h_peaks), "ms_per_step": e2e_peaks_ms / args.steps,
                           "note": "as e2e_sequential, with NBT_F_LS_PEAKS: each O-C periodogram reduced to its 3 highest peaks on the device, power arrays not copied back"},
-            "gpu_launches": 3 * args.steps + launches_extra,   # k_integrate, k_fit, k_ls_oc per timed device step (+ the north-star passes)
+            "gpu_launches": 6 * args.steps + launches_extra,   # k_integrate, k_fit, k_ls_oc per step of the two device-timed regions (+ the north-star passes)
             "clocks": clocks,
             "ranks": {"columns": ["ms_per_step", "e2e_sequential_ms_per_step", "sm_mhz", "sw_power_cap"], "rows": per_rank},
             "north_star": north,

@@ -102,7 +102,7 @@ enum { NBT_F_MEANS = 1 << 0,       /* time means of Jacobi a, e, inc (analyze :2
 enum { NBT_S_NONFINITE = 1 << 0, NBT_S_UNBOUND = 1 << 1, NBT_S_KEPLER = 1 << 2,
        NBT_S_TT_OVERFLOW = 1 << 3, NBT_S_FEW_TRANSITS = 1 << 4,
        NBT_S_UNCALIBRATED = 1 << 5, /* outside the envelope the sub-step rule was calibrated on (a planet pair closer
-                                       than 4 mutual Hill radii, e > 0.1, or m_planet / m_star > 0.013): the fixed-step
+                                       than 4 mutual Hill radii, e > 0.1, or m_planet / m_star > 0.02): the fixed-step
                                        result may miss the parity tolerances; engine.run_verified checks such systems
                                        by step doubling and re-integrates the ones that need it */
        NBT_S_UNRESOLVED = 1 << 6 }; /* set by engine.run_verified: step doubling did not converge and no fallback ran */

@@ -154,7 +154,7 @@ class Plan:
 
     def uncalibrated(self):
         """Mask of the systems outside the envelope the sub-step rule was calibrated on (what nbt_run reports as
-        NBT_S_UNCALIBRATED: a pair inside 4 mutual Hill radii, e > 0.1 or m_planet / m_star > 0.013)."""
+        NBT_S_UNCALIBRATED: a pair inside 4 mutual Hill radii, e > 0.1 or m_planet / m_star > 0.02)."""
         lib = _abi.load()
         return np.array([lib.nbt_uncalibrated(_abi.ptr(self.params[b]), self.N) for b in range(self.B)], dtype=bool)
 

@@ -13,7 +13,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_in
 echo "ncu $case_name rc=$?"
 ncu -i $rep --page raw --csv > gpurun_out/${tag}_raw.csv 2>/dev/null
 ncu -i $rep --page source --csv > gpurun_out/${tag}_source.csv 2>/dev/null
-ncu -i $rep --page source --print-source cuda --csv > gpurun_out/${tag}_cuda.csv 2>/dev/null
 ls -la gpurun_out/${tag}_raw.csv gpurun_out/${tag}_source.csv
 [ -n "$keep" ] && [ "$(du -sm $rep | cut -f1)" -lt 30 ] && cp $rep gpurun_out/
 exit 0
