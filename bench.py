@@ -401,8 +401,8 @@ def run_ours(args, rank, world, local_rank):
     #   e2e_peaks      sequential, periodograms reduced to their peaks on the device (NBT_F_LS_PEAKS)
     n_sets = 1 if world > 1 else min(max(args.steps, 1), 4)
     param_sets = [params] + [workloads.c2_params(args.draws, args.omegas, seed=100 + i) for i in range(1, n_sets)]
-    plan_threads = max(1, min(8, (os.cpu_count() or 8) // world))
     depth = max(1, args.e2e_depth if args.e2e_depth > 0 else (4 if world <= 2 else 3))
+    plan_threads = max(1, min(8, (os.cpu_count() or 8) // (world * depth)))      # nbt_plan threads per call: no oversubscription
     names = ("tt", "ttv", "n_tt", "period", "t0", "ttv_max", "mean_a", "mean_e", "mean_inc", "mean_omega", "status",
              "ls_oc_power", "ls_oc_nfreq", "ls_oc_peaks")
 
