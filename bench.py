@@ -362,20 +362,22 @@ def run_ours(args, rank, world, local_rank):
     # second set is another seed of the workload; N > 1: the rank's shard again.  One event pair around the region.
     plan_b = plan if world > 1 else engine.Plan(workloads.c2_params(args.draws, args.omegas, seed=1), N_DAYS, N_OUTPUTS,
                                                 flags=flags, device=local_rank)
-    sets = [(plan, dbuf), (plan_b, engine.DeviceBuffers(plan_b))]
+    main_sets = [(plan, dbuf), (plan_b, engine.DeviceBuffers(plan_b))]
     streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
 
-    def overlapped(n):
+    def overlapped(n, sets=None, streams_=None):
+        sets = sets or main_sets
+        streams_ = streams_ or streams
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cur = torch.cuda.current_stream(dev)
         e0.record(cur)
-        for st_ in streams:
+        for st_ in streams_:
             st_.wait_event(e0)
         for k in range(n):
-            with torch.cuda.stream(streams[k % 2]):
+            with torch.cuda.stream(streams_[k % 2]):
                 flush.fill_(k & 0xFF)                  # L2 flush in front of every step, on the step's own stream
                 engine.run_device(*sets[k % 2])
-        for st_ in streams:
+        for st_ in streams_:
             cur.wait_stream(st_)
         e1.record(cur)
         e1.synchronize()
@@ -385,9 +387,9 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     dev_ms = overlapped(args.steps)
     barrier()
-    steps_timed = sum(sets[k % 2][0].n_steps for k in range(args.steps))
+    steps_timed = sum(main_sets[k % 2][0].n_steps for k in range(args.steps))
     clocks = sampler.finish()
-    del sets, streams
+    del main_sets
 
     # ---- end to end through the host-pointer C ABI: plan + H2D + kernels + D2H every step --------------------
     # N = 1: a fresh parameter block every step (other seeds of the same workload), so nothing of a plan can be reused;
@@ -551,7 +553,7 @@ def run_ours(args, rank, world, local_rank):
     north = {}
     launches_extra = 0
     if not args.no_north_star:
-        def block(name, par, n_days, n_outputs, fl, note, scaling, steps=2, warmup=1, cpu_sample=0):
+        def block(name, par, n_days, n_outputs, fl, note, scaling, steps=2, warmup=1, cpu_sample=0, overlap=True):
             nonlocal launches_extra
             t_plan = time.perf_counter()
             pl = engine.Plan(par, n_days, n_outputs, flags=fl, device=local_rank)
@@ -560,11 +562,21 @@ def run_ours(args, rank, world, local_rank):
             ms_tot, st = timer(pl, db, steps, warmup)
             status = db.status.cpu().numpy()
             bad = int(((status & (_abi.S_NONFINITE | _abi.S_UNBOUND | _abi.S_KEPLER | _abi.S_TT_OVERFLOW)) != 0).sum())
+            ms_two = 0.0
+            if overlap:      # the same passes with two in flight (two streams, two buffer sets), like the headline `value`
+                db2 = engine.DeviceBuffers(pl)
+                pair = [(pl, db), (pl, db2)]
+                if warmup:
+                    overlapped(2, pair)
+                barrier()
+                ms_two = overlapped(2 * steps, pair)
+                barrier()
+                del db2, pair
             del db
             torch.cuda.empty_cache()
-            (ms_tot, integ), (nsys, nsteps, flops, nbad) = reduce_max_sum(
-                [ms_tot, st[0]], [float(pl.B), float(pl.n_steps), float(survey_flops(pl)), float(bad)])
-            launches_extra += (2 + (1 if fl & _abi.F_LS_OC else 0)) * steps
+            (ms_tot, integ, ms_two), (nsys, nsteps, flops, nbad) = reduce_max_sum(
+                [ms_tot, st[0], ms_two], [float(pl.B), float(pl.n_steps), float(survey_flops(pl)), float(bad)])
+            launches_extra += (2 + (1 if fl & _abi.F_LS_OC else 0)) * steps * (3 if overlap else 1)
             ach = survey_flops(pl) / (st[0] / steps * 1e-3) * 1e-12       # this rank's kernel against this rank's peak
             entry = {
                 "workload": note, "systems": nsys, "n_planets": pl.Np, "n_days": n_days, "n_outputs": n_outputs, "scaling": scaling,
@@ -576,6 +588,12 @@ def run_ours(args, rank, world, local_rank):
                              "flops_per_system_step": f_step(pl.Np), "launch_ms_rank0": st[0] / steps},
                 "systems_broken_or_overflowing": nbad, "host_plan_s_rank0": t_plan,
             }
+            if overlap and ms_two > 0:
+                rate = 2 * steps / (ms_two * 1e-3)
+                entry["two_in_flight"] = {
+                    "passes_timed": 2 * steps, "ms_per_pass": ms_two / (2 * steps), "system_steps_per_s": nsteps * rate, "sims_per_s": nsys * rate,
+                    "roofline_frac": flops * rate * 1e-12 / (fp64_peak * world),
+                    "note": "two passes in flight on two streams (the next pass fills the tail of the current launch); frac = SURVEY 8(d) FLOPs of the passes / elapsed time of the region (k_fit and k_ls_oc inside) / measured FP64 peak"}
             if cpu_sample and rank == 0 and world == 1 and not args.no_cpu:
                 dt, nt, _ = cpu_path(par[:cpu_sample], n_days, n_outputs, fl)
                 entry["cpu_port"] = {"sims_per_s": cpu_sample / dt, "system_steps_per_s": cpu_sample * (n_outputs - 1) / dt, "cores": nt,
@@ -669,7 +687,8 @@ def run_ours(args, rank, world, local_rank):
 
 
 def extra_blocks(args, local_rank):
-    """Two more end-to-end figures of BASELINE configs on the public API, beside the CPU port (N = 1 only):
+    """Three more end-to-end figures of BASELINE configs on the public API, beside the CPU port (N = 1 only; C4 — the TTV
+    grid of simulations/simulation_grid.py at full size through grid.simulation_grid — is the third):
     C3 — the nested-sampling likelihood batch (nbody/nested.py:85-95): loglike/s through nested.NestedLikelihood
          .loglike_batch, i.e. planning + H2D + forward model at 30-min cadence + ephemeris + chi^2 on the device +
          D2H of loglike[B] per call;
@@ -742,6 +761,47 @@ def extra_blocks(args, local_rank):
         entry["cpu_port"] = {"simulations_per_s": len(par) / dtc, "draws_per_s": len(par) / dtc / (1.0 / max(acc, 1e-9) + 6.0), "cores": nt,
                              "sample": "4 candidate draws x 7 simulations, oracle on %d host threads, %.1f s; draws/s = simulations/s / (1 / acceptance + 6)" % (nt, dtc)}
     out["training_set_generator"] = entry
+    # ---- C4: the reference's TTV grid at full size -----------------------------------------------------------------
+    from nbody_ai_b200 import grid
+    npts = args.c4_npts
+    objs = workloads.c4_objects()
+    mass_grid, period_grid = workloads.c4_grids(npts)
+    grid.simulation_grid(objs, mass_grid[:8, :8], period_grid[:8, :8], epochs=500, n_order=4, device=local_rank)      # warm-up
+    t0 = time.perf_counter()
+    g = grid.simulation_grid(objs, mass_grid, period_grid, epochs=500, n_order=4, device=local_rank)
+    dt4 = time.perf_counter() - t0
+    amp = g["ttv_grid"] * 1440
+    entry = {"workload": "BASELINE config 4: simulations/simulation_grid.py:88-153 — %d x %d cells (perturber mass 0.5-325 Mearth x period ratio 1.41-2.41 around a 10 Mearth planet at 1.42 d, 1 Msun), 500 epochs @ 30 min (34 080 outputs); per cell: transit times, O-C, exact periodogram, find_peaks, harmonic least squares, softmax amplitude, RV semi-amplitude" % (npts, npts),
+             "api": "grid.simulation_grid (one nbt_run + one nbt_grid_post for the whole grid, host buffers)",
+             "seconds": dt4, "cells_per_s": npts * npts / dt4, "ttv_amplitude_min_max_minutes": [float(np.nanmin(amp)), float(np.nanmax(amp))],
+             "cells_with_a_peak": int((g["per_epoch_grid"][0] > 0).sum())}
+    if not args.no_cpu:
+        from scipy.signal import find_peaks
+        sel = np.linspace(0, npts * npts - 1, 48).astype(int)
+        par, meta = workloads.c4_params(npts)
+        plan = HostPlan(par[sel], meta["ndays"], meta["noutputs"], _abi.F_PLANET1_ONLY)
+        from nbody_ai_b200 import engine
+        buf = engine.Buffers(plan)
+        nt = oracle.max_threads()
+        t0 = time.perf_counter()
+        oracle.run(plan.cfg, plan.params, buf, n_threads=nt)
+        for b in range(len(sel)):      # the post-processing of generate_sim (:33-69) with the reference's own calls
+            Tc = buf.tt_of(b, 0)
+            n = len(Tc)
+            if n < 3:
+                continue
+            orbit = np.arange(n)
+            t0_, per = np.linalg.lstsq(np.vstack([np.ones(n), orbit]).T, Tc, rcond=None)[0]
+            ttv = Tc - per * orbit - t0_
+            freq, power = oracle.lomb_scargle(orbit.astype(float), ttv, 1. / (1.5 * 500), 1. / 2.1, 20)
+            pk, am = find_peaks(power, height=0.05)
+            pk = pk[np.argsort(am['peak_heights'])[::-1]][:4]
+            basis = [np.ones(n), orbit] + [f(2 * np.pi * orbit * freq[k]) for k in pk for f in (np.sin, np.cos)]
+            np.linalg.lstsq(np.vstack(basis).T, Tc, rcond=None)
+        dtc = time.perf_counter() - t0
+        entry["cpu_port"] = {"cells_per_s": len(sel) / dtc, "cores": nt,
+                             "sample": "48 cells spread over the grid: oracle (IAS15) on %d host threads + numpy / scipy post-processing on one, %.1f s" % (nt, dtc)}
+    out["c4_grid"] = entry
     return out
 
 
@@ -814,6 +874,7 @@ def main():
     ap.add_argument("--c3-batch", type=int, default=5000)
     ap.add_argument("--c3-calls", type=int, default=10)
     ap.add_argument("--gen-draws", type=int, default=512)
+    ap.add_argument("--c4-npts", type=int, default=256)
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     with StdoutToStderr() as OUT:
