@@ -469,11 +469,17 @@ def run_ours(args, rank, world, local_rank):
                 q.close()
             pools, gather_note = None, "unavailable on another rank: per-rank pinned buffers only"
     shared = pools is not None
-    consumed, stop_reader, reader = [0, 0], [False], None
+    consumed, stop_reader, reader, reader_error = [0, 0], [False], None, []
     if shared:
         dist.barrier()                                  # every segment exists
         if rank == 0:
             def read_all():
+                try:
+                    read_loop()
+                except BaseException as exc:            # surfaced by the wait below
+                    reader_error.append(exc)
+
+            def read_loop():
                 views = {}
                 while not stop_reader[0]:
                     idle = True
@@ -510,7 +516,10 @@ def run_ours(args, rank, world, local_rank):
     pipelined(args.steps)
     if shared:
         if rank == 0:                                   # the gather is complete when rank 0 has read every step of every rank
+            t_wait = time.perf_counter()
             while consumed[0] < world * (n_warm + args.steps):
+                if reader_error or time.perf_counter() - t_wait > 120.0:
+                    raise RuntimeError("bench.py: the shared-memory gather did not complete (%s)" % (reader_error or "timeout"))
                 time.sleep(2e-4)
         dist.barrier()
     torch.cuda.synchronize(dev)

@@ -6,7 +6,6 @@ path — find_zero/transit interpolation, TTV, maxavg, lomb_scargle — is evalu
 on the GPU through the C ABI (include/nbt.h); there is no CPU fallback, the calls raise when the
 CUDA library or a device is missing.
 """
-import copy
 import ctypes as C
 
 import numpy as np

@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from nbody_ai_b200 import _abi, engine, nested, simulation, tools, workloads
-from conftest import (TOL_OC_MIN, TOL_TT_S, assert_parity_or_chaotic, compare_products, golden, oracle_is_chaotic,
+from conftest import (TOL_OC_MIN, TOL_TT_S, assert_parity_or_chaotic, compare_products, golden,
                       parity_report)
 
 pytestmark = pytest.mark.gpu
