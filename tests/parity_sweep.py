@@ -1,7 +1,7 @@
 """Parity statistics of the CUDA path against the CPU oracle over large seeded samples of the reference priors and of
 the reference's own grid (run on the GPU box; TEST INFRASTRUCTURE, uses oracle/).  Writes a JSON summary.
 
-    python tests/parity_sweep.py [n_c2] [out.json] [n_c5] [c4_npts]
+    python tests/parity_sweep.py [n_c2] [out.json] [n_c5] [c4_npts] [n_3planet]
 
 Every system is compared — there is no a-priori cut (period ratio, Hill separation).  The only exclusion is the
 oracle self-sensitivity test (conftest.chaotic_mask): a system whose ORACLE answer moves by more than 0.01 s in a transit
@@ -154,6 +154,16 @@ def main():
         add(sweep(workloads.random_systems(n, 2, seed=1001), 365.0, 8760, "C2 priors (randomize()), 2 planets, 365 d @ 1 h", dump=out[:-5] + "_c2.npz"))
     if n5:
         add(sweep(workloads.random_systems(n5, 4, seed=1002), 1095.0, 26280, "C5 priors, 4 planets, 1095 d @ 1 h", dump=out[:-5] + "_c5.npz"))
+    n3 = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    if n3:       # the three-planet kernel at scale (the north-star system class) and the README system under random phases
+        add(sweep(workloads.random_systems(n3, 3, seed=1003), 365.0, 8760, "random 3-planet systems (priors extended outward), 365 d @ 1 h",
+                  dump=out[:-5] + "_np3.npz"))
+        rng = np.random.default_rng(1004)
+        par = workloads.c1_params(n3 // 4)
+        par[:, 1:, 5] = rng.uniform(0, 2 * np.pi, (len(par), 3))
+        par[:, 1:, 6] = rng.uniform(0, 2 * np.pi, (len(par), 3))
+        par[:, 1:, 2] = rng.uniform(0, 0.05, (len(par), 3))
+        add(sweep(par, 365.0, 8760, "README system (README.md:23-28) with random e < 0.05, omega, f per planet, 365 d @ 1 h"))
     if npts:
         par, meta = workloads.c4_params(npts)
         add(sweep(par, meta["ndays"], meta["noutputs"], "C4 reference grid %d x %d (1 Msun, 10 Mearth, ratio 1.41-2.41), %d epochs @ 30 min" % (npts, npts, meta["epochs"]),

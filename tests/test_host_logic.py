@@ -175,3 +175,26 @@ def test_bench_cpu_arm_plans_without_the_cuda_library(nbt):
     hp, lp = bench.HostPlan(par, nd, no, _abi.F_PLANET1_ONLY), engine.Plan(par, nd, no, flags=_abi.F_PLANET1_ONLY)
     assert np.array_equal(hp.tt_offsets, lp.tt_offsets) and np.array_equal(hp.n_outputs_sys, lp.n_outputs_sys)
     assert bench.f_step(2) == 579 and bench.f_step(3) == 926 and bench.f_step(4) == 1298
+
+
+def test_bench_reference_arm_line(built):
+    """`bench.py --impl reference` (the driver's CPU arm): one JSON line on stdout with the contract's keys, the same
+    `config` as the GPU arm's, and no libnbt.so in the process."""
+    import json
+    import subprocess
+    import sys
+    import bench
+    from conftest import ROOT
+    code = ("import sys, json; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--ref-sample', '8'];"
+            "import bench; bench.main(); print('LIBNBT' if 'libnbt.so' in open('/proc/self/maps').read() else 'CLEAN', file=sys.stderr)")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1 and "CLEAN" in r.stderr
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    args = type("A", (), dict(draws=10000, omegas=6))()
+    assert d["config"] == bench.base_config(args, 1) and d["value"] > 0
