@@ -126,6 +126,8 @@ def main():
             par = workloads.c2_params(40000, 6, 0)
             par = par[(par[:, 1, 1] > 2.6) & (par[:, 2, 1] / par[:, 1, 1] > 2.0)][:227328]
             timed(par, 30.0, 721, _abi.F_MEANS | _abi.F_MEAN_OMEGA, substeps=1)
+        elif c.startswith("c2d"):        # the bench workload at another size: <draws> x 7 systems
+            timed(workloads.c2_params(int(c[3:]), 6, 0), 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, reps=1)
         elif c.startswith("c2seed"):     # the bench batch of another seed (rank r of a multi-GPU run before balancing)
             timed(workloads.c2_params(10000, 6, int(c[len("c2seed"):])), 365.0, 8760, _abi.F_MEANS | _abi.F_MEAN_OMEGA | _abi.F_LS_OC, reps=1)
         elif c == "c5":
