@@ -490,7 +490,7 @@ def run_ours(args, rank, world, local_rank):
                                 v = engine.SharedHostPool.attach(seg % (r, w), ack=True)
                                 views[(r, w)] = v
                             if v["seq"] > int(v["_hdr"][2]):
-                                consumed[1] += int(v["n_tt"].sum()) + int(v["status"].shape[0]) + int(v["ls_oc_power"][-1] == v["ls_oc_power"][-1])
+                                consumed[1] += int(v["n_tt"].sum()) + int(v["status"].shape[0]) + int(v["ls_oc_power" if "ls_oc_power" in v else "ls_oc_peaks"].size > 0)
                                 engine.SharedHostPool.acknowledge(v)
                                 consumed[0] += 1
                                 idle = False
@@ -504,26 +504,34 @@ def run_ours(args, rank, world, local_rank):
 
     pipe = engine.Pipeline(depth=depth, device=local_rank, pools=pools, threads=plan_threads)
 
-    def pipelined(n):
-        futs = [pipe.submit(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=flags, on_done=publish if shared else None) for k in range(n)]
+    def pipelined(n, fl, skip):
+        futs = [pipe.submit(param_sets[k % n_sets], N_DAYS, N_OUTPUTS, flags=fl, skip=skip, on_done=publish if shared else None) for k in range(n)]
         for f in futs:
             f.result()
 
-    n_warm = max(2 * depth, n_sets)
-    pipelined(n_warm)
-    barrier()
-    t0 = time.perf_counter()
-    pipelined(args.steps)
-    if shared:
-        if rank == 0:                                   # the gather is complete when rank 0 has read every step of every rank
-            t_wait = time.perf_counter()
-            while consumed[0] < world * (n_warm + args.steps):
-                if reader_error or time.perf_counter() - t_wait > 120.0:
-                    raise RuntimeError("bench.py: the shared-memory gather did not complete (%s)" % (reader_error or "timeout"))
-                time.sleep(2e-4)
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    published = [0]
+
+    def timed_pipeline(fl, skip=()):
+        """Warm-up, then K pipelined steps; N > 1: until rank 0 has read every step of every rank (the gather)."""
+        n_warm = max(2 * depth, n_sets)
+        pipelined(n_warm, fl, skip)
+        barrier()
+        t0 = time.perf_counter()
+        pipelined(args.steps, fl, skip)
+        published[0] += n_warm + args.steps
+        if shared:
+            if rank == 0:
+                t_wait = time.perf_counter()
+                while consumed[0] < world * published[0]:
+                    if reader_error or time.perf_counter() - t_wait > 120.0:
+                        raise RuntimeError("bench.py: the shared-memory gather did not complete (%s)" % (reader_error or "timeout"))
+                    time.sleep(2e-4)
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) * 1e3
+
+    e2e_ms = timed_pipeline(flags)
+    e2e_peaks_pipe_ms = timed_pipeline(flags | _abi.F_LS_PEAKS, lean)      # the same with the periodograms reduced to peaks
     pipe.close()
     stop_reader[0] = True
     if reader is not None:
@@ -542,8 +550,8 @@ def run_ours(args, rank, world, local_rank):
     del chk, ref_run
 
     my_dev_ms, my_e2e_ms = dev_ms, e2e_seq_ms      # this rank's own times (the `ranks` table), before the max over ranks
-    (dev_ms, e2e_ms, integ_ms, e2e_peaks_ms, e2e_seq_ms, seq_ms), (sims_all, steps_all, ntt_all, steps_one) = reduce_max_sum(
-        [dev_ms, e2e_ms, stage_ms[0], e2e_peaks_ms, e2e_seq_ms, seq_ms], [float(B), float(steps_timed), float(n_tt_total), float(plan.n_steps)])
+    (dev_ms, e2e_ms, integ_ms, e2e_peaks_ms, e2e_seq_ms, seq_ms, e2e_peaks_pipe_ms), (sims_all, steps_all, ntt_all, steps_one) = reduce_max_sum(
+        [dev_ms, e2e_ms, stage_ms[0], e2e_peaks_ms, e2e_seq_ms, seq_ms, e2e_peaks_pipe_ms], [float(B), float(steps_timed), float(n_tt_total), float(plan.n_steps)])
     # per-rank view (diagnosis of the max-over-ranks figure): step time, e2e time, SM clock, power-cap flag
     mine_t = torch.tensor([my_dev_ms / args.steps, my_e2e_ms / args.steps, clocks["sm_mhz"] or 0.0,
                          1.0 if "sw_power_cap" in clocks["reasons"] else 0.0], dtype=torch.float64, device=dev)
@@ -675,7 +683,9 @@ def run_ours(args, rank, world, local_rank):
                                "note": "one step at a time: plan, nbt_run (H2D + kernels + D2H + sync), next; per-rank pinned buffers, no gather"},
             "e2e_peaks": {"value": sims_all * args.steps / (e2e_peaks_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                           "d2h_bytes_per_step": int(d2h_peaks), "ms_per_step": e2e_peaks_ms / args.steps,
-                          "note": "as e2e_sequential, with NBT_F_LS_PEAKS: each O-C periodogram reduced to its 3 highest peaks on the device, power arrays not copied back"},
+                          "note": "as e2e_sequential, with NBT_F_LS_PEAKS: each O-C periodogram reduced to its 3 highest peaks on the device, power arrays not copied back",
+                          "pipelined": {"value": sims_all * args.steps / (e2e_peaks_pipe_ms * 1e-3), "unit": "sims/s", "ms_per_step": e2e_peaks_pipe_ms / args.steps,
+                                        "note": "as e2e (steps in flight, gather for N > 1), with NBT_F_LS_PEAKS"}},
             "gpu_launches": 6 * args.steps + launches_extra,   # k_integrate, k_fit, k_ls_oc per step of the two device-timed regions (+ the north-star passes)
             "clocks": clocks,
             "ranks": {"columns": ["ms_per_step", "e2e_sequential_ms_per_step", "sm_mhz", "sw_power_cap"], "rows": per_rank},
