@@ -469,7 +469,7 @@ def run_ours(args, rank, world, local_rank):
                 q.close()
             pools, gather_note = None, "unavailable on another rank: per-rank pinned buffers only"
     shared = pools is not None
-    consumed, stop_reader, reader, reader_error = [0, 0], [False], None, []
+    consumed, stop_reader, reader, reader_error, gather_failed = [0, 0], [False], None, [], []
     if shared:
         dist.barrier()                                  # every segment exists
         if rank == 0:
@@ -528,8 +528,10 @@ def run_ours(args, rank, world, local_rank):
                 if rank == 0:
                     t_wait = time.perf_counter()
                     while consumed[0] < world * published[0]:
-                        if reader_error or time.perf_counter() - t_wait > 120.0:
-                            raise RuntimeError("bench.py: the shared-memory gather did not complete (%s)" % (reader_error or "timeout"))
+                        if reader_error or time.perf_counter() - t_wait > 60.0:      # never hang the job: report it instead
+                            gather_failed.append(str(reader_error[0]) if reader_error else "rank 0 did not see every step within 60 s")
+                            consumed[0] = world * published[0]
+                            break
                         time.sleep(2e-4)
                 dist.barrier()
             torch.cuda.synchronize(dev)
@@ -684,7 +686,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": sims_all * args.steps / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps, "steps_in_flight": depth,
                     "repeats_ms_per_step_rank0": [round(x / args.steps, 3) for x in e2e_runs], "statistic": "median of 3 repeats of K steps (max over ranks of each rank's median)",
-                    "final_host_gather": gather_note},
+                    "final_host_gather": gather_note if not gather_failed else "INCOMPLETE (%s) — %s" % (gather_failed[0], gather_note)},
             "e2e_sequential": {"value": sims_all * args.steps / (e2e_seq_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_seq_ms / args.steps,
                                "host_plan_ms_per_step_rank0": 1e3 * plan_s / args.steps,

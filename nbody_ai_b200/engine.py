@@ -401,15 +401,18 @@ class SharedHostPool(BufferPool):
         hdr[0] = len(blob)
         hdr[1] += 1                                  # after the directory and the data: a reader that sees it sees them
 
-    def wait_consumed(self, timeout=60.0):
-        """Block until the reader has acknowledged everything published so far (before the segment is reused)."""
+    def wait_consumed(self, timeout=10.0):
+        """Block until the reader has acknowledged everything published so far (before the segment is reused).  Returns
+        False if it has not within `timeout` seconds — the caller decides whether overwriting an unread step is an error
+        (a dead reader must not hang the producers)."""
         import time
         hdr = self.base[:24].view(np.int64)
         t0 = time.perf_counter()
         while hdr[2] < hdr[1]:
             if time.perf_counter() - t0 > timeout:
-                raise TimeoutError("SharedHostPool %s: reader did not acknowledge step %d" % (self.name, int(hdr[1])))
+                return False
             time.sleep(2e-4)
+        return True
 
     def close(self):
         """Unregister and unlink the segment (the mapping itself goes with the last view of it)."""
@@ -492,6 +495,7 @@ class Pipeline:
         self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
         self.jobs = [queue.Queue() for _ in range(depth)]
         self.next = 0
+        self.unacknowledged = 0      # steps of a SharedHostPool overwritten before their reader acknowledged them
         self.workers = [threading.Thread(target=self._work, args=(w,), daemon=True) for w in range(depth)]
         for t in self.workers:
             t.start()
@@ -505,7 +509,8 @@ class Pipeline:
             fut, params, n_days, n_outputs, kw, skip, on_done = job
             try:
                 if hasattr(pool, "wait_consumed"):
-                    pool.wait_consumed()
+                    if not pool.wait_consumed():
+                        self.unacknowledged += 1          # the reader is gone or stuck: overwrite rather than hang
                     pool.reset()
                 plan = Plan(params, n_days, n_outputs, device=self.device, pool=pool, threads=self.threads, **kw)
                 buf = run(plan, pool.buffers_for(plan, skip=skip), stream=stream)

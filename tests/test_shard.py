@@ -121,7 +121,7 @@ def _shared_worker(rank, world, port, q, tag):
                             first_tt[b, j] = sh["tt"][sh["tt_offsets"][q_ * 2 + j]]
                 engine.SharedHostPool.acknowledge(sh)
                 del sh
-        pool.wait_consumed()                      # the owner may reuse its segment once the reader has acknowledged
+        assert pool.wait_consumed()               # the owner may reuse its segment once the reader has acknowledged
         dist.barrier()
     if rank == 0:
         q.put({"n_tt": n_tt, "mean_a": mean_a, "first_tt": first_tt})
