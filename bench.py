@@ -527,10 +527,16 @@ def run_ours(args, rank, world, local_rank):
             if shared:
                 if rank == 0:
                     t_wait = time.perf_counter()
-                    while consumed[0] < world * published[0]:
+                    while consumed[0] < world * published[0] and not gather_failed:
                         if reader_error or time.perf_counter() - t_wait > 60.0:      # never hang the job: report it instead
                             gather_failed.append(str(reader_error[0]) if reader_error else "rank 0 did not see every step within 60 s")
                             consumed[0] = world * published[0]
+                            for r in range(world):                  # release every producer for good
+                                for w in range(depth):
+                                    try:
+                                        engine.SharedHostPool.attach(seg % (r, w), ack=True)["_hdr"][2] = 1 << 62
+                                    except Exception:
+                                        pass
                             break
                         time.sleep(2e-4)
                 dist.barrier()
