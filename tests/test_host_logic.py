@@ -198,3 +198,63 @@ def test_bench_reference_arm_line(built):
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
     args = type("A", (), dict(draws=10000, omegas=6))()
     assert d["config"] == bench.base_config(args, 1) and d["value"] > 0
+
+
+def test_fits_layout_of_the_grid(tmp_path):
+    """grid.write_fits against the layout simulations/simulation_grid.py:219-295 writes with astropy: a primary HDU
+    (TTV amplitude [min]) + three IMAGE extensions (O-C periodicity 1st / 2nd [epochs], RV amplitude [m/s]), BUNIT,
+    COMMENT, the linear axes, the objects, EXTNAME; periodicities and RV masked to NaN where the amplitude is <= 1 min
+    (:174-179); plain FITS: 2880-byte blocks of 80-character cards, big-endian doubles."""
+    from nbody_ai_b200 import grid
+    npts = 5
+    obj = workloads.c4_objects()
+    mass_grid, period_grid = workloads.c4_grids(npts)
+    obj[2]['m'], obj[2]['P'] = mass_grid[-1][-1], period_grid[-1][-1]
+    rng = np.random.default_rng(0)
+    grids = {"ttv_grid": rng.uniform(0, 3, (npts, npts)) / 1440, "per_epoch_grid": rng.uniform(2, 400, (4, npts, npts)),
+             "rv_grid": rng.uniform(1, 100, (npts, npts))}
+    k = workloads.MSUN_ASTROPY / workloads.MEARTH_ASTROPY
+    path = str(tmp_path / "ttv_grid.fits")
+    grid.write_fits(path, grids, mass_grid, period_grid, obj, k)
+    raw = open(path, "rb").read()
+    assert len(raw) % 2880 == 0 and raw[:30] == b"SIMPLE  =                    T"
+    hdus = grid.read_fits(path)
+    assert [h["EXTNAME"] for h, _ in hdus] == ["TTV_AMPLITUDE", "TTV_PERIODICITY1", "TTV_PERIODICITY2", "RV_AMPLITUDE"]
+    assert [h["BUNIT"] for h, _ in hdus] == ["minutes", "epochs", "epochs", "m/s"]
+    assert "XTENSION" not in hdus[0][0] and all(h["XTENSION"] == "IMAGE" for h, _ in hdus[1:])
+    amp = grids["ttv_grid"] * 24 * 60                      # the reference's expression (:220)
+    mask = amp > 1
+    assert np.array_equal(hdus[0][1], amp)
+    for (h, a), want in zip(hdus[1:], (grids["per_epoch_grid"][0], grids["per_epoch_grid"][1], grids["rv_grid"])):
+        assert np.array_equal(a[mask], want[mask]) and np.isnan(a[~mask]).all() and (~mask).any() and mask.any()
+    for h, a in hdus:
+        assert h["BITPIX"] == -64 and h["NAXIS"] == 2 and h["NAXIS1"] == npts and h["NAXIS2"] == npts and a.shape == (npts, npts)
+        assert h["CRPIX1"] == 1 and h["CRPIX2"] == 1
+        assert abs(h["CRVAL1"] - 0.5) < 1e-12 and abs(h["CDELT1"] - (325 - 0.5) / npts) < 1e-12          # mass axis [Mearth]
+        assert abs(h["CRVAL2"] - 1.41) < 1e-12 and abs(h["CDELT2"] - (2.41 - 1.41) / npts) < 1e-12       # period ratio
+        assert h["STARMASS"] == 1.0 and h["P1_PER"] == 1.42 and h["P1_OMEGA"] == 0.01 and abs(h["P2_OMEGA"] - np.pi / 2) < 1e-15
+        assert h["P2_MASS"] == obj[2]['m'] and h["P2_PER"] == obj[2]['P'] and h["P1_ECC"] == 0.0
+    assert hdus[0][0]["COMMENT"] == ["TTV amplitude in minutes"] and hdus[3][0]["COMMENT"] == ["Radial velocity amplitude in m/s"]
+
+
+def test_make_sin_and_weighted_periodogram_host_branches():
+    """The two off-path branches of the reference's tools that stay on the host: make_sin (nbody/tools.py:78-95) and the
+    dy-weighted floating-mean periodogram behind lomb_scargle(dy=ndarray) — against direct formulas / scipy."""
+    from scipy.signal import lombscargle
+    t = np.linspace(0, 30, 200)
+    pars = np.array([[0.2, 1.5, 0.3], [0.05, 0.7, 1.1]])
+    want = 1.5 * np.sin(t * 2 * np.pi * 0.2 + 0.3) + 0.7 * np.sin(t * 2 * np.pi * 0.05 + 1.1)
+    assert np.allclose(tools.make_sin(t, pars), want, rtol=0, atol=1e-14)
+    assert np.allclose(tools.make_sin(t, pars.ravel()), want, rtol=0, atol=1e-14)
+    assert np.allclose(tools.make_sin(t, pars[:, 1:], freqs=[0.2, 0.05]), want, rtol=0, atol=1e-14)
+    rng = np.random.default_rng(3)
+    y = want + rng.normal(0, 0.1, len(t))
+    freq = 1 / 365 + np.arange(300) / 30 / 10
+    # equal weights: the weighted form reduces to the floating-mean generalised LS that scipy computes
+    p = tools._weighted_ls_host(t, y, np.full(len(t), 0.1), freq)
+    ps = lombscargle(t, y, 2 * np.pi * freq, floating_mean=True, normalize=True)
+    assert np.abs(p - ps).max() < 1e-10 and abs(freq[np.argmax(p)] - 0.2) < 0.01
+    # unequal weights change it, and down-weighting the noisy half moves it towards the clean signal's periodogram
+    dy = np.where(np.arange(len(t)) % 2 == 0, 0.05, 5.0)
+    pw = tools._weighted_ls_host(t, y, dy, freq)
+    assert np.abs(pw - p).max() > 1e-3 and abs(freq[np.argmax(pw)] - 0.2) < 0.01
