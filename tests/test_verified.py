@@ -83,3 +83,44 @@ def test_splice_roundtrip():
         assert np.array_equal(b.rv[:, r], a.rv[:, r])
     untouched = np.setdiff1d(np.arange(40), rows)
     assert not b.status[untouched].any() and not b.rv[:, untouched].any()
+
+
+def test_training_set_generator_on_the_host_build(hostsim, monkeypatch):
+    """dataset.generate_training_set (simulations/generate_simulations.py:41-110) with the host build of the device
+    integrator standing in for nbt_run: one launch per block on per-system grids, the rejection rule applied to the
+    results, the [X, y] layout, resume from an existing set."""
+    from nbody_ai_b200 import dataset
+
+    def host_with_amplitude(plan, buffers=None, stream=None):
+        buf = host_run(hostsim, plan)
+        for b in range(plan.B):                        # k_fit's maxavg(ttv) (tools.py:22), with the oracle's
+            n = buf.n_transits(b, 0)
+            if n >= 3:
+                off = int(plan.tt_offsets[b * plan.Np])
+                buf.ttv_max[b * plan.Np] = oracle.maxavg(buf.ttv[off:off + n])
+        return buf
+
+    monkeypatch.setattr(engine, "run", host_with_amplitude)
+    st = {}
+    X, y = dataset.generate_training_set(samples=5, omegas=2, periods=30, rng=np.random.default_rng(3), stats=st)
+    assert len(X) == len(y) == 15 and st["launches"] >= 1 and st["simulations"] == 3 * st["candidates"]
+    assert all(len(r) == 7 for r in X) and all(len(t) == 30 for t in y)
+    for g in range(0, 15, 3):                          # a draw and its omega variants share everything but omega_2
+        assert X[g][:5] == X[g + 1][:5] == X[g + 2][:5] and X[g][6] == X[g + 1][6] and len({X[g][5], X[g + 1][5], X[g + 2][5]}) == 3
+        P1 = X[g][1]
+        assert np.all(np.diff(y[g]) > 0.9 * P1) and np.all(np.diff(y[g]) < 1.1 * P1) and y[g][0] < 1.05 * P1
+    # the accepted draws pass the reference's rule in the oracle too
+    par = np.zeros((5, 3, 7))
+    for i, g in enumerate(range(0, 15, 3)):
+        r = X[g]
+        par[i, 0, 0], par[i, 1, 1], par[i, 2, 1], par[i, 2, 5], par[i, 2, 2] = r[0], r[1], r[3], r[5], r[6]
+        par[i, 1, 0], par[i, 2, 0] = r[2] * dataset.mearth / dataset.msun, r[4] * dataset.mearth / dataset.msun
+        par[i, 1:, 3] = np.pi / 2
+    nd, no = dataset.grids(par, 30)
+    want = oracle_run(engine.Plan(par, nd, no, flags=_abi.F_PLANET1_ONLY))
+    for i in range(5):
+        assert want.n_tt[2 * i] >= 30 and want.ttv_max[2 * i] * 1440 <= 180
+        assert np.abs(want.tt_of(i, 0)[:30] - y[3 * i]).max() * 86400 < 1.0
+    # resume: an existing set is continued, not redrawn
+    X2, y2 = dataset.generate_training_set(samples=7, omegas=2, periods=30, rng=np.random.default_rng(4), X=list(X), y=list(y))
+    assert len(X2) == 21 and X2[:15] == X
